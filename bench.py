@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Headline benchmark of the batched closed-loop flight path (BASELINE.json metric: drone-sim-steps/s).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...          # the reference-style CPU path (oracle port) on the host cores
+
+Workload (config.workload): BASELINE.json configs[2] -- 10^5 lab_course rollouts per GPU with
+Monte-Carlo PID gains and mass/inertia perturbations, velocity 3.0 (config.ini) => 10 760 ticks each,
+1.076e9 drone-sim-steps per GPU and step.  One "step" = one pass of the hot path over the batch:
+min-snap solve of the mission (K1, take-off + course tables), table geometry, persistent rollout
+(K2) of every drone over the whole mission, metrics written.  Weak scaling: every rank flies its own
+10^5 rollouts (Monte-Carlo inputs keyed by the global rollout index) and the per-rollout metrics are
+all-gathered over NCCL inside the timed region.
+
+`value`  : steps/s with inputs resident in HBM (CUDA events around the K timed steps, max over ranks).
+`e2e`    : same metric through the public API with HOST buffers: per step the Monte-Carlo arrays and the
+           waypoints are copied from pinned host memory, the metrics are copied back.
+`roofline`: K2 is FP32-issue bound (no dense contraction => no tensor path, ~0 HBM bytes per tick in
+           metrics-only mode); `achieved` = 306 algorithmic flop/tick x ticks / K2 time,
+           `peak` = FP32 FMA rate measured in this run by uavb_measure_fma_peak.  `roofline_log` is the
+           HBM roofline of the full-rate state-log mode (52 B/tick) against MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_TICK = 306          # algorithmic fp32-equivalent flop per drone tick with 4 AABBs (DESIGN.md "K2 work per tick")
+LOG_BYTES_PER_TICK = 52      # 13 fp32 state words
+ROLLOUTS_PER_GPU = 100_000   # BASELINE configs[2]
+VELOCITY = 3.0               # config.ini:7
+FREQUENCY = 10               # config.ini:2
+METRIC = "drone-sim-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rollouts", type=int, default=ROLLOUTS_PER_GPU, help="rollouts per GPU (default: BASELINE configs[2])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the solves/s and log-mode side measurements")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall-clock budget of the CPU baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+_TABLE_CACHE = {}
+
+
+def lab_course_table(velocity):
+    """(table, waypoints, obstacles) of the lab_course mission from the oracle planner (cached per process)."""
+    if velocity not in _TABLE_CACHE:
+        from oracle import minsnap_np
+        from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES, LAB_COURSE_WAYPOINTS
+        tab = minsnap_np.mission_table(LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES, velocity, 0.01)
+        _TABLE_CACHE[velocity] = (tab, LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES)
+    return _TABLE_CACHE[velocity]
+
+
+def _cpu_worker(job):
+    """Fly `ticks` ticks of a Monte-Carlo-perturbed lab_course mission with the NumPy oracle port."""
+    seed, ticks = job
+    import numpy as np
+    from oracle import flight_np
+    rng = np.random.default_rng(seed)
+    veh = flight_np.Vehicle().perturbed(rng.uniform(0.8, 1.2, 11), rng.uniform(0.9, 1.1), rng.uniform(0.9, 1.1, 3))
+    tab, wp, obs = lab_course_table(VELOCITY)
+    t0 = time.perf_counter()
+    flight_np.closed_loop(veh, tab, wp[0], obstacles=obs, goal=wp[-1], n_ticks=ticks)
+    return ticks, time.perf_counter() - t0
+
+
+def cpu_rollout_rate(seconds: float, cores: int | None = None):
+    """Whole-machine rate of the oracle port (the reference's Python/NumPy style: one drone per
+    process, small-array NumPy calls per tick) on a bounded sample of the same workload."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        ticks_probe = 400
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(i, ticks_probe) for i in range(cores)])       # also warms imports and the table
+        per_core = ticks_probe / max(time.perf_counter() - t0, 1e-6)
+        ticks = max(1000, int(per_core * seconds * 0.8))
+        ticks = min(ticks, FREQUENCY * 1076)
+        t0 = time.perf_counter()
+        done = pool.map(_cpu_worker, [(1000 + i, ticks) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    total = sum(d[0] for d in done)
+    return total / wall, cores, f"{cores} processes x {ticks} ticks of Monte-Carlo lab_course rollouts (v={VELOCITY}), oracle/flight_np.py"
+
+
+def run_reference(args):
+    """--impl reference: the reference-style CPU implementation (oracle port; the reference itself is
+    Python + MuJoCo and cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_rollout_rate(per_step)
+        if i >= args.warmup:
+            vals.append(v)
+    value = statistics.mean(vals)
+    ms = 1e3 * ROLLOUTS_PER_GPU * FREQUENCY * 1076 / value
+    line = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": workload_name(args.rollouts), "note": "bounded sample per step; ms_per_step extrapolated to the full batch"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(rollouts):
+    return (f"BASELINE configs[2]: {rollouts} lab_course rollouts per GPU, Monte-Carlo gains x U(0.8,1.2), mass/inertia x U(0.9,1.1), "
+            f"v={VELOCITY} m/s, 10760 ticks each, 4 AABBs, metrics only")
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/uavb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in open(self.path):
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "power_w_max": max(power),
+                "samples": len(sm)}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from uav_ac_b200 import _native as nat, kernels, sharding
+    from uav_ac_b200.simulation.scene import LAB_COURSE_GOAL, LAB_COURSE_OBSTACLES, LAB_COURSE_START, LAB_COURSE_WAYPOINTS
+
+    rank, local, world = sharding.init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nat.lib()
+    B = args.rollouts
+    total = B * world
+    begin, end = sharding.shard_range(total, rank, world)
+    assert end - begin == B
+
+    # ---- host inputs (pinned): waypoints, velocity, Monte-Carlo scales as a user would hand them over
+    veh = nat.default_vehicle()
+    base = np.array(list(veh.gains) + [veh.mass] + list(veh.inertia), dtype=np.float32)
+    lo, hi = [0.8] * 11 + [0.9] * 4, [1.2] * 11 + [1.1] * 4
+    scales = kernels.mc_uniform(20261017, B, lo, hi, index_base=begin, device=dev)          # keyed by the global rollout index
+    mc_dev = (scales * torch.tensor(base, device=dev)[:, None]).contiguous()                # [15, B] fp32: 11 gains, mass, 3 inertia
+    mc_host = mc_dev.cpu().pin_memory()
+    wp_host = torch.tensor(LAB_COURSE_WAYPOINTS, dtype=torch.float64).pin_memory()
+    vel_host = torch.tensor([VELOCITY], dtype=torch.float64).pin_memory()
+    obs = torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=dev)
+    start = torch.tensor(LAB_COURSE_START, dtype=torch.float64, device=dev)
+    goal = torch.tensor(LAB_COURSE_GOAL, dtype=torch.float64, device=dev)
+    metrics_host = torch.empty((B, nat.N_METRICS), dtype=torch.float32).pin_memory()
+    wp_dev = wp_host.to(dev)
+    vel_dev = vel_host.to(dev)
+    result = kernels.RolloutResult(torch.empty((B, nat.N_METRICS), dtype=torch.float32, device=dev), None, None, None)
+    n_ticks_holder = {}
+
+    def hot_path(wp, vel, mc):
+        """K1 (two tables) + table geometry + K2 over the shard; returns the per-rollout metrics."""
+        plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True)
+        n_ticks = n_ticks_holder.get("n")
+        if n_ticks is None:                                  # mission length is data dependent: read it once, outside the timed steps
+            n_ticks = n_ticks_holder["n"] = FREQUENCY * int(plan.total_rows.item())
+        kernels.rollout(plan, B, n_ticks, start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc[:11], mc_mass=mc[11],
+                        mc_inertia=mc[12:15], obstacles=obs, want_state=False, out=result, index_base=begin)
+        return result.metrics
+
+    def step_device():
+        m = hot_path(wp_dev, vel_dev, mc_dev)
+        return sharding.gather_metrics(m, total) if world > 1 else m
+
+    def step_e2e():
+        wp = wp_host.to(dev, non_blocking=True)
+        vel = vel_host.to(dev, non_blocking=True)
+        mc = mc_host.to(dev, non_blocking=True)
+        m = hot_path(wp, vel, mc)
+        if world > 1:
+            m = sharding.gather_metrics(m, total)
+            m = m[begin:end]
+        metrics_host.copy_(m, non_blocking=True)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)                    # > 126 MB L2
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s in range(steps):
+            flush.fill_(s & 0xFF)                                                           # flush L2 between timed iterations
+            ev[s][0].record()
+            fn()
+            ev[s][1].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks
+
+    W = max(args.warmup, 3)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, clocks = timed(step_device, args.steps, W, sampler)
+    n_ticks = n_ticks_holder["n"]
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    torch.cuda.synchronize()
+    sim_steps = float(total) * n_ticks                                                       # whole job, one step
+    value = sim_steps * args.steps / (ms_dev * 1e-3)
+    e2e = sim_steps * args.steps / (ms_e2e * 1e-3)
+
+    # ---- K2 alone: average launch duration with events on the launching stream
+    plan = kernels.plan_missions([(wp_dev[None, :2].contiguous(), vel_dev), (wp_dev[None, 1:].contiguous(), vel_dev)], FREQUENCY * veh.dt, shared=True)
+    kw = dict(start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc_dev[:11], mc_mass=mc_dev[11], mc_inertia=mc_dev[12:15],
+              obstacles=obs, want_state=False, out=result)
+    k2 = []
+    for i in range(2 + args.steps):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); kernels.rollout(plan, B, n_ticks, **kw); b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            k2.append(a.elapsed_time(b))
+    k2_ms = statistics.mean(k2)
+    summary = sharding.summarize(result.metrics)
+
+    line = None
+    if rank == 0:
+        fp32_peak, fp64_peak = nat.measure_fma_peak(local)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        achieved = FLOP_PER_TICK * float(B) * n_ticks / (k2_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(B), "rollouts_per_gpu": B, "ticks_per_rollout": n_ticks, "frequency": FREQUENCY,
+                       "l2": "256 MB buffer written between timed iterations (L2 flush)", "fp64_parts": "K1 solve and 100 Hz set-point evaluation"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(mc_host.numel() * 4 + wp_host.numel() * 8 + 8),
+                    "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": 5 * args.steps,        # per step: 2x minsnap_solve, 2x table_meta, 1x rollout (torch glue kernels not counted)
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+                         "traffic": None, "kernel": "rollout_kernel<float,false>", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,
+                         "peak_source": "uavb_measure_fma_peak in this run (MEASURED_PEAKS.json carries no fp32 figure)",
+                         "fp64_peak_tflops": fp64_peak, "ticks_per_s_k2": float(B) * n_ticks / (k2_ms * 1e-3)},
+            "mission_report": summary,
+        }
+        if not args.no_extras:
+            line["roofline_log"] = log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush)
+            line["solves"] = solve_rate(kernels, dev, flush, peaks)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, sample = cpu_rollout_rate(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush):
+    """Full-rate state log (52 B/tick): HBM roofline of the logging epilogue (north_star)."""
+    import torch
+    Bl = 16384
+    ticks = 4000                                          # 16384 x 4000 x 52 B = 3.4 GB of log per launch
+    kw = dict(kw)
+    for k in ("mc_gains", "mc_mass", "mc_inertia"):
+        kw[k] = kw[k][..., :Bl].contiguous()
+    kw["out"] = None
+    kw["want_metrics"] = False
+    log = torch.empty((ticks, 13, Bl), dtype=torch.float32, device=dev)
+    res = kernels.RolloutResult(None, None, log, None)
+    kw["out"] = res
+    ms = []
+    for i in range(4):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); kernels.rollout(plan, Bl, ticks, log_stride=1, **kw); b.record()
+        torch.cuda.synchronize()
+        if i >= 1:
+            ms.append(a.elapsed_time(b))
+    t = statistics.mean(ms) * 1e-3
+    gbs = LOG_BYTES_PER_TICK * float(Bl) * ticks / t / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+            "kernel": "rollout_kernel<float,true>", "kernel_ms": t * 1e3, "ticks_per_s": float(Bl) * ticks / t,
+            "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+            "note": "rollouts x ticks x 52 B of state log per launch; the kernel stays FP32-issue bound, so this fraction is the HBM share the log uses"}
+
+
+def solve_rate(kernels, dev, flush, peaks):
+    """BASELINE configs[1]: 10^6 random 5-waypoint missions, K1 only (second half of the headline metric)."""
+    import torch
+    Bm = 1_000_000
+    wp, vel = kernels.mc_missions(99, Bm, 4, device=dev)
+    ms = []
+    for i in range(6):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); kernels.minsnap_solve(wp, vel); b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(a.elapsed_time(b))
+    t = statistics.mean(ms) * 1e-3
+    byts = 928.0 * Bm                                      # 128 B in + 800 B out per solve
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"metric": "min-snap solves/s", "value": Bm / t, "unit": "solves/s", "missions": Bm, "splines": 4, "kernel_ms": t * 1e3,
+            "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peak, "unit": "GB/s", "frac": byts / t / 1e9 / peak,
+                         "traffic": None, "kernel": "minsnap_solve_kernel<4,true>", "note": "includes output allocation by torch (cached allocator)"}}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

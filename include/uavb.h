@@ -1,0 +1,267 @@
+/*
+ * uavb.h -- C ABI of the B200-native batched closed-loop flight path (libuavb.so).
+ *
+ * The reference (Mdhvince/UAV-Autonomous-control) is pure Python and has no FFI; the seams this
+ * library replaces are plain Python calls between objects.  Every entry point
+ * below names the reference interface it stands in for (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - return 0 on success, a negative UAVB_E* code otherwise; uavb_last_error() returns a
+ *     thread-local message for the last failing call on this thread.
+ *   - unless the name ends in _host, every pointer is a DEVICE pointer owned by the caller, the
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default stream) and the
+ *     call returns without synchronising.  No hidden global state: calls on different streams or
+ *     threads do not interact.
+ *   - *_host entry points take HOST pointers, copy host->device, launch, copy device->host and
+ *     synchronise before returning (the end-to-end path a ctypes / cgo style binding would use).
+ *   - there is NO CPU implementation behind this ABI: on a machine without a CUDA device every
+ *     compute entry point fails with UAVB_ENODEVICE.
+ *   - frames: NED world / FRD body, scalar-first quaternion, state X = [x y z  q0 q1 q2 q3
+ *     vx vy vz  p q r] exactly as uav_ac/quadrotor/quad.py:75-80.
+ */
+#ifndef UAVB_H
+#define UAVB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVB_VERSION 100            /* 0.1.0 */
+
+#define UAVB_OK          0
+#define UAVB_EINVAL     -1          /* bad argument (null pointer, size out of range) */
+#define UAVB_ECUDA      -2          /* CUDA runtime error, see uavb_last_error() */
+#define UAVB_ENODEVICE  -3          /* no CUDA device / wrong architecture */
+#define UAVB_ENOMEM     -4
+
+#define UAVB_N_COEFFS    8          /* coefficients per spline and axis: minimum_snap.py:28 */
+#define UAVB_STATE_DIM  13          /* quad.py:75-80 */
+#define UAVB_N_GAINS    11          /* kp_xy kd_xy kp_z kd_z ki_z kp_roll kp_pitch kp_yaw kp_p kp_q kp_r (quad.py:65-73) */
+#define UAVB_N_METRICS   8
+#define UAVB_CARRY_WORDS 48         /* 32-bit words per rollout in the resumable carry block */
+#define UAVB_MAX_SPLINES 64         /* upper bound on splines per mission accepted by the solver */
+
+/* per-mission solver status (status_out of uavb_minsnap_solve_f64) */
+#define UAVB_SOLVE_OK        0
+#define UAVB_SOLVE_DEGENERATE 1     /* a segment has zero length (T_i = 0) or velocity <= 0: KKT singular
+                                       (np.linalg.solve would raise LinAlgError, minimum_snap.py:151) */
+#define UAVB_SOLVE_NONFINITE 2      /* non-finite input or result */
+
+/* per-rollout status bits (metrics column 5 and status_out of uavb_rollout_f32) */
+#define UAVB_ROLLOUT_OK        0
+#define UAVB_ROLLOUT_NONFINITE 1    /* state became NaN/Inf (the reference has no guard: controller.py:50,150,167) */
+#define UAVB_ROLLOUT_DIVERGED  2    /* |position| left the 1e4 m sanity ball */
+
+/* metrics_out columns */
+#define UAVB_M_FINAL_DIST 0         /* |p - goal| after the last tick            (main.py:115)            */
+#define UAVB_M_COLLISION  1         /* 1.0 if the body origin was ever inside an AABB (minimum_snap.py:327-357) */
+#define UAVB_M_RMSE       2         /* sqrt(mean e^2), e = per-outer-period tracking error                */
+#define UAVB_M_MEAN_ERR   3         /* mean e (tests/integration/test_mujoco_trajectory_tracking.py:31,35) */
+#define UAVB_M_MAX_ERR    4
+#define UAVB_M_STATUS     5         /* UAVB_ROLLOUT_* bits as a float                                     */
+#define UAVB_M_FIRST_HIT  6         /* tick index of the first AABB hit, -1 if none                       */
+#define UAVB_M_PERIODS    7         /* number of outer periods that contributed to the error statistics  */
+
+int         uavb_version(void);
+const char* uavb_last_error(void);
+/* Number of visible CUDA devices (0 on a GPU-less host; never fails). */
+int         uavb_device_count(void);
+/* SM count and compute capability of device `dev`; UAVB_ENODEVICE without a GPU. */
+int         uavb_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  minimum-snap solve, fp64, one thread per mission.
+ *
+ * Replaces MinimumSnap._compute_spline_parameters (uav_ac/planning/minimum_snap.py:138-153) together
+ * with _generate_time_per_spline (:311-321) for B missions at once.  The unique solution of the
+ * reference's KKT system [[Q,A^T],[A,0]] (rows listed at :171-255, Q at :155-169) is computed from
+ * its reduced form: the free unknowns are velocity/acceleration/jerk at the S-1 interior waypoints,
+ * the stationarity conditions form an SPD block-tridiagonal system with 3x3 blocks that is solved
+ * in registers, and the 8 coefficients of every spline follow in closed form (DESIGN.md "K1").
+ *
+ *   waypoints  [B][S+1][3]  row-major, NED metres
+ *   velocity   [B]          cruise speed of each mission (minimum_snap.py:13 `velocity`)
+ *   start_end_time_factor   MinimumSnap.START_END_TIME_FACTOR (1.5, minimum_snap.py:10)
+ *   coeffs_out [B][8*S][3]  row 8*i+j = coefficient of t^j of spline i -- the layout of the
+ *                           reference attribute MinimumSnap.coeffs (minimum_snap.py:153)
+ *   times_out  [B][S]       MinimumSnap.times
+ *   status_out [B]          UAVB_SOLVE_*; may be NULL
+ * 1 <= S <= UAVB_MAX_SPLINES.
+ */
+int uavb_minsnap_solve_f64(const double* waypoints, const double* velocity, int B, int S,
+                           double start_end_time_factor, double* coeffs_out, double* times_out,
+                           int* status_out, void* stream);
+
+/* Ragged variant: mission b owns waypoints [wp_offsets[b], wp_offsets[b+1]) of the packed array and
+ * S_b = wp_offsets[b+1]-wp_offsets[b]-1 splines; its first spline is packed segment
+ * wp_offsets[b]-b.  coeffs_out [n_seg][8][3], times_out [n_seg], n_seg = wp_offsets[B]-B.
+ * Used by the obstacle-correction loop (minimum_snap.py:63-95) where midpoint insertion makes S
+ * differ between missions. */
+int uavb_minsnap_solve_ragged_f64(const double* waypoints, const int* wp_offsets, const double* velocity,
+                                  int B, double start_end_time_factor, double* coeffs_out,
+                                  double* times_out, int* status_out, void* stream);
+
+/* Table geometry of MinimumSnap._generate_trajectory (minimum_snap.py:97-124) without sampling it:
+ *   rows_out  [n_seg]  len(np.arange(0, T_i, dt)) of every packed segment (:104)
+ *   yaw0_out  [B]      yaw taken by the rows that precede the first row with horizontal speed
+ *                      >= 1e-3 (the look-ahead of _calculate_yaws, :126-136); 0 when no row is valid
+ *   total_rows_out [B] rows of the whole table of mission b; may be NULL
+ * seg_offsets [B+1] gives the packed segment range of every mission. */
+int uavb_minsnap_table_meta_f64(const double* coeffs, const double* times, const int* seg_offsets, int B,
+                                double dt, int* rows_out, double* yaw0_out, int* total_rows_out, void* stream);
+
+/* K3  sampled table, the (N, 11) array returned by MinimumSnap.get_trajectory()
+ * (minimum_snap.py:59-61, 97-124): [x y z  vx vy vz  ax ay az  yaw  spline_id].
+ *   row_offsets [B+1]  exclusive prefix sum of total rows per mission (from uavb_minsnap_table_meta_f64)
+ *   table_out   [row_offsets[B]][11]
+ * Yaw uses hold-last-valid and np.unwrap semantics per mission (:126-136). */
+int uavb_minsnap_sample_f64(const double* coeffs, const double* times, const int* seg_offsets,
+                            const int* seg_rows, const int* row_offsets, int B, double dt,
+                            double* table_out, void* stream);
+
+/* Inclusive point-in-AABB over sampled tables, the test of the correction loop
+ * (minimum_snap.py:84-87 with is_collision_cuboid :327-357).  For every mission b, ORs into
+ * hit_mask_out[b] (uint64, bit s) the splines s that have a sampled row inside `cuboid` (6 doubles,
+ * [xmin xmax ymin ymax zmin zmax]).  cuboid_stride = 0: one cuboid for all missions, 6: one each. */
+int uavb_minsnap_table_hits_f64(const double* table, const int* row_offsets, int B, const double* cuboid,
+                                int cuboid_stride, unsigned long long* hit_mask_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  persistent closed-loop rollout, fp32 state in registers, one thread per drone.
+ */
+typedef struct uavb_vehicle {
+  /* Quad.__init__ arguments (uav_ac/quadrotor/quad.py:11-51) and lab_course.xml constants */
+  double g, dt;                                   /* gravity, inner (physics) time step             */
+  double mass, inertia[3];
+  double arm, kf, kappa;                          /* lever arm, force coefficient, drag-to-thrust   */
+  double min_thrust, max_thrust;                  /* per rotor                                      */
+  double tau_rise, tau_fall;                      /* motor time constants                           */
+  double max_ascent, max_descent, max_speed_xy, max_horiz_accel, max_tilt;   /* flight limits       */
+  double gains[UAVB_N_GAINS];                     /* order of UAVB_N_GAINS above (quad.py:65-73)    */
+  double integral_limit;                          /* CascadedController.INTEGRAL_ERROR_LIMIT (controller.py:10) */
+} uavb_vehicle;
+
+typedef struct uavb_rollout_args {
+  int B;                      /* rollouts in this launch                                            */
+  int n_ticks;                /* inner ticks to advance (every rollout the same number)             */
+  int inner_per_outer;        /* config.ini `frequency` (main.py:39): outer loop every N ticks      */
+  int thrust_frame_lag;       /* 1 = headless loop (stale data.xmat), 0 = viewer path   */
+  int resume;                 /* 0: initialise from `start`; 1: continue from `carry`               */
+  int log_stride;             /* 0 = no state log; else one sample after every log_stride ticks     */
+  int n_obs;                  /* AABBs per obstacle set                                              */
+  int n_obs_sets;             /* number of obstacle sets in `aabbs` (>= 1 when n_obs > 0)            */
+  long long index_base;       /* global index of rollout 0 of this launch (sharding; informational) */
+
+  uavb_vehicle veh;           /* defaults for every rollout                                          */
+
+  /* optional per-rollout Monte-Carlo overrides, SoA, NULL = use veh.* (BASELINE configs[2..3]) */
+  const float* mc_mass;       /* [B]                                                                 */
+  const float* mc_inertia;    /* [3][B]                                                              */
+  const float* mc_gains;      /* [UAVB_N_GAINS][B]                                                   */
+  const float* mc_wind;       /* [3][B] constant world-frame force in N (extension, not in reference) */
+
+  /* mission: packed segments in the reference coefficient layout (MinimumSnap.coeffs rows) */
+  const double* seg_coeffs;   /* [n_seg][8][3]                                                       */
+  const int*    seg_rows;     /* [n_seg] table rows of each segment (uavb_minsnap_table_meta_f64)     */
+  const int*    seg_table;    /* [n_seg] 1 where a new MinimumSnap table starts (yaw hold restarts:
+                                  main.py:80-84 stitches two independent tables), else 0              */
+  const double* seg_yaw0;     /* [n_seg] yaw0 of the table that starts at this segment (else unused)  */
+  const int*    mission_seg_begin;  /* [B] first packed segment of each rollout, NULL = 0 for all     */
+  const int*    mission_seg_count;  /* [B] segments of each rollout, NULL = n_seg_shared for all      */
+  int           n_seg_shared;
+  double        dt_outer;     /* table sampling period, quad.dt * frequency (main.py:97)             */
+
+  const double* start;        /* initial position, [3] (start_stride 0) or [B][3] (start_stride 3)    */
+  int           start_stride;
+  const double* goal;         /* goal for final_dist, same striding; NULL = no final_dist (0)         */
+  int           goal_stride;
+
+  const float*  aabbs;        /* [n_obs_sets][n_obs][6] = [xmin xmax ymin ymax zmin zmax]              */
+  const int*    aabb_set;     /* [B] obstacle set of each rollout, NULL = set 0                        */
+
+  float*        carry;        /* [UAVB_CARRY_WORDS][B] resumable rollout state (in when resume, always out); may be NULL when resume = 0 */
+  float*        state_out;    /* [13][B] final X, SoA; may be NULL                                     */
+  float*        metrics_out;  /* [B][UAVB_N_METRICS]; may be NULL                                      */
+  float*        log_out;      /* [n_ticks / log_stride][13][B] SoA samples; required iff log_stride > 0 */
+} uavb_rollout_args;
+
+/* Replaces, for B drones and n_ticks ticks, the loop
+ *     trajectory_controller.step(); simulation.step()
+ * of tests/integration/test_mujoco_trajectory_tracking.py:27-31, i.e. TrajectoryController.step
+ * (uav_ac/main.py:37-61), CascadedController.{altitude,lateral,reduced_attitude,body_rate_controller}
+ * (uav_ac/control/controller.py:26-168), Quad.set_propeller_speed/_allocate_rotor_forces
+ * (uav_ac/quadrotor/quad.py:88-122), MujocoSimulation.step (uav_ac/simulation/mujoco_sim.py:144-151,
+ * restated as a free rigid body) and the table rows of MinimumSnap._generate_trajectory
+ * (minimum_snap.py:97-124) evaluated on the fly. */
+int uavb_rollout_f32(const uavb_rollout_args* args, void* stream);
+
+/* Same rollout with every state variable and operation in fp64 (validation of the fp32 path). */
+int uavb_rollout_f64(const uavb_rollout_args* args, void* stream);
+
+/* Fill `veh` with the lab_course.xml vehicle and the gains of Quad.__init__ (quad.py:54-73). */
+void uavb_vehicle_defaults(uavb_vehicle* veh);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage-level entry points: one controller / vehicle method for B drones (unit-test granularity).
+ * All arrays fp32 SoA of length B unless noted; X is [13][B].
+ *
+ *   stage                replaces                                          in                     out
+ *   UAVB_STAGE_OUTER     TrajectoryController._update_outer_loop           X, target[10][B],      thrust[B], pqr_cmd[3][B],
+ *                        (main.py:47-61)                                   integral[B]            integral (updated)
+ *   UAVB_STAGE_INNER     body_rate_controller + set_propeller_speed        X, thrust, pqr_cmd,    moment[3][B], forces[4][B],
+ *                        (controller.py:115-130, quad.py:88-122)           omega[4][B]            omega (updated)
+ *   UAVB_STAGE_PHYSICS   MujocoSimulation.step (mujoco_sim.py:144-151)     X, omega, zb[3][B]     X (updated)
+ */
+#define UAVB_STAGE_OUTER   1
+#define UAVB_STAGE_INNER   2
+#define UAVB_STAGE_PHYSICS 3
+typedef struct uavb_stage_args {
+  int B;
+  int stage;
+  uavb_vehicle veh;
+  double dt_outer;
+  float* X;            /* [13][B] */
+  const float* target; /* [10][B]: x y z vx vy vz ax ay az yaw of the table row */
+  float* integral;     /* [B] */
+  float* thrust;       /* [B] */
+  float* pqr_cmd;      /* [3][B] */
+  float* moment;       /* [3][B] */
+  float* forces;       /* [4][B] */
+  float* omega;        /* [4][B] */
+  const float* zb;     /* [3][B] thrust direction (third column of the body rotation) or NULL = from X */
+  const float* wind;   /* [3][B] or NULL */
+} uavb_stage_args;
+int uavb_stage_f32(const uavb_stage_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Monte-Carlo inputs from a counter-based generator (Philox4x32-10 keyed by `seed`, counter =
+ * global rollout index), so results do not depend on how rollouts are sharded over GPUs.
+ *   out[k][i] = lo[k] + (hi[k]-lo[k]) * U(seed, index_base+i, stream_id, k)      k < n_fields
+ * out is [n_fields][B] fp32 SoA. */
+int uavb_mc_uniform_f32(unsigned long long seed, long long index_base, int stream_id, int B, int n_fields,
+                        const float* lo, const float* hi, float* out, void* stream);
+
+/* BASELINE configs[1] mission generator, fp64: first waypoint uniform in
+ * [2,22]x[2,12]x[-5,-1]; each next = previous + step * u, u uniform on the sphere with z scaled by
+ * 0.4, step ~ U(2,5) m; velocity ~ U(2,3) m/s.  waypoints_out [B][S+1][3], velocity_out [B]. */
+int uavb_mc_missions_f64(unsigned long long seed, long long index_base, int B, int S,
+                         double* waypoints_out, double* velocity_out, void* stream);
+
+/* Measured FMA throughput of the device in TFLOP/s (2 flop per FMA), for the roofline denominators
+ * that MEASURED_PEAKS.json does not carry.  Synchronous. */
+int uavb_measure_fma_peak(int dev, double* fp32_tflops, double* fp64_tflops);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer (end-to-end) entry points: HOST pointers in and out, copies and synchronisation inside.
+ */
+int uavb_minsnap_solve_f64_host(const double* waypoints, const double* velocity, int B, int S,
+                                double start_end_time_factor, double* coeffs_out, double* times_out,
+                                int* status_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVB_H */

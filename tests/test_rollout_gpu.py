@@ -1,0 +1,273 @@
+"""K2 parity through the C ABI: the persistent fp32 rollout kernel against closed-loop logs produced
+by the reference's own TrajectoryController / CascadedController / Quad objects (tests/golden/
+closed_loop_*.npz; physics = oracle/freebody.py, parity unpinned at the MuJoCo boundary) and against
+the NumPy oracle on seeded Monte-Carlo inputs.
+
+Tolerances (BASELINE.json north_star): closed-loop states 1e-4 m / 1e-4 rad over the lab_course
+mission with fp32 rollouts; collision flags bit-exact.  Velocities and body rates are held to
+1e-3 m/s and 1e-3 rad/s (not named by north_star; measured ~3e-6 and ~3e-5)."""
+import numpy as np
+import pytest
+
+from helpers import GOAL, lab_course_plan, mc_arrays, rotation_angle
+
+pytestmark = pytest.mark.gpu
+POS_TOL, ANG_TOL, VEL_TOL, RATE_TOL = 1e-4, 1e-4, 1e-3, 1e-3
+
+
+def _fly(dev, plan, B, n_ticks, dtype=None, **kw):
+    import torch
+    from uav_ac_b200 import kernels
+    from uav_ac_b200.simulation.scene import LAB_COURSE_START
+    start = kw.pop("start", None)
+    if start is None:
+        start = torch.tensor(LAB_COURSE_START, dtype=torch.float64, device=dev)
+    goal = kw.pop("goal", torch.tensor(GOAL, dtype=torch.float64, device=dev))
+    res = kernels.rollout(plan, B, n_ticks, start=start, goal=goal, dtype=dtype or torch.float32, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def _check_log(log, gold, pos_tol=POS_TOL, ang_tol=ANG_TOL):
+    """log [n, 13, B] -> compare rollout 0 with the golden per-period states [n, 13]."""
+    X = log[:, :, 0].double().cpu().numpy()
+    ref = gold["X"]
+    assert X.shape == ref.shape
+    dp = np.abs(X[:, 0:3] - ref[:, 0:3]).max()
+    da = rotation_angle(X[:, 3:7], ref[:, 3:7]).max()
+    dv = np.abs(X[:, 7:10] - ref[:, 7:10]).max()
+    dw = np.abs(X[:, 10:13] - ref[:, 10:13]).max()
+    print(f"max |dpos| {dp:.2e} m, attitude {da:.2e} rad, |dvel| {dv:.2e} m/s, |drate| {dw:.2e} rad/s")
+    assert dp < pos_tol and da < ang_tol and dv < VEL_TOL and dw < RATE_TOL
+    return dp, da
+
+
+def _check_metrics(m, gold, prefix="", tol=2e-5):
+    m = m.double().cpu().numpy()
+    g = lambda k: float(gold[prefix + k])
+    assert abs(m[0] - g("final_dist")) < POS_TOL
+    assert m[1] == float(bool(gold[prefix + "collision"]))                  # bit-exact flag
+    assert abs(m[2] - g("rmse")) < tol and abs(m[3] - g("mean_err")) < tol and abs(m[4] - g("max_err")) < POS_TOL
+    assert m[5] == 0 and m[6] == float(gold[prefix + "first_collision_tick"])
+    assert m[7] == len(gold[prefix + "errors"])
+
+
+@pytest.mark.parametrize("v", [2, 3])
+def test_lab_course_fp32_rollout_matches_reference_closed_loop(cuda, golden, v):
+    import torch
+    from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES
+    gold = golden[f"closed_loop_v{v}"]
+    plan = lab_course_plan(cuda, float(v))
+    n_rows = int(plan.total_rows.item())
+    assert n_rows == len(gold["X"])                                          # 1613 / 1076 table rows
+    obs = torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=cuda)
+    res = _fly(cuda, plan, 1, 10 * n_rows, obstacles=obs, log_stride=10)
+    _check_log(res.log, gold)
+    _check_metrics(res.metrics[0], gold)
+    # the reference integration thresholds (tests/integration/test_mujoco_trajectory_tracking.py:34-36)
+    m = res.metrics[0].cpu().numpy()
+    assert m[0] < 0.5 and m[3] < 0.5 and m[1] == 0.0
+    # first 2000 ticks at full rate, incl. rotor speeds' effect on the state
+    fine = _fly(cuda, plan, 1, 2000, log_stride=1).log[:, :, 0].double().cpu().numpy()
+    ref = gold["fine"][:, :13]
+    assert np.abs(fine[:, :3] - ref[:, :3]).max() < POS_TOL and rotation_angle(fine[:, 3:7], ref[:, 3:7]).max() < ANG_TOL
+
+
+@pytest.mark.parametrize("v", [2, 3])
+def test_lab_course_fp64_rollout_matches_reference_closed_loop(cuda, golden, v):
+    import torch
+    gold = golden[f"closed_loop_v{v}"]
+    plan = lab_course_plan(cuda, float(v))
+    res = _fly(cuda, plan, 1, 10 * len(gold["X"]), dtype=torch.float64, log_stride=10)
+    dp, da = _check_log(res.log, gold, 1e-6, 1e-6)
+    _check_metrics(res.metrics[0], gold, tol=1e-7)
+
+
+def test_variants_thrust_frame_wind_montecarlo_and_collision(cuda, golden):
+    import torch
+    from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES
+    var = golden["closed_loop_variants"]
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * int(plan.total_rows.item())
+    obs = torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=cuda)
+
+    def sub(prefix):
+        return {k[len(prefix):]: var[k] for k in var.files if k.startswith(prefix)}
+
+    res = _fly(cuda, plan, 1, n, obstacles=obs, log_stride=10, thrust_frame_lag=0)     # viewer path: fresh thrust frame
+    _check_log(res.log, sub("nolag_")); _check_metrics(res.metrics[0], sub("nolag_"))
+    for j in range(3):                                                                 # Monte-Carlo gains / mass / inertia
+        g = sub(f"mc{j}_")
+        mc = mc_arrays(cuda, 1, g["gain_scale"][None], [float(g["mass_scale"])], g["inertia_scale"][None])
+        res = _fly(cuda, plan, 1, n, obstacles=obs, log_stride=10, **mc)
+        _check_log(res.log, g); _check_metrics(res.metrics[0], g)
+    g = sub("wind_")
+    res = _fly(cuda, plan, 1, n, obstacles=obs, log_stride=10, **mc_arrays(cuda, 1, wind=g["force"][None]))
+    _check_log(res.log, g); _check_metrics(res.metrics[0], g)
+    g = sub("hit_")                                                                    # an AABB on the course: flag and first tick exact
+    res = _fly(cuda, plan, 1, n, obstacles=torch.tensor(g["obstacles"], dtype=torch.float32, device=cuda), log_stride=10)
+    _check_log(res.log, g); _check_metrics(res.metrics[0], g)
+    assert res.metrics[0, 1].item() == 1.0 and res.metrics[0, 6].item() == 4086.0
+
+
+def test_batch_is_deterministic_and_position_independent(cuda, golden):
+    """The same rollout at every thread position gives bit-identical results; a batch mixing the golden
+    Monte-Carlo variants reproduces each of them wherever it sits in the grid."""
+    import torch
+    var = golden["closed_loop_variants"]
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * int(plan.total_rows.item())
+    B = 1000
+    res = _fly(cuda, plan, B, n)
+    assert bool((res.state == res.state[:, :1]).all()) and bool((res.metrics == res.metrics[:1]).all())
+    gs, ms, ins = np.ones((B, 11)), np.ones(B), np.ones((B, 3))
+    where = {0: 3, 1: 517, 2: 999}
+    for j, b in where.items():
+        gs[b], ms[b], ins[b] = var[f"mc{j}_gain_scale"], float(var[f"mc{j}_mass_scale"]), var[f"mc{j}_inertia_scale"]
+    res2 = _fly(cuda, plan, B, n, **mc_arrays(cuda, B, gs, ms, ins))
+    for j, b in where.items():
+        Xf = res2.state[:, b].double().cpu().numpy()
+        ref = var[f"mc{j}_X"][-1]
+        assert np.abs(Xf[:3] - ref[:3]).max() < POS_TOL and rotation_angle(Xf[3:7], ref[3:7]) < ANG_TOL
+        assert abs(res2.metrics[b, 0].item() - float(var[f"mc{j}_final_dist"])) < POS_TOL
+    # untouched slots equal the nominal flight (fp32 defaults are the rounded fp64 defaults)
+    assert np.abs((res2.state[:, 0] - res.state[:, 0]).cpu().numpy()).max() < 1e-5
+
+
+def test_chunked_launches_resume_bit_exactly(cuda):
+    import torch
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * int(plan.total_rows.item())
+    B = 256
+    rng = np.random.default_rng(3)
+    mc = mc_arrays(cuda, B, rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3)))
+    whole = _fly(cuda, plan, B, n, **mc)
+    first = _fly(cuda, plan, B, 4003, want_carry=True, **mc)                    # split in the middle of an outer period
+    second = _fly(cuda, plan, B, n - 4003, carry=first.carry, resume=True, **mc)
+    assert torch.equal(whole.state, second.state)
+    assert torch.equal(whole.metrics, second.metrics)
+
+
+def test_holds_last_row_after_the_table_ends(cuda, golden):
+    """index = min(index+1, N-1) (main.py:61): flying past the table keeps tracking the last row."""
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * int(plan.total_rows.item())
+    res = _fly(cuda, plan, 1, n + 5000)
+    m = res.metrics[0].cpu().numpy()
+    assert m[7] == (n + 5000) // 10 and m[5] == 0
+    assert m[0] < 0.02                                                          # settles on the goal while holding the last row
+
+
+def test_montecarlo_batch_matches_numpy_oracle_on_a_sample(cuda, golden):
+    """BASELINE configs[2] at reduced size: per-rollout perturbed gains / mass / inertia from the
+    counter-based generator; a strided sample is re-flown by the NumPy oracle with the same fp32 inputs."""
+    import torch
+    from oracle import flight_np
+    from uav_ac_b200 import kernels, _native as nat
+    g = golden["planning"]
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * int(plan.total_rows.item())
+    B = 20000
+    sc = kernels.mc_uniform(11, B, [0.8] * 11 + [0.9] * 4, [1.2] * 11 + [1.1] * 4)            # [15, B] multiplicative scales
+    v = nat.default_vehicle()
+    base = torch.tensor(list(v.gains) + [v.mass] + list(v.inertia), dtype=torch.float32, device=cuda)[:, None]
+    vals = (sc * base).contiguous()
+    obs = torch.tensor(g["obstacles"], dtype=torch.float32, device=cuda)
+    res = _fly(cuda, plan, B, n, obstacles=obs, mc_gains=vals[:11].contiguous(), mc_mass=vals[11].contiguous(),
+               mc_inertia=vals[12:15].contiguous())
+    met = res.metrics.cpu().numpy()
+    assert np.isfinite(met).all() and (met[:, 5] == 0).all()
+    vals = vals.double().cpu().numpy()
+    tab = g["v3_table"]
+    worst = 0.0
+    for b in range(0, B, B // 6):
+        veh = flight_np.Vehicle()
+        kw = {k: getattr(veh, k) for k in veh.__dataclass_fields__}
+        for k, name in enumerate(flight_np.Vehicle.GAIN_NAMES):
+            kw[name] = vals[k, b]
+        kw["mass"], kw["inertia"] = vals[11, b], vals[12:15, b]
+        ref = flight_np.closed_loop(flight_np.Vehicle(**kw), tab, g["waypoints"][0], obstacles=g["obstacles"], goal=GOAL)
+        Xf = res.state[:, b].double().cpu().numpy()
+        dp = np.abs(Xf[:3] - ref["X"][:3]).max()
+        worst = max(worst, dp)
+        assert dp < POS_TOL and rotation_angle(Xf[3:7], ref["X"][3:7]) < ANG_TOL
+        assert met[b, 1] == float(ref["collision"])
+        assert abs(met[b, 3] - ref["mean_err"]) < 2e-5 and abs(met[b, 0] - ref["final_dist"]) < POS_TOL
+    print(f"worst final-position difference over the sample: {worst:.2e} m")
+
+
+def test_random_missions_wind_and_obstacle_sets_match_numpy_oracle(cuda):
+    """BASELINE configs[3] at reduced size: per-rollout waypoint sets (vertical take-off + 4-spline course),
+    constant wind, per-rollout AABB sets; collision flags exact outside the 1e-4 m ambiguity band."""
+    import torch
+    from oracle import flight_np, minsnap_np
+    from uav_ac_b200 import kernels
+    B, S = 4096, 4
+    wp, vel = kernels.mc_missions(21, B, S)
+    ground = wp[:, 0].clone()
+    ground[:, 2] = -0.021
+    tk = torch.stack((ground, wp[:, 0]), dim=1).contiguous()                  # vertical take-off to the first waypoint
+    plan = kernels.plan_missions([(tk, vel), (wp, vel)], 0.01)
+    wind = kernels.mc_uniform(22, B, [-0.08] * 3, [0.08] * 3)
+    # 8 obstacle sets of 5 boxes scattered in the flight volume
+    rng = np.random.default_rng(8)
+    ctr = rng.uniform([2, 2, -5], [22, 12, -1], (8, 5, 3))
+    half = rng.uniform(0.3, 1.2, (8, 5, 3))
+    boxes = np.stack((ctr[..., 0] - half[..., 0], ctr[..., 0] + half[..., 0], ctr[..., 1] - half[..., 1], ctr[..., 1] + half[..., 1],
+                      ctr[..., 2] - half[..., 2], ctr[..., 2] + half[..., 2]), axis=-1).astype(np.float32)
+    sets = torch.tensor(rng.integers(0, 8, B), dtype=torch.int32, device=cuda)
+    n_ticks = int(plan.total_rows.max().item()) * 10
+    res = _fly(cuda, plan, B, n_ticks, start=ground.contiguous(), goal=wp[:, -1].contiguous(), mc_wind=wind,
+               obstacles=torch.tensor(boxes, device=cuda), obstacle_set=sets)
+    met = res.metrics.cpu().numpy()
+    assert np.isfinite(met[:, :5]).all()
+    assert 0.02 < met[:, 1].mean() < 0.98                                      # both outcomes are exercised
+    wpn, veln, windn, setn = wp.cpu().numpy(), vel.cpu().numpy(), wind.double().cpu().numpy(), sets.cpu().numpy()
+    checked = ambiguous = 0
+    for b in range(0, B, B // 10):
+        tab = np.vstack([minsnap_np.sample_table(*minsnap_np.solve_coeffs(w, veln[b], "solve"), 0.01)
+                         for w in (np.stack((ground[b].cpu().numpy(), wpn[b, 0])), wpn[b])])
+        veh = flight_np.Vehicle()
+        ob = boxes[setn[b]].astype(float)
+        ref = flight_np.closed_loop(veh, tab, ground[b].cpu().numpy(), obstacles=ob, goal=wpn[b, -1], wind=windn[:, b], n_ticks=n_ticks,
+                                    log_stride=1)
+        if met[b, 5] != 0 or ref["max_err"] > 5.0:
+            continue                                                          # diverged flights amplify rounding: not comparable
+        Xf = res.state[:, b].double().cpu().numpy()
+        assert np.abs(Xf[:3] - ref["X"][:3]).max() < POS_TOL and rotation_angle(Xf[3:7], ref["X"][3:7]) < ANG_TOL
+        # signed distance of the fp64 path to the nearest box face decides whether the flag is ambiguous
+        P = ref["log"][:, :3]
+        gap = np.inf
+        for q in ob:
+            d = np.maximum.reduce([q[0] - P[:, 0], P[:, 0] - q[1], q[2] - P[:, 1], P[:, 1] - q[3], q[4] - P[:, 2], P[:, 2] - q[5]])
+            gap = min(gap, np.abs(d).min())
+        if gap < POS_TOL:
+            ambiguous += 1
+            continue
+        assert met[b, 1] == float(ref["collision"]) and met[b, 6] == ref["first_collision_tick"]
+        checked += 1
+    print(f"collision flags: {checked} exact, {ambiguous} inside the {POS_TOL} m ambiguity band")
+    assert checked >= 5
+
+
+def test_state_log_layout_and_stride(cuda):
+    import torch
+    plan = lab_course_plan(cuda, 3.0)
+    B, n = 96, 3000
+    a = _fly(cuda, plan, B, n, log_stride=1)
+    b = _fly(cuda, plan, B, n, log_stride=50)
+    assert a.log.shape == (n, 13, B) and b.log.shape == (n // 50, 13, B)
+    assert torch.equal(a.log[49::50], b.log)                                   # sample s is the state after tick (s+1)*stride
+    assert torch.equal(a.log[-1], a.state)
+
+
+def test_argument_errors_are_reported_not_ignored(cuda):
+    import torch
+    from uav_ac_b200 import kernels, _native as nat
+    plan = lab_course_plan(cuda, 3.0)
+    with pytest.raises(nat.UavbError):
+        kernels.rollout(plan, 4, 100, start=torch.zeros(3, dtype=torch.float64))            # host tensor: no CPU path
+    with pytest.raises(nat.UavbError):
+        kernels.rollout(plan, 4, 100, start=torch.zeros(3, dtype=torch.float64, device=cuda), frequency=0)
+    with pytest.raises(ValueError):
+        kernels.rollout(plan, 4, 100, start=torch.zeros(3, dtype=torch.float64, device=cuda), mc_mass=torch.ones(3, device=cuda))

@@ -1,0 +1,107 @@
+// capi.cu -- library-level C-ABI entry points: version, errors, device probing, FMA peak probe.
+#include "uavb_common.cuh"
+
+namespace uavb {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return set_error(UAVB_ENODEVICE, "no CUDA device visible (%s); libuavb has no CPU path",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  return UAVB_OK;
+}
+
+// Dependent-chain-free FMA loops: 8 independent accumulators per thread, enough CTAs to fill the chip.
+template <class T> __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+  T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+      x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+template <class T> static int measure_one(int sms, double* tflops) {
+  const int threads = 256, blocks = sms * 8, iters = sizeof(T) == 4 ? 4096 : 2048;
+  T* buf = nullptr;
+  UAVB_CUDA_OK(cudaMalloc(&buf, sizeof(T) * threads * blocks));
+  cudaEvent_t e0, e1;
+  UAVB_CUDA_OK(cudaEventCreate(&e0));
+  UAVB_CUDA_OK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    UAVB_CUDA_OK(cudaEventRecord(e0));
+    fma_peak_kernel<T><<<blocks, threads>>>(buf, iters, (T)0.999, (T)0.001);
+    UAVB_CUDA_OK(cudaEventRecord(e1));
+    UAVB_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    UAVB_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 64.0 * (double)iters * threads * blocks;
+    if (rep > 0 && ms > 0.f) best = fmax(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return UAVB_OK;
+}
+
+}  // namespace uavb
+
+extern "C" int uavb_version(void) { return UAVB_VERSION; }
+extern "C" const char* uavb_last_error(void) { return uavb::error_buffer(); }
+
+extern "C" int uavb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int uavb_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor) {
+  int rc = uavb::require_device();
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  UAVB_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return UAVB_OK;
+}
+
+extern "C" int uavb_measure_fma_peak(int dev, double* fp32_tflops, double* fp64_tflops) {
+  int rc = uavb::require_device();
+  if (rc) return rc;
+  UAVB_CUDA_OK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  UAVB_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  double a = 0.0, b = 0.0;
+  rc = uavb::measure_one<float>(prop.multiProcessorCount, &a);
+  if (rc) return rc;
+  rc = uavb::measure_one<double>(prop.multiProcessorCount, &b);
+  if (rc) return rc;
+  if (fp32_tflops) *fp32_tflops = a;
+  if (fp64_tflops) *fp64_tflops = b;
+  return UAVB_OK;
+}

@@ -1,0 +1,329 @@
+// minsnap_kernels.cu -- K1 (batched minimum-snap solve), table geometry, K3 (sampled table) and the
+// sampled-point AABB test of the correction loop.  All fp64, sm_100a.
+//
+// K1 is one thread per mission: ~2.5 k fp64 flops against 928 B of HBM traffic for S = 4
+// (SURVEY 8(d)), i.e. HBM-bound.  The per-mission output (8 S x 3 doubles, contiguous) is staged in
+// shared memory and leaves the CTA as one contiguous tile so every 32-byte sector is written whole.
+#include "minsnap_core.cuh"
+#include "uavb_common.cuh"
+
+namespace uavb {
+
+constexpr int kSolveThreads = 64;
+
+// ---------------------------------------------------------------------------------------------
+// K1, uniform S.  STAGED: coefficients go to shared memory [thread][24 S + 1] (odd pitch in doubles:
+// consecutive threads start 2 banks apart, so a warp's 64-bit stores need the minimal 2 wavefronts)
+// and are then copied out by the whole CTA with consecutive threads writing consecutive doubles.
+// !STAGED (S > 8): per-thread direct stores, work arrays in local memory.
+template <int MAXS, bool STAGED>
+__global__ void __launch_bounds__(kSolveThreads) minsnap_solve_kernel(
+    const double* __restrict__ waypoints, const double* __restrict__ velocity, int B, int S, double factor,
+    double* __restrict__ coeffs_out, double* __restrict__ times_out, int* __restrict__ status_out) {
+  extern __shared__ double s_out[];
+  const int per = 24 * S;              // doubles per mission
+  const int pitch = per + 1;
+  const long long base = (long long)blockIdx.x * kSolveThreads;
+  const long long b = base + threadIdx.x;
+  double* mine = STAGED ? s_out + (size_t)threadIdx.x * pitch : coeffs_out + (size_t)(b < B ? b : 0) * per;
+  if (b < B) {
+    const double* w = waypoints + (size_t)b * (S + 1) * 3;
+    double* tout = times_out + (size_t)b * S;
+    const int st = minsnap_solve_one<MAXS>(
+        S, velocity[b], factor, [w](int i, int ax) { return __ldg(w + 3 * i + ax); },
+        [mine](int seg, int j, int ax, double val) { mine[seg * 24 + j * 3 + ax] = val; },
+        [tout](int seg, double t) { tout[seg] = t; });
+    if (status_out) status_out[b] = st;
+  }
+  if (!STAGED) return;
+  __syncthreads();
+  const int n_here = (int)((B - base) < kSolveThreads ? (B - base) : kSolveThreads);
+  double* gout = coeffs_out + (size_t)base * per;
+  const int total = n_here * per;
+  int mi = 0, off = threadIdx.x;       // e = mi * per + off, advanced without a division
+  while (off >= per) { off -= per; ++mi; }
+  for (int e = threadIdx.x; e < total; e += kSolveThreads) {
+    gout[e] = s_out[(size_t)mi * pitch + off];
+    off += kSolveThreads;
+    while (off >= per) { off -= per; ++mi; }
+  }
+}
+
+// K1, ragged S (obstacle-correction loop): per-thread direct stores, packed segments.
+template <int MAXS>
+__global__ void __launch_bounds__(kSolveThreads) minsnap_solve_ragged_kernel(
+    const double* __restrict__ waypoints, const int* __restrict__ wp_offsets, const double* __restrict__ velocity, int B,
+    double factor, double* __restrict__ coeffs_out, double* __restrict__ times_out, int* __restrict__ status_out) {
+  const long long b = (long long)blockIdx.x * kSolveThreads + threadIdx.x;
+  if (b >= B) return;
+  const int w0 = wp_offsets[b], w1 = wp_offsets[b + 1];
+  const int S = w1 - w0 - 1;
+  const int seg0 = w0 - (int)b;
+  if (S < 1 || S > MAXS) {
+    if (status_out) status_out[b] = UAVB_SOLVE_DEGENERATE;
+    return;
+  }
+  const double* w = waypoints + (size_t)w0 * 3;
+  double* cout = coeffs_out + (size_t)seg0 * 24;
+  double* tout = times_out + seg0;
+  const int st = minsnap_solve_one<MAXS>(
+      S, velocity[b], factor, [w](int i, int ax) { return __ldg(w + 3 * i + ax); },
+      [cout](int seg, int j, int ax, double val) { cout[seg * 24 + j * 3 + ax] = val; },
+      [tout](int seg, double t) { tout[seg] = t; });
+  if (status_out) status_out[b] = st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table geometry: rows per segment and the look-ahead yaw of every table (minimum_snap.py:104,126-136).
+// len(np.arange(0, T, dt)) = ceil(T / dt) with the division in fp64 (NumPy's arange length rule).
+__device__ __forceinline__ int arange_len(double T, double dt) {
+  const double n = ceil(T / dt);
+  return n > 0.0 ? (n < 2147483647.0 ? (int)n : 2147483647) : 0;
+}
+
+__device__ __forceinline__ void eval_vel_xy(const double* __restrict__ c, double t, double* vx, double* vy) {
+  double v[2];
+#pragma unroll
+  for (int ax = 0; ax < 2; ++ax) {
+    const double c7 = c[21 + ax], c6 = c[18 + ax], c5 = c[15 + ax], c4 = c[12 + ax], c3 = c[9 + ax], c2 = c[6 + ax], c1 = c[3 + ax];
+    v[ax] = (((((7.0 * c7 * t + 6.0 * c6) * t + 5.0 * c5) * t + 4.0 * c4) * t + 3.0 * c3) * t + 2.0 * c2) * t + c1;
+  }
+  *vx = v[0]; *vy = v[1];
+}
+
+__global__ void __launch_bounds__(128) table_meta_kernel(const double* __restrict__ coeffs, const double* __restrict__ times,
+                                                         const int* __restrict__ seg_offsets, int B, double dt,
+                                                         int* __restrict__ rows_out, double* __restrict__ yaw0_out,
+                                                         int* __restrict__ total_rows_out) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
+  int total = 0;
+  double yaw0 = 0.0;
+  bool found = false;
+  for (int s = s0; s < s1; ++s) {
+    const int n = arange_len(times[s], dt);
+    rows_out[s] = n;
+    total += n;
+    if (!found) {
+      const double* c = coeffs + (size_t)s * 24;
+      for (int j = 0; j < n; ++j) {
+        double vx, vy;
+        eval_vel_xy(c, (double)j * dt, &vx, &vy);
+        if (sqrt(vx * vx + vy * vy) >= 1e-3) { yaw0 = atan2(vy, vx); found = true; break; }
+      }
+    }
+  }
+  yaw0_out[b] = yaw0;
+  if (total_rows_out) total_rows_out[b] = total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 sampled table.  Pass 1: one warp per mission, lanes stride the rows of each segment and write
+// position / velocity / acceleration / spline id; the yaw column receives atan2(vy, vx) or NaN for
+// rows below the speed threshold.  Pass 2: one thread per mission walks its rows in order and
+// applies np.unwrap + hold-last-valid + first-valid look-ahead (minimum_snap.py:126-136).
+__global__ void __launch_bounds__(128) sample_rows_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
+                                                          const int* __restrict__ seg_rows, const int* __restrict__ row_offsets, int B,
+                                                          double dt, double* __restrict__ table) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const int s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
+  long long row = row_offsets[b];
+  for (int s = s0; s < s1; ++s) {
+    const int n = seg_rows[s];
+    const double* c = coeffs + (size_t)s * 24;
+    for (int j = lane; j < n; j += 32) {
+      const double t = (double)j * dt;
+      double* o = table + (size_t)(row + j) * 11;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        const double c7 = c[21 + ax], c6 = c[18 + ax], c5 = c[15 + ax], c4 = c[12 + ax];
+        const double c3 = c[9 + ax], c2 = c[6 + ax], c1 = c[3 + ax], c0 = c[ax];
+        o[ax] = ((((((c7 * t + c6) * t + c5) * t + c4) * t + c3) * t + c2) * t + c1) * t + c0;
+        o[3 + ax] = (((((7.0 * c7 * t + 6.0 * c6) * t + 5.0 * c5) * t + 4.0 * c4) * t + 3.0 * c3) * t + 2.0 * c2) * t + c1;
+        o[6 + ax] = ((((42.0 * c7 * t + 30.0 * c6) * t + 20.0 * c5) * t + 12.0 * c4) * t + 6.0 * c3) * t + 2.0 * c2;
+      }
+      const double vx = o[3], vy = o[4];
+      o[9] = (sqrt(vx * vx + vy * vy) >= 1e-3) ? atan2(vy, vx) : nan("");
+      o[10] = (double)(s - s0);
+    }
+    row += n;
+  }
+}
+
+__global__ void __launch_bounds__(128) sample_yaw_kernel(const int* __restrict__ row_offsets, int B, double* __restrict__ table) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long r0 = row_offsets[b], r1 = row_offsets[b + 1];
+  const double two_pi = 6.283185307179586476925286766559, pi = 3.141592653589793238462643383279;
+  // first valid yaw (look-ahead for the leading rows)
+  double first = 0.0;
+  long long rf = r1;
+  for (long long r = r0; r < r1; ++r) {
+    const double y = table[(size_t)r * 11 + 9];
+    if (y == y) { first = y; rf = r; break; }
+  }
+  if (rf == r1) {                       // no valid row: all zeros (minimum_snap.py:130-131)
+    for (long long r = r0; r < r1; ++r) table[(size_t)r * 11 + 9] = 0.0;
+    return;
+  }
+  double prev_raw = first, hold = first;
+  for (long long r = r0; r < r1; ++r) {
+    double* y = table + (size_t)r * 11 + 9;
+    const double raw = *y;
+    if (r > rf && raw == raw) {
+      // np.unwrap: dd = raw - prev_raw; ddmod = mod(dd + pi, 2 pi) - pi, with -pi -> +pi when dd > 0;
+      // correction applied only where |dd| >= pi; cumulative.
+      const double dd = raw - prev_raw;
+      double ddmod = dd + pi;
+      ddmod = ddmod - two_pi * floor(ddmod / two_pi) - pi;
+      if (ddmod == -pi && dd > 0.0) ddmod = pi;
+      double corr = ddmod - dd;
+      if (fabs(dd) < pi) corr = 0.0;
+      hold = hold + dd + corr;
+      prev_raw = raw;
+    }
+    *y = hold;
+  }
+}
+
+// Sampled-point AABB test of the correction loop (minimum_snap.py:84-87): one warp per mission.
+__global__ void __launch_bounds__(128) table_hits_kernel(const double* __restrict__ table, const int* __restrict__ row_offsets, int B,
+                                                         const double* __restrict__ cuboid, int cuboid_stride,
+                                                         unsigned long long* __restrict__ hit_mask) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const double* q = cuboid + (size_t)cuboid_stride * b;
+  const double x0 = q[0], x1 = q[1], y0 = q[2], y1 = q[3], z0 = q[4], z1 = q[5];
+  unsigned long long m = 0ull;
+  for (long long r = row_offsets[b] + lane; r < row_offsets[b + 1]; r += 32) {
+    const double* o = table + (size_t)r * 11;
+    const double x = o[0], y = o[1], z = o[2];
+    if (x0 <= x && x <= x1 && y0 <= y && y <= y1 && z0 <= z && z <= z1) m |= 1ull << ((int)o[10] & 63);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
+  if (lane == 0) hit_mask[b] |= m;
+}
+
+template <int MAXS, bool STAGED>
+static int launch_solve(const double* w, const double* vel, int B, int S, double factor, double* c, double* t, int* st, cudaStream_t stream) {
+  const size_t smem = STAGED ? sizeof(double) * (size_t)kSolveThreads * (24 * S + 1) : 0;
+  if (smem > 48 * 1024)
+    UAVB_CUDA_OK(cudaFuncSetAttribute(minsnap_solve_kernel<MAXS, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  minsnap_solve_kernel<MAXS, STAGED><<<div_up(B, kSolveThreads), kSolveThreads, smem, stream>>>(w, vel, B, S, factor, c, t, st);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+}  // namespace uavb
+
+using namespace uavb;
+
+extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* velocity, int B, int S, double factor,
+                                      double* coeffs_out, double* times_out, int* status_out, void* stream) {
+  UAVB_REQUIRE(waypoints && velocity && coeffs_out && times_out, "minsnap_solve: NULL pointer");
+  UAVB_REQUIRE(B >= 0, "minsnap_solve: B must be >= 0");
+  UAVB_REQUIRE(S >= 1 && S <= UAVB_MAX_SPLINES, "minsnap_solve: S must be in [1, UAVB_MAX_SPLINES]");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (S == 1) return launch_solve<1, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  if (S == 2) return launch_solve<2, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  if (S <= 4) return launch_solve<4, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  if (S <= 8) return launch_solve<8, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  return launch_solve<UAVB_MAX_SPLINES, false>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+}
+
+extern "C" int uavb_minsnap_solve_ragged_f64(const double* waypoints, const int* wp_offsets, const double* velocity, int B,
+                                             double factor, double* coeffs_out, double* times_out, int* status_out, void* stream) {
+  UAVB_REQUIRE(waypoints && wp_offsets && velocity && coeffs_out && times_out, "minsnap_solve_ragged: NULL pointer");
+  UAVB_REQUIRE(B >= 0, "minsnap_solve_ragged: B must be >= 0");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  minsnap_solve_ragged_kernel<UAVB_MAX_SPLINES><<<div_up(B, kSolveThreads), kSolveThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      waypoints, wp_offsets, velocity, B, factor, coeffs_out, times_out, status_out);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+extern "C" int uavb_minsnap_table_meta_f64(const double* coeffs, const double* times, const int* seg_offsets, int B, double dt,
+                                           int* rows_out, double* yaw0_out, int* total_rows_out, void* stream) {
+  UAVB_REQUIRE(coeffs && times && seg_offsets && rows_out && yaw0_out, "table_meta: NULL pointer");
+  UAVB_REQUIRE(B >= 0 && dt > 0.0, "table_meta: B >= 0 and dt > 0 required");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  table_meta_kernel<<<div_up(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(coeffs, times, seg_offsets, B, dt, rows_out,
+                                                                                   yaw0_out, total_rows_out);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+extern "C" int uavb_minsnap_sample_f64(const double* coeffs, const double* times, const int* seg_offsets, const int* seg_rows,
+                                       const int* row_offsets, int B, double dt, double* table_out, void* stream) {
+  (void)times;
+  UAVB_REQUIRE(coeffs && seg_offsets && seg_rows && row_offsets && table_out, "minsnap_sample: NULL pointer");
+  UAVB_REQUIRE(B >= 0 && dt > 0.0, "minsnap_sample: B >= 0 and dt > 0 required");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  sample_rows_kernel<<<div_up((long long)B * 32, 128), 128, 0, st>>>(coeffs, seg_offsets, seg_rows, row_offsets, B, dt, table_out);
+  UAVB_CUDA_OK(cudaGetLastError());
+  sample_yaw_kernel<<<div_up(B, 128), 128, 0, st>>>(row_offsets, B, table_out);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+extern "C" int uavb_minsnap_table_hits_f64(const double* table, const int* row_offsets, int B, const double* cuboid,
+                                           int cuboid_stride, unsigned long long* hit_mask_out, void* stream) {
+  UAVB_REQUIRE(table && row_offsets && cuboid && hit_mask_out, "table_hits: NULL pointer");
+  UAVB_REQUIRE(cuboid_stride == 0 || cuboid_stride == 6, "table_hits: cuboid_stride must be 0 or 6");
+  UAVB_REQUIRE(B >= 0, "table_hits: B must be >= 0");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  table_hits_kernel<<<div_up((long long)B * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(table, row_offsets, B, cuboid,
+                                                                                                 cuboid_stride, hit_mask_out);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+extern "C" int uavb_minsnap_solve_f64_host(const double* waypoints, const double* velocity, int B, int S, double factor,
+                                           double* coeffs_out, double* times_out, int* status_out) {
+  UAVB_REQUIRE(waypoints && velocity && coeffs_out && times_out, "minsnap_solve_host: NULL pointer");
+  UAVB_REQUIRE(B >= 0 && S >= 1 && S <= UAVB_MAX_SPLINES, "minsnap_solve_host: B >= 0 and 1 <= S <= UAVB_MAX_SPLINES required");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  const size_t nw = (size_t)B * (S + 1) * 3, nc = (size_t)B * 24 * S, nt = (size_t)B * S;
+  double *dw = nullptr, *dv = nullptr, *dc = nullptr, *dtm = nullptr;
+  int* ds = nullptr;
+  cudaStream_t st = nullptr;
+  auto cleanup = [&]() { cudaFree(dw); cudaFree(dv); cudaFree(dc); cudaFree(dtm); cudaFree(ds); };
+  if (cudaMalloc(&dw, nw * 8) != cudaSuccess || cudaMalloc(&dv, (size_t)B * 8) != cudaSuccess || cudaMalloc(&dc, nc * 8) != cudaSuccess ||
+      cudaMalloc(&dtm, nt * 8) != cudaSuccess || cudaMalloc(&ds, (size_t)B * 4) != cudaSuccess) {
+    cleanup();
+    cudaGetLastError();
+    return set_error(UAVB_ENOMEM, "minsnap_solve_host: device allocation failed");
+  }
+  cudaError_t e = cudaMemcpyAsync(dw, waypoints, nw * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dv, velocity, (size_t)B * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    rc = uavb_minsnap_solve_f64(dw, dv, B, S, factor, dc, dtm, ds, st);
+    if (rc) { cleanup(); return rc; }
+    e = cudaMemcpyAsync(coeffs_out, dc, nc * 8, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(times_out, dtm, nt * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out, ds, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) return set_error(UAVB_ECUDA, "minsnap_solve_host: %s", cudaGetErrorString(e));
+  return UAVB_OK;
+}

@@ -1,0 +1,252 @@
+// rollout_kernels.cu -- K2: persistent closed-loop rollout, one thread per drone (sm_100a).
+//
+// Each thread keeps its drone's 13-state, position low part, rotor speeds, controller integrator,
+// commands, table cursor and metric accumulators in registers for the whole launch (thousands of
+// 1 kHz ticks), evaluates the min-snap set-point in fp64 at the 100 Hz outer rate, runs the cascade,
+// allocation, motor lag and rigid-body step in fp32 every tick and touches HBM only for
+//   * its Monte-Carlo parameters (once), the 24 doubles of the current spline (once per outer
+//     period, broadcast through L1 when the mission is shared),
+//   * the optional decimated state log [sample][field][B] (one 4-byte store per field and thread:
+//     a warp writes one full 128-byte line per field, no partial sectors),
+//   * metrics / final state / carry (once).
+// Nothing here is a dense contraction, so no tensor-core path exists; the bound is the FP32 issue
+// rate (metrics-only) or HBM (full-rate log).  See DESIGN.md "K2".
+#include "rollout_core.cuh"
+#include "uavb_common.cuh"
+#include "veh_setup.cuh"
+
+namespace uavb {
+
+constexpr int kRolloutThreads = 128;
+
+struct RolloutDev {
+  uavb_rollout_args a;
+  VehDerived dv;
+  int tick0;  // unused when resuming (taken from the carry block)
+};
+
+// Shared obstacle set staged in shared memory (broadcast reads) or a per-rollout set in global
+// memory; inclusive bounds exactly as is_collision_cuboid (minimum_snap.py:352-357).
+struct Boxes {
+  const float* b;
+  int n;
+  template <class R> __device__ __forceinline__ bool hit(R x, R y, R z) const {
+    bool h = false;
+    for (int i = 0; i < n; ++i) {
+      const float* q = b + 6 * i;
+      h |= (q[0] <= x) & (x <= q[1]) & (q[2] <= y) & (y <= q[3]) & (q[4] <= z) & (z <= q[5]);
+    }
+    return h;
+  }
+};
+
+// [sample][13][B] state log, one sample after every `stride` ticks.
+template <class R> struct GlobalLog {
+  R* out;
+  long long B;
+  int stride, left;
+  __device__ __forceinline__ void tick(const Drone<R>& d) {
+    if (--left) return;
+    left = stride;
+    R* o = out;
+    o[0 * B] = d.px; o[1 * B] = d.py; o[2 * B] = d.pz;
+    o[3 * B] = d.q0; o[4 * B] = d.q1; o[5 * B] = d.q2; o[6 * B] = d.q3;
+    o[7 * B] = d.vx; o[8 * B] = d.vy; o[9 * B] = d.vz;
+    o[10 * B] = d.wx; o[11 * B] = d.wy; o[12 * B] = d.wz;
+    out += 13 * B;
+  }
+};
+
+__device__ __forceinline__ float i2f(int x) { return __int_as_float(x); }
+__device__ __forceinline__ int f2i(float x) { return __float_as_int(x); }
+
+// Resumable carry block, [UAVB_CARRY_WORDS][B] 32-bit words (fp32 rollout only).
+struct Carry {
+  float* p;
+  long long B;
+  __device__ __forceinline__ float& w(int k) const { return p[(long long)k * B]; }
+  __device__ void store(const Drone<float>& d, const Cursor<float>& c, const Accum<float>& a, int tick) const {
+    w(0) = d.px; w(1) = d.py; w(2) = d.pz; w(3) = d.plx; w(4) = d.ply; w(5) = d.plz;
+    w(6) = d.q0; w(7) = d.q1; w(8) = d.q2; w(9) = d.q3;
+    w(10) = d.vx; w(11) = d.vy; w(12) = d.vz; w(13) = d.wx; w(14) = d.wy; w(15) = d.wz;
+    w(16) = d.om0; w(17) = d.om1; w(18) = d.om2; w(19) = d.om3;
+    w(20) = d.integral; w(21) = d.thrust_cmd; w(22) = d.pc; w(23) = d.qc; w(24) = d.rc;
+    w(25) = d.zbx; w(26) = d.zby; w(27) = d.zbz; w(28) = c.yaw_hold;
+    w(29) = i2f(c.seg); w(30) = i2f(c.row); w(31) = i2f(c.phase);
+    w(32) = i2f(__double2loint(c.tx)); w(33) = i2f(__double2hiint(c.tx));
+    w(34) = i2f(__double2loint(c.ty)); w(35) = i2f(__double2hiint(c.ty));
+    w(36) = i2f(__double2loint(c.tz)); w(37) = i2f(__double2hiint(c.tz));
+    w(38) = a.sum_e; w(39) = a.sum_e2; w(40) = a.max_e;
+    w(41) = i2f(a.periods); w(42) = i2f(a.collided); w(43) = i2f(a.first_hit); w(44) = i2f(a.status);
+    w(45) = i2f(tick);
+  }
+  __device__ void load(Drone<float>& d, Cursor<float>& c, Accum<float>& a, int* tick) const {
+    d.px = w(0); d.py = w(1); d.pz = w(2); d.plx = w(3); d.ply = w(4); d.plz = w(5);
+    d.q0 = w(6); d.q1 = w(7); d.q2 = w(8); d.q3 = w(9);
+    d.vx = w(10); d.vy = w(11); d.vz = w(12); d.wx = w(13); d.wy = w(14); d.wz = w(15);
+    d.om0 = w(16); d.om1 = w(17); d.om2 = w(18); d.om3 = w(19);
+    d.integral = w(20); d.thrust_cmd = w(21); d.pc = w(22); d.qc = w(23); d.rc = w(24);
+    d.zbx = w(25); d.zby = w(26); d.zbz = w(27); c.yaw_hold = w(28);
+    c.seg = f2i(w(29)); c.row = f2i(w(30)); c.phase = f2i(w(31));
+    c.tx = __hiloint2double(f2i(w(33)), f2i(w(32)));
+    c.ty = __hiloint2double(f2i(w(35)), f2i(w(34)));
+    c.tz = __hiloint2double(f2i(w(37)), f2i(w(36)));
+    a.sum_e = w(38); a.sum_e2 = w(39); a.max_e = w(40);
+    a.periods = f2i(w(41)); a.collided = f2i(w(42)); a.first_hit = f2i(w(43)); a.status = f2i(w(44));
+    *tick = f2i(w(45));
+  }
+};
+
+template <class R, bool LOG>
+__global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutDev p) {
+  extern __shared__ float s_boxes[];
+  const uavb_rollout_args& a = p.a;
+  const bool shared_boxes = a.n_obs > 0 && a.aabb_set == nullptr;
+  if (shared_boxes) {
+    for (int j = threadIdx.x; j < a.n_obs * 6; j += blockDim.x) s_boxes[j] = a.aabbs[j];
+    __syncthreads();
+  }
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B) return;
+  const long long B = a.B;
+
+  // per-rollout constants
+  McValues<float> mc;
+  mc_from_vehicle(mc, a.veh);
+  if (a.mc_mass) mc.mass = a.mc_mass[i];
+  if (a.mc_inertia) { mc.inertia[0] = a.mc_inertia[i]; mc.inertia[1] = a.mc_inertia[B + i]; mc.inertia[2] = a.mc_inertia[2 * B + i]; }
+  if (a.mc_gains) {
+#pragma unroll
+    for (int k = 0; k < UAVB_N_GAINS; ++k) mc.gains[k] = a.mc_gains[k * B + i];
+  }
+  if (a.mc_wind) { mc.wind[0] = a.mc_wind[i]; mc.wind[1] = a.mc_wind[B + i]; mc.wind[2] = a.mc_wind[2 * B + i]; }
+  Veh<R> v;
+  if (a.mc_mass || a.mc_inertia || a.mc_gains || a.mc_wind) {
+    make_veh<R>(v, a.veh, p.dv, mc, a.inner_per_outer);
+  } else {                       // no overrides: derive from the fp64 defaults, not their fp32 roundings
+    McValues<double> md;
+    mc_from_vehicle(md, a.veh);
+    make_veh<R>(v, a.veh, p.dv, md, a.inner_per_outer);
+  }
+
+  MissionView m;
+  m.coeffs = a.seg_coeffs; m.rows = a.seg_rows; m.table = a.seg_table; m.yaw0 = a.seg_yaw0;
+  m.seg_begin = a.mission_seg_begin ? a.mission_seg_begin[i] : 0;
+  m.seg_count = a.mission_seg_count ? a.mission_seg_count[i] : a.n_seg_shared;
+  m.dt_outer = a.dt_outer;
+
+  Drone<R> d;
+  Cursor<R> c;
+  Accum<R> acc;
+  int tick0 = 0;
+  bool resumed = false;
+  if constexpr (sizeof(R) == 4) {
+    if (a.resume) {
+      Carry cb{a.carry + i, B};
+      cb.load(d, c, acc, &tick0);
+      resumed = true;
+    }
+  }
+  if (!resumed) {
+    const double* s = a.start + (size_t)a.start_stride * i;
+    drone_init<R>(d, s[0], s[1], s[2]);
+    cursor_init<R>(c);
+    accum_init<R>(acc);
+  }
+
+  Boxes boxes;
+  boxes.n = a.n_obs;
+  boxes.b = shared_boxes ? s_boxes : (a.n_obs > 0 ? a.aabbs + (size_t)a.aabb_set[i] * a.n_obs * 6 : nullptr);
+
+  if constexpr (LOG) {
+    GlobalLog<R> lg;
+    lg.out = reinterpret_cast<R*>(a.log_out) + i;
+    lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride;
+    rollout_run<R>(d, c, acc, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, boxes, lg);
+  } else {
+    NoLog lg;
+    rollout_run<R>(d, c, acc, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, boxes, lg);
+  }
+
+  if constexpr (sizeof(R) == 4) {
+    if (a.carry) {
+      Carry cb{a.carry + i, B};
+      cb.store(d, c, acc, tick0 + a.n_ticks);
+    }
+  }
+  if (a.state_out) {
+    R* o = reinterpret_cast<R*>(a.state_out) + i;
+    o[0 * B] = d.px; o[1 * B] = d.py; o[2 * B] = d.pz;
+    o[3 * B] = d.q0; o[4 * B] = d.q1; o[5 * B] = d.q2; o[6 * B] = d.q3;
+    o[7 * B] = d.vx; o[8 * B] = d.vy; o[9 * B] = d.vz;
+    o[10 * B] = d.wx; o[11 * B] = d.wy; o[12 * B] = d.wz;
+  }
+  if (a.metrics_out) {
+    R fd = R(0);
+    if (a.goal) {
+      const double* g = a.goal + (size_t)a.goal_stride * i;
+      const R ex = pos_err<R>(g[0], d.px, d.plx), ey = pos_err<R>(g[1], d.py, d.ply), ez = pos_err<R>(g[2], d.pz, d.plz);
+      fd = Math<R>::sqrt(ex * ex + ey * ey + ez * ez);
+    }
+    const R np = acc.periods > 0 ? R(1) / (R)acc.periods : R(0);
+    R* o = reinterpret_cast<R*>(a.metrics_out) + (size_t)i * UAVB_N_METRICS;
+    o[UAVB_M_FINAL_DIST] = fd;
+    o[UAVB_M_COLLISION] = (R)acc.collided;
+    o[UAVB_M_RMSE] = Math<R>::sqrt(acc.sum_e2 * np);
+    o[UAVB_M_MEAN_ERR] = acc.sum_e * np;
+    o[UAVB_M_MAX_ERR] = acc.max_e;
+    o[UAVB_M_STATUS] = (R)acc.status;
+    o[UAVB_M_FIRST_HIT] = (R)acc.first_hit;
+    o[UAVB_M_PERIODS] = (R)acc.periods;
+  }
+}
+
+static int check_args(const uavb_rollout_args* a, bool f64) {
+  UAVB_REQUIRE(a != nullptr, "rollout: args is NULL");
+  UAVB_REQUIRE(a->B >= 0 && a->n_ticks >= 0, "rollout: B and n_ticks must be >= 0");
+  UAVB_REQUIRE(a->inner_per_outer >= 1, "rollout: inner_per_outer must be >= 1");
+  UAVB_REQUIRE(a->seg_coeffs && a->seg_rows && a->seg_table && a->seg_yaw0, "rollout: mission segment arrays are required");
+  UAVB_REQUIRE((a->mission_seg_begin == nullptr) == (a->mission_seg_count == nullptr),
+               "rollout: mission_seg_begin and mission_seg_count must be given together");
+  UAVB_REQUIRE(a->mission_seg_begin != nullptr || a->n_seg_shared >= 1, "rollout: n_seg_shared must be >= 1 for a shared mission");
+  UAVB_REQUIRE(a->resume || a->start != nullptr, "rollout: start is required when resume = 0");
+  UAVB_REQUIRE(a->start_stride == 0 || a->start_stride == 3, "rollout: start_stride must be 0 or 3");
+  UAVB_REQUIRE(a->goal == nullptr || a->goal_stride == 0 || a->goal_stride == 3, "rollout: goal_stride must be 0 or 3");
+  UAVB_REQUIRE(!a->resume || a->carry != nullptr, "rollout: resume = 1 needs a carry block");
+  UAVB_REQUIRE(!(f64 && (a->resume || a->carry)), "rollout_f64: the fp64 validation rollout has no carry/resume");
+  UAVB_REQUIRE(a->log_stride >= 0, "rollout: log_stride must be >= 0");
+  UAVB_REQUIRE(a->log_stride == 0 || a->log_out != nullptr, "rollout: log_stride > 0 needs log_out");
+  UAVB_REQUIRE(a->n_obs >= 0 && a->n_obs <= 1024, "rollout: n_obs out of range");
+  UAVB_REQUIRE(a->n_obs == 0 || (a->aabbs != nullptr && a->n_obs_sets >= 1), "rollout: n_obs > 0 needs aabbs and n_obs_sets >= 1");
+  UAVB_REQUIRE(a->dt_outer > 0.0 && a->veh.dt > 0.0 && a->veh.mass > 0.0, "rollout: dt_outer, veh.dt and veh.mass must be positive");
+  return UAVB_OK;
+}
+
+template <class R> static int launch_rollout(const uavb_rollout_args* a, void* stream) {
+  int rc = check_args(a, sizeof(R) == 8);
+  if (rc) return rc;
+  rc = require_device();
+  if (rc) return rc;
+  if (a->B == 0) return UAVB_OK;
+  RolloutDev p;
+  p.a = *a;
+  p.dv = derive_vehicle(a->veh);
+  p.tick0 = 0;
+  const int grid = div_up(a->B, kRolloutThreads);
+  const size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->log_stride > 0)
+    rollout_kernel<R, true><<<grid, kRolloutThreads, smem, st>>>(p);
+  else
+    rollout_kernel<R, false><<<grid, kRolloutThreads, smem, st>>>(p);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+}  // namespace uavb
+
+extern "C" int uavb_rollout_f32(const uavb_rollout_args* args, void* stream) { return uavb::launch_rollout<float>(args, stream); }
+extern "C" int uavb_rollout_f64(const uavb_rollout_args* args, void* stream) { return uavb::launch_rollout<double>(args, stream); }
+extern "C" void uavb_vehicle_defaults(uavb_vehicle* veh) {
+  if (veh) uavb::vehicle_defaults(veh);
+}

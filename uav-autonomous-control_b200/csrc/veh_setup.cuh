@@ -1,0 +1,72 @@
+// veh_setup.cuh -- turn the ABI vehicle description (+ optional per-rollout Monte-Carlo overrides)
+// into the per-drone constant set of flight_core.cuh.  Derived constants are formed in fp64 and
+// rounded once.  Reference: Quad.__init__ (uav_ac/quadrotor/quad.py:36-73), motor lag response
+// 1 - exp(-dt/tau) (quad.py:102), lab_course.xml:3,8-13,100,116-119.
+#pragma once
+
+#include "flight_core.cuh"
+#include "../../include/uavb.h"
+
+namespace uavb {
+
+template <class T> struct McValues {
+  T mass;
+  T inertia[3];
+  T gains[UAVB_N_GAINS];
+  T wind[3];
+};
+
+UAVB_HD void vehicle_defaults(uavb_vehicle* v) {
+  v->g = 9.81; v->dt = 0.001;                       // lab_course.xml:3
+  v->mass = 0.5; v->inertia[0] = 0.0023; v->inertia[1] = 0.0023; v->inertia[2] = 0.0046;   // :100
+  v->arm = 0.120208; v->kf = 1.0; v->kappa = 0.016;  // :116-119, :9-10
+  v->min_thrust = 0.1; v->max_thrust = 4.5;         // :11
+  v->tau_rise = 0.0125; v->tau_fall = 0.025;        // :12
+  v->max_ascent = 3.0; v->max_descent = 2.0; v->max_speed_xy = 3.0; v->max_horiz_accel = 12.0; v->max_tilt = 0.7;  // :13
+  // quad.py:54-73: second_order_gains(tau, zeta) = (1/tau^2, 2 zeta/tau)
+  v->gains[0] = 1.0 / (0.25 * 0.25); v->gains[1] = 2.0 * 0.875 / 0.25;     // kp_xy kd_xy
+  v->gains[2] = 1.0 / (0.2 * 0.2);   v->gains[3] = 2.0 * 0.8 / 0.2;        // kp_z kd_z
+  v->gains[4] = 0.1;                                                       // ki_z
+  v->gains[5] = 1.0 / 0.07; v->gains[6] = 1.0 / 0.07; v->gains[7] = 1.0 / 0.25;   // kp_roll kp_pitch kp_yaw
+  v->gains[8] = 1.0 / 0.008; v->gains[9] = 1.0 / 0.008; v->gains[10] = 1.0 / 0.09; // kp_p kp_q kp_r
+  v->integral_limit = 10.0;                         // controller.py:10
+}
+
+template <class T> UAVB_HD void mc_from_vehicle(McValues<T>& o, const uavb_vehicle& u) {
+  o.mass = (T)u.mass;
+  for (int i = 0; i < 3; ++i) { o.inertia[i] = (T)u.inertia[i]; o.wind[i] = T(0); }
+  for (int i = 0; i < UAVB_N_GAINS; ++i) o.gains[i] = (T)u.gains[i];
+}
+
+// Motor-lag responses 1 - exp(-dt/tau) (quad.py:102) are uniform per launch: computed once on the host.
+struct VehDerived {
+  double a_rise, a_fall;
+};
+inline VehDerived derive_vehicle(const uavb_vehicle& u) {
+  VehDerived d;
+  d.a_rise = 1.0 - exp(-u.dt / u.tau_rise);
+  d.a_fall = 1.0 - exp(-u.dt / u.tau_fall);
+  return d;
+}
+
+template <class R, class T>
+UAVB_HD void make_veh(Veh<R>& v, const uavb_vehicle& u, const VehDerived& dv, const McValues<T>& o, int freq) {
+  const double mass = (double)o.mass;
+  const double Ix = (double)o.inertia[0], Iy = (double)o.inertia[1], Iz = (double)o.inertia[2];
+  v.mass = (R)mass; v.inv_mass = (R)(1.0 / mass);
+  v.Ix = (R)Ix; v.Iy = (R)Iy; v.Iz = (R)Iz;
+  v.inv_Ix = (R)(1.0 / Ix); v.inv_Iy = (R)(1.0 / Iy); v.inv_Iz = (R)(1.0 / Iz);
+  v.kp_xy = (R)o.gains[0]; v.kd_xy = (R)o.gains[1]; v.kp_z = (R)o.gains[2]; v.kd_z = (R)o.gains[3]; v.ki_z = (R)o.gains[4];
+  v.kp_roll = (R)o.gains[5]; v.kp_pitch = (R)o.gains[6]; v.kp_yaw = (R)o.gains[7];
+  v.Ikp_p = (R)(Ix * (double)o.gains[8]); v.Ikp_q = (R)(Iy * (double)o.gains[9]); v.Ikp_r = (R)(Iz * (double)o.gains[10]);
+  v.wax = (R)((double)o.wind[0] / mass); v.way = (R)((double)o.wind[1] / mass); v.waz = (R)((double)o.wind[2] / mass);
+  v.g = (R)u.g; v.dt = (R)u.dt; v.dt_outer = (R)(u.dt * freq);
+  v.arm = (R)u.arm; v.inv_arm4 = (R)(0.25 / u.arm); v.kf = (R)u.kf; v.inv_kf = (R)(1.0 / u.kf);
+  v.kappa = (R)u.kappa; v.inv_kappa4 = (R)(0.25 / u.kappa);
+  v.fmin = (R)u.min_thrust; v.fmax = (R)u.max_thrust;
+  v.a_rise = (R)dv.a_rise; v.a_fall = (R)dv.a_fall;
+  v.max_ascent = (R)u.max_ascent; v.max_descent = (R)u.max_descent; v.max_speed_xy = (R)u.max_speed_xy;
+  v.max_acc_xy = (R)u.max_horiz_accel; v.max_tilt = (R)u.max_tilt; v.integral_limit = (R)u.integral_limit;
+}
+
+}  // namespace uavb

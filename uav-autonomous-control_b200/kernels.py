@@ -1,0 +1,282 @@
+"""Tensor-level entry points over the C ABI: batched min-snap solve (K1), table geometry, sampled
+tables (K3), mission packing and the persistent closed-loop rollout (K2).
+
+Every function takes/returns CUDA tensors and enqueues on the current torch stream; nothing here
+computes on the CPU.  Reference call sites replaced are cited per function (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as nat
+
+START_END_TIME_FACTOR = 1.5  # MinimumSnap.START_END_TIME_FACTOR (uav_ac/planning/minimum_snap.py:10)
+
+
+def _dev(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise nat.UavbError("no CUDA device visible: the batched flight path has no CPU implementation")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+# ------------------------------------------------------------------------------------------ K1
+def minsnap_solve(waypoints: torch.Tensor, velocity: torch.Tensor, factor: float = START_END_TIME_FACTOR):
+    """Batched MinimumSnap._compute_spline_parameters (minimum_snap.py:138-153).
+
+    waypoints [B, S+1, 3] f64, velocity [B] f64 -> coeffs [B, 8S, 3], times [B, S], status [B] i32.
+    """
+    if waypoints.dim() != 3 or waypoints.shape[2] != 3 or waypoints.shape[1] < 2:
+        raise ValueError("waypoints must have shape (B, S+1, 3) with S >= 1")
+    B, S = waypoints.shape[0], waypoints.shape[1] - 1
+    if velocity.shape != (B,):
+        raise ValueError("velocity must have shape (B,)")
+    dev = waypoints.device
+    coeffs = torch.empty((B, 8 * S, 3), dtype=torch.float64, device=dev)
+    times = torch.empty((B, S), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    nat.check(nat.lib().uavb_minsnap_solve_f64(
+        nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(velocity, torch.float64, "velocity"), B, S, float(factor),
+        nat.ptr(coeffs), nat.ptr(times), nat.ptr(status), nat.stream_ptr(dev)), "uavb_minsnap_solve_f64")
+    return coeffs, times, status
+
+
+def minsnap_solve_ragged(waypoints: torch.Tensor, wp_offsets: torch.Tensor, velocity: torch.Tensor,
+                         factor: float = START_END_TIME_FACTOR):
+    """Ragged K1: packed waypoints [n_wp, 3], wp_offsets [B+1] i32 -> coeffs [n_seg, 8, 3], times [n_seg], status [B]."""
+    B = wp_offsets.numel() - 1
+    n_seg = waypoints.shape[0] - B
+    dev = waypoints.device
+    coeffs = torch.empty((n_seg, 8, 3), dtype=torch.float64, device=dev)
+    times = torch.empty((n_seg,), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    nat.check(nat.lib().uavb_minsnap_solve_ragged_f64(
+        nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(wp_offsets, torch.int32, "wp_offsets"),
+        nat.ptr(velocity, torch.float64, "velocity"), B, float(factor), nat.ptr(coeffs), nat.ptr(times), nat.ptr(status),
+        nat.stream_ptr(dev)), "uavb_minsnap_solve_ragged_f64")
+    return coeffs, times, status
+
+
+def table_meta(coeffs: torch.Tensor, times: torch.Tensor, seg_offsets: torch.Tensor, dt: float):
+    """Rows per segment, look-ahead yaw and total rows per table (minimum_snap.py:104, 126-136).
+
+    coeffs [n_seg, 8, 3] (or any contiguous view with 24 doubles per segment), times [n_seg],
+    seg_offsets [B+1] i32 -> rows [n_seg] i32, yaw0 [B] f64, total_rows [B] i32.
+    """
+    B = seg_offsets.numel() - 1
+    n_seg = times.numel()
+    dev = coeffs.device
+    rows = torch.empty((n_seg,), dtype=torch.int32, device=dev)
+    yaw0 = torch.empty((B,), dtype=torch.float64, device=dev)
+    total = torch.empty((B,), dtype=torch.int32, device=dev)
+    nat.check(nat.lib().uavb_minsnap_table_meta_f64(
+        nat.ptr(coeffs, torch.float64, "coeffs"), nat.ptr(times, torch.float64, "times"), nat.ptr(seg_offsets, torch.int32, "seg_offsets"),
+        B, float(dt), nat.ptr(rows), nat.ptr(yaw0), nat.ptr(total), nat.stream_ptr(dev)), "uavb_minsnap_table_meta_f64")
+    return rows, yaw0, total
+
+
+def minsnap_sample(coeffs: torch.Tensor, times: torch.Tensor, seg_offsets: torch.Tensor, seg_rows: torch.Tensor,
+                   row_offsets: torch.Tensor, dt: float) -> torch.Tensor:
+    """K3: the (N, 11) tables of MinimumSnap._generate_trajectory (minimum_snap.py:97-124), packed over missions."""
+    B = seg_offsets.numel() - 1
+    n_rows = int(row_offsets[-1].item())
+    table = torch.empty((n_rows, 11), dtype=torch.float64, device=coeffs.device)
+    nat.check(nat.lib().uavb_minsnap_sample_f64(
+        nat.ptr(coeffs, torch.float64, "coeffs"), nat.ptr(times, torch.float64, "times"), nat.ptr(seg_offsets, torch.int32, "seg_offsets"),
+        nat.ptr(seg_rows, torch.int32, "seg_rows"), nat.ptr(row_offsets, torch.int32, "row_offsets"), B, float(dt), nat.ptr(table),
+        nat.stream_ptr(coeffs.device)), "uavb_minsnap_sample_f64")
+    return table
+
+
+def table_hits(table: torch.Tensor, row_offsets: torch.Tensor, cuboid: torch.Tensor, hit_mask: torch.Tensor) -> torch.Tensor:
+    """OR into hit_mask [B] (int64 bit s) the splines with a sampled point inside `cuboid` ([6] or [B, 6])
+    -- the test of the correction loop (minimum_snap.py:84-87, 327-357)."""
+    B = row_offsets.numel() - 1
+    stride = 0 if cuboid.dim() == 1 else 6
+    nat.check(nat.lib().uavb_minsnap_table_hits_f64(
+        nat.ptr(table, torch.float64, "table"), nat.ptr(row_offsets, torch.int32, "row_offsets"), B,
+        nat.ptr(cuboid, torch.float64, "cuboid"), stride, nat.ptr(hit_mask, torch.int64, "hit_mask"), nat.stream_ptr(table.device)),
+        "uavb_minsnap_table_hits_f64")
+    return hit_mask
+
+
+# ------------------------------------------------------------------------------------------ missions
+@dataclass
+class MissionPlan:
+    """Packed mission segments in the layout K2 reads (struct uavb_rollout_args, include/uavb.h)."""
+    seg_coeffs: torch.Tensor           # [n_seg, 8, 3] f64, MinimumSnap.coeffs rows per spline
+    seg_rows: torch.Tensor             # [n_seg] i32
+    seg_table: torch.Tensor            # [n_seg] i32, 1 where a MinimumSnap table starts
+    seg_yaw0: torch.Tensor             # [n_seg] f64
+    dt: float                          # table sampling period (quad.dt * frequency, main.py:97)
+    n_seg_shared: int = 0              # > 0: every rollout flies segments [0, n_seg_shared)
+    seg_begin: Optional[torch.Tensor] = None   # [B] i32 per-rollout missions
+    seg_count: Optional[torch.Tensor] = None   # [B] i32
+    total_rows: Optional[torch.Tensor] = None  # [n_missions] i32 table rows of each mission
+    times: Optional[torch.Tensor] = None       # [n_seg] f64 (MinimumSnap.times)
+
+    @property
+    def shared(self) -> bool:
+        return self.seg_begin is None
+
+
+def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float, shared: bool = False,
+                  factor: float = START_END_TIME_FACTOR) -> MissionPlan:
+    """Solve and pack missions made of consecutive MinimumSnap tables.
+
+    ``tables`` lists (waypoints [B, S_k+1, 3], velocity [B]) per table, e.g. the vertical take-off
+    (S=1) followed by the course of ``_generate_mission_trajectory`` (uav_ac/main.py:73-84).  Mission b
+    flies table 0 then table 1 ...; each table keeps its own yaw hold like the reference, where the
+    two MinimumSnap instances are independent.  ``shared=True`` requires B == 1 and lets every
+    rollout fly the same mission (BASELINE configs[2]).
+    """
+    B = tables[0][0].shape[0]
+    dev = tables[0][0].device
+    per_table = []
+    for wp, vel in tables:
+        if wp.shape[0] != B:
+            raise ValueError("all tables must have the same batch size")
+        S = wp.shape[1] - 1
+        coeffs, times, _ = minsnap_solve(wp, vel, factor)
+        offs = torch.arange(B + 1, dtype=torch.int32, device=dev) * S
+        rows, yaw0, total = table_meta(coeffs, times.reshape(-1), offs, dt)
+        flag = torch.zeros((B, S), dtype=torch.int32, device=dev)
+        flag[:, 0] = 1
+        y0 = torch.zeros((B, S), dtype=torch.float64, device=dev)
+        y0[:, 0] = yaw0
+        per_table.append((coeffs.reshape(B, S, 8, 3), rows.reshape(B, S), flag, y0, total, times))
+    seg_coeffs = torch.cat([t[0] for t in per_table], dim=1).contiguous()
+    seg_rows = torch.cat([t[1] for t in per_table], dim=1).contiguous()
+    seg_table = torch.cat([t[2] for t in per_table], dim=1).contiguous()
+    seg_yaw0 = torch.cat([t[3] for t in per_table], dim=1).contiguous()
+    times = torch.cat([t[5] for t in per_table], dim=1).contiguous()
+    total = sum(t[4] for t in per_table)
+    n_per = seg_rows.shape[1]
+    plan = MissionPlan(seg_coeffs.reshape(-1, 8, 3), seg_rows.reshape(-1), seg_table.reshape(-1), seg_yaw0.reshape(-1), float(dt),
+                       total_rows=total.to(torch.int32), times=times.reshape(-1))
+    if shared:
+        if B != 1:
+            raise ValueError("shared=True needs a single mission")
+        plan.n_seg_shared = n_per
+    else:
+        plan.seg_begin = torch.arange(B, dtype=torch.int32, device=dev) * n_per
+        plan.seg_count = torch.full((B,), n_per, dtype=torch.int32, device=dev)
+    return plan
+
+
+# ------------------------------------------------------------------------------------------ K2
+@dataclass
+class RolloutResult:
+    metrics: Optional[torch.Tensor]    # [B, 8]: final_dist, collision, rmse, mean_err, max_err, status, first_hit, periods
+    state: Optional[torch.Tensor]      # [13, B] final X (SoA)
+    log: Optional[torch.Tensor]        # [n_samples, 13, B]
+    carry: Optional[torch.Tensor]      # [48, B] resumable block
+    n_ticks: int = 0
+
+
+def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goal: Optional[torch.Tensor] = None,
+            vehicle: Optional[nat.Vehicle] = None, frequency: int = 10, mc_mass: Optional[torch.Tensor] = None,
+            mc_inertia: Optional[torch.Tensor] = None, mc_gains: Optional[torch.Tensor] = None, mc_wind: Optional[torch.Tensor] = None,
+            obstacles: Optional[torch.Tensor] = None, obstacle_set: Optional[torch.Tensor] = None, thrust_frame_lag: int = 1,
+            log_stride: int = 0, carry: Optional[torch.Tensor] = None, resume: bool = False, want_state: bool = True,
+            want_metrics: bool = True, want_carry: bool = False, dtype: torch.dtype = torch.float32, index_base: int = 0,
+            out: Optional[RolloutResult] = None) -> RolloutResult:
+    """n_ticks ticks of `trajectory_controller.step(); simulation.step()` for B drones
+    (tests/integration/test_mujoco_trajectory_tracking.py:27-31) in one persistent kernel launch.
+
+    start / goal: [3] or [B, 3] f64.  mc_mass [B], mc_inertia [3, B], mc_gains [11, B], mc_wind [3, B] f32 (SoA).
+    obstacles: [n_obs, 6] (shared) or [n_sets, n_obs, 6] f32 with obstacle_set [B] i32.
+    dtype float64 selects the validation kernel (outputs f64, no carry).
+    """
+    dev = plan.seg_coeffs.device
+    f64 = dtype == torch.float64
+    odt = torch.float64 if f64 else torch.float32
+    a = nat.RolloutArgs()
+    a.B, a.n_ticks, a.inner_per_outer = int(B), int(n_ticks), int(frequency)
+    a.thrust_frame_lag, a.resume, a.log_stride = int(thrust_frame_lag), int(bool(resume)), int(log_stride)
+    a.index_base = int(index_base)
+    a.veh = vehicle if vehicle is not None else nat.default_vehicle()
+    a.mc_mass = nat.ptr(mc_mass, torch.float32, "mc_mass")
+    a.mc_inertia = nat.ptr(mc_inertia, torch.float32, "mc_inertia")
+    a.mc_gains = nat.ptr(mc_gains, torch.float32, "mc_gains")
+    a.mc_wind = nat.ptr(mc_wind, torch.float32, "mc_wind")
+    for name, t, shape in (("mc_mass", mc_mass, (B,)), ("mc_inertia", mc_inertia, (3, B)), ("mc_gains", mc_gains, (nat.N_GAINS, B)),
+                           ("mc_wind", mc_wind, (3, B))):
+        if t is not None and tuple(t.shape) != shape:
+            raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+    a.seg_coeffs = nat.ptr(plan.seg_coeffs, torch.float64, "seg_coeffs")
+    a.seg_rows = nat.ptr(plan.seg_rows, torch.int32, "seg_rows")
+    a.seg_table = nat.ptr(plan.seg_table, torch.int32, "seg_table")
+    a.seg_yaw0 = nat.ptr(plan.seg_yaw0, torch.float64, "seg_yaw0")
+    if plan.shared:
+        a.n_seg_shared = int(plan.n_seg_shared)
+    else:
+        if plan.seg_begin.numel() != B:
+            raise ValueError("plan holds per-rollout missions for a different batch size")
+        a.mission_seg_begin = nat.ptr(plan.seg_begin, torch.int32, "seg_begin")
+        a.mission_seg_count = nat.ptr(plan.seg_count, torch.int32, "seg_count")
+    a.dt_outer = float(plan.dt)
+    a.start = nat.ptr(start, torch.float64, "start")
+    a.start_stride = 0 if start.dim() == 1 else 3
+    if goal is not None:
+        a.goal = nat.ptr(goal, torch.float64, "goal")
+        a.goal_stride = 0 if goal.dim() == 1 else 3
+    keep = [start, goal]
+    if obstacles is not None and obstacles.numel() > 0:
+        obs = obstacles if obstacles.dim() == 3 else obstacles.unsqueeze(0)
+        obs = obs.to(torch.float32).contiguous()
+        keep.append(obs)
+        a.n_obs_sets, a.n_obs = int(obs.shape[0]), int(obs.shape[1])
+        a.aabbs = nat.ptr(obs, torch.float32, "obstacles")
+        if obstacle_set is not None:
+            a.aabb_set = nat.ptr(obstacle_set, torch.int32, "obstacle_set")
+        elif obs.shape[0] != 1:
+            raise ValueError("several obstacle sets need obstacle_set")
+    res = out if out is not None else RolloutResult(None, None, None, None)
+    res.n_ticks = int(n_ticks)
+    if want_metrics and res.metrics is None:
+        res.metrics = torch.empty((B, nat.N_METRICS), dtype=odt, device=dev)
+    if want_state and res.state is None:
+        res.state = torch.empty((nat.STATE_DIM, B), dtype=odt, device=dev)
+    if log_stride > 0 and res.log is None:
+        res.log = torch.empty((n_ticks // log_stride, nat.STATE_DIM, B), dtype=odt, device=dev)
+    if resume:
+        if carry is None:
+            raise ValueError("resume=True needs the carry block of the previous launch")
+        res.carry = carry
+    elif (want_carry or carry is not None) and not f64:
+        res.carry = carry if carry is not None else torch.empty((nat.CARRY_WORDS, B), dtype=torch.float32, device=dev)
+    a.carry = nat.ptr(res.carry, torch.float32, "carry")
+    a.state_out = nat.ptr(res.state if want_state else None)
+    a.metrics_out = nat.ptr(res.metrics if want_metrics else None)
+    a.log_out = nat.ptr(res.log if log_stride > 0 else None)
+    fn = nat.lib().uavb_rollout_f64 if f64 else nat.lib().uavb_rollout_f32
+    nat.check(fn(ctypes.byref(a), nat.stream_ptr(dev)), "uavb_rollout_f64" if f64 else "uavb_rollout_f32")
+    return res
+
+
+# ------------------------------------------------------------------------------------------ Monte-Carlo inputs
+def mc_uniform(seed: int, B: int, lo: Sequence[float], hi: Sequence[float], *, index_base: int = 0, stream_id: int = 0,
+               device=None) -> torch.Tensor:
+    """[n_fields, B] f32 with field k uniform in (lo[k], hi[k]); Philox keyed by (seed, global index)."""
+    dev = _dev(device)
+    lo_t = torch.tensor(list(lo), dtype=torch.float32, device=dev)
+    hi_t = torch.tensor(list(hi), dtype=torch.float32, device=dev)
+    out = torch.empty((lo_t.numel(), B), dtype=torch.float32, device=dev)
+    nat.check(nat.lib().uavb_mc_uniform_f32(int(seed), int(index_base), int(stream_id), int(B), int(lo_t.numel()), nat.ptr(lo_t), nat.ptr(hi_t),
+                                            nat.ptr(out), nat.stream_ptr(dev)), "uavb_mc_uniform_f32")
+    return out
+
+
+def mc_missions(seed: int, B: int, S: int = 4, *, index_base: int = 0, device=None):
+    """BASELINE configs[1] generator on the device: waypoints [B, S+1, 3] f64, velocity [B] f64."""
+    dev = _dev(device)
+    wp = torch.empty((B, S + 1, 3), dtype=torch.float64, device=dev)
+    vel = torch.empty((B,), dtype=torch.float64, device=dev)
+    nat.check(nat.lib().uavb_mc_missions_f64(int(seed), int(index_base), int(B), int(S), nat.ptr(wp), nat.ptr(vel), nat.stream_ptr(dev)),
+              "uavb_mc_missions_f64")
+    return wp, vel
