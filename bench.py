@@ -147,7 +147,7 @@ class ClockSampler:
     def start(self):
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
