@@ -41,7 +41,7 @@ extern "C" {
 #define UAVB_STATE_DIM  13          /* quad.py:75-80 */
 #define UAVB_N_GAINS    11          /* kp_xy kd_xy kp_z kd_z ki_z kp_roll kp_pitch kp_yaw kp_p kp_q kp_r (quad.py:65-73) */
 #define UAVB_N_METRICS   8
-#define UAVB_CARRY_WORDS 48         /* 32-bit words per rollout in the resumable carry block */
+#define UAVB_CARRY_WORDS 52         /* 32-bit words per rollout in the resumable carry block */
 #define UAVB_MAX_SPLINES 64         /* upper bound on splines per mission accepted by the solver */
 
 /* per-mission solver status (status_out of uavb_minsnap_solve_f64) */

@@ -20,7 +20,7 @@ template <class R> struct VecLog {
   void tick(const Drone<R>& d) {
     if (--left) return;
     left = stride;
-    double x[17] = {(double)d.px + (double)d.plx, (double)d.py + (double)d.ply, (double)d.pz + (double)d.plz,
+    double x[17] = {d.px + (double)d.dx, d.py + (double)d.dy, d.pz + (double)d.dz,
                     (double)d.q0, (double)d.q1, (double)d.q2, (double)d.q3, (double)d.vx, (double)d.vy, (double)d.vz,
                     (double)d.wx, (double)d.wy, (double)d.wz, (double)d.om0, (double)d.om1, (double)d.om2, (double)d.om3};
     out->insert(out->end(), x, x + 17);
@@ -46,20 +46,22 @@ template <class R> int run(const char* in, const char* outp) {
   fclose(f);
   uavb_vehicle uv;
   vehicle_defaults(&uv);
-  McValues<double> o;
+  McValues o;
   o.mass = uv.mass * mc[0];
   for (int i = 0; i < 3; ++i) o.inertia[i] = uv.inertia[i] * mc[1 + i];
   for (int i = 0; i < 11; ++i) o.gains[i] = uv.gains[i] * mc[4 + i];
   for (int i = 0; i < 3; ++i) o.wind[i] = mc[15 + i];
-  Veh<R> v;
-  make_veh<R>(v, uv, derive_vehicle(uv), o, 10);
+  VehU<R> u;
+  make_vehu<R>(u, uv, uv.dt * 10);
+  VehP<R> v;
+  make_vehp<R>(v, uv, o);
   MissionView m{coeffs.data(), rows.data(), table.data(), yaw0.data(), 0, n_seg, uv.dt * 10};
   Drone<R> d; Cursor<R> c; Accum<R> a;
-  drone_init<R>(d, start[0], start[1], start[2]); cursor_init<R>(c); accum_init<R>(a);
+  drone_init<R>(d, u, start[0], start[1], start[2]); cursor_init<R>(c); accum_init<R>(a);
   std::vector<double> log;
   VecLog<R> lg{&log, 10, 10};
   NoObstacles no;
-  rollout_run<R>(d, c, a, v, m, 0, n_ticks, 10, lag, no, lg);
+  rollout_run<R>(d, c, a, u, v, m, 0, n_ticks, 10, lag, no, lg);
   FILE* g = fopen(outp, "wb");
   fwrite(log.data(), 8, log.size(), g);
   fclose(g);

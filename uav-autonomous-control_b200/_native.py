@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libuavb.so")
 
 N_GAINS = 11
 N_METRICS = 8
-CARRY_WORDS = 48
+CARRY_WORDS = 52
 STATE_DIM = 13
 MAX_SPLINES = 64
 GAIN_NAMES = ("kp_xy", "kd_xy", "kp_z", "kd_z", "ki_z", "kp_roll", "kp_pitch", "kp_yaw", "kp_p", "kp_q", "kp_r")

@@ -12,9 +12,17 @@
 // The type parameter R is the state/arithmetic type: float for the production rollout, double for
 // the validation build.  In float mode three things keep the closed loop within 1e-4 m of an fp64
 // run over 16k ticks (DESIGN.md "fp32 budget"):
-//   * position is carried as an unevaluated sum hi+lo and advanced with a compensated add;
+//   * position is carried in fp64 and advanced once per outer period; inside the period the 1 kHz
+//     ticks accumulate the displacement since the last fold in an fp32 register triple (|d| < 0.1 m,
+//     so its rounding is ~1e-9 m per tick instead of 1e-6 m at |p| ~ 20 m);
 //   * set-points come from fp64 Horner evaluation and position errors are formed in fp64;
 //   * the quaternion is advanced by adding q*(dq-1), so only the final add rounds at 1 ulp of q.
+//
+// Instruction diet of the 1 kHz body (DESIGN.md "K2 optimisation log"): per-launch constants live in
+// the kernel parameter block (constant-bank operands, no registers), products of constants are
+// folded on the host (kf dt/m, dt/I, arm kf ...), the gyroscopic term uses the diagonal-inertia
+// identity w x (I w) = ((Iz-Iy) wy wz, (Ix-Iz) wz wx, (Iy-Ix) wx wy), the allocation takes a
+// division-free path whenever no rotor limit binds, sqrt/rcp/rsqrt are single MUFU instructions.
 #pragma once
 
 #include <math.h>
@@ -33,20 +41,36 @@ constexpr double kPi = 3.141592653589793238462643383279;
 template <class R> struct Math;
 template <> struct Math<float> {
   static UAVB_HD float sqrt(float x) { return sqrtf(x); }
+  // single-MUFU forms (max relative error 2^-23 .. 2^-22, PTX ISA "sqrt.approx / rcp.approx / rsqrt.approx")
+  static UAVB_HD float sqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+  }
+  static UAVB_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+  }
   static UAVB_HD float rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 #else
     return 1.0f / sqrtf(x);
 #endif
   }
-  static UAVB_HD float div(float a, float b) {
-#if defined(__CUDA_ARCH__)
-    return __fdividef(a, b);
-#else
-    return a / b;
-#endif
-  }
+  static UAVB_HD float div(float a, float b) { return a * rcp_fast(b); }
+  static UAVB_HD float fma(float a, float b, float c) { return fmaf(a, b, c); }
   static UAVB_HD float atan2(float y, float x) { return atan2f(y, x); }
   static UAVB_HD void sincos(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
@@ -55,7 +79,6 @@ template <> struct Math<float> {
     *s = sinf(x); *c = cosf(x);
 #endif
   }
-  static UAVB_HD float rint(float x) { return rintf(x); }
   static UAVB_HD float floor(float x) { return floorf(x); }
   static UAVB_HD float abs(float x) { return fabsf(x); }
   static UAVB_HD float fmin(float a, float b) { return fminf(a, b); }
@@ -64,11 +87,13 @@ template <> struct Math<float> {
 };
 template <> struct Math<double> {
   static UAVB_HD double sqrt(double x) { return ::sqrt(x); }
+  static UAVB_HD double sqrt_fast(double x) { return ::sqrt(x); }
+  static UAVB_HD double rcp_fast(double x) { return 1.0 / x; }
   static UAVB_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   static UAVB_HD double div(double a, double b) { return a / b; }
+  static UAVB_HD double fma(double a, double b, double c) { return ::fma(a, b, c); }
   static UAVB_HD double atan2(double y, double x) { return ::atan2(y, x); }
   static UAVB_HD void sincos(double x, double* s, double* c) { *s = ::sin(x); *c = ::cos(x); }
-  static UAVB_HD double rint(double x) { return ::rint(x); }
   static UAVB_HD double floor(double x) { return ::floor(x); }
   static UAVB_HD double abs(double x) { return ::fabs(x); }
   static UAVB_HD double fmin(double a, double b) { return ::fmin(a, b); }
@@ -78,32 +103,40 @@ template <> struct Math<double> {
 
 template <class R> UAVB_HD R clampr(R x, R lo, R hi) { return Math<R>::fmin(Math<R>::fmax(x, lo), hi); }
 
-// Per-drone constants.  Fields above the marker may differ between rollouts (Monte-Carlo); the rest
-// is uniform across a launch.
-template <class R> struct Veh {
-  // per rollout
-  R mass, inv_mass;
-  R Ix, Iy, Iz, inv_Ix, inv_Iy, inv_Iz;
-  R Ikp_p, Ikp_q, Ikp_r;            // I * kp of the body-rate loop (controller.py:128)
-  R kp_xy, kd_xy, kp_z, kd_z, ki_z, kp_roll, kp_pitch, kp_yaw;
-  R wax, way, waz;                  // wind force / mass (extension; zero for reference runs)
-  // uniform
-  R g, dt, dt_outer;
-  R arm, inv_arm4, kf, inv_kf, kappa, inv_kappa4;   // inv_*4 = 1/(4 x): mixer division by 4 folded in (quad.py:112)
-  R fmin, fmax, a_rise, a_fall;
+// Constants that are uniform across a launch.  The rollout kernel receives this struct by value in
+// its parameter block, so every field is a constant-bank operand.
+template <class R> struct VehU {
+  R dt, half_dt, dt_outer, g;
+  R kf, inv_kf, arm_kf, kappa_kf;                  // arm*kf, kappa*kf: torque per unit of summed w^2
+  R inv_arm4, inv_kappa4;                          // 1/(4 arm), 1/(4 kappa): mixer division by 4 folded in (quad.py:112)
+  R fmin, fmax, fmin4, fmax4, a_rise, a_fall;      // a_* = 1 - exp(-dt/tau) (quad.py:102)
   R max_ascent, max_descent, max_speed_xy, max_acc_xy, max_tilt, integral_limit;
+};
+
+// Constants that differ between rollouts under Monte-Carlo perturbation (uniform otherwise).
+template <class R> struct VehP {
+  // 1 kHz body
+  R kf_dt_over_m;                                  // kf dt / m: velocity gained per unit of summed w^2
+  R dIx, dIy, dIz;                                 // Iz-Iy, Ix-Iz, Iy-Ix (gyroscopic term, diagonal inertia)
+  R Ikp_p, Ikp_q, Ikp_r;                           // I * kp of the body-rate loop (controller.py:128)
+  R dt_invIx, dt_invIy, dt_invIz;                  // dt / I
+  R dvx, dvy, dvz;                                 // dt * (wind/m + g e_z): velocity gained per tick without thrust
+  // 100 Hz outer loop
+  R mass, kp_xy, kd_xy, kp_z, kd_z, ki_z, kp_roll, kp_pitch, kp_yaw;
+  R acc_max;                                       // bound on |acceleration| (4 fmax/m + g + |wind|/m): obstacle culling
 };
 
 // Persistent per-drone state (registers across the whole rollout).
 template <class R> struct Drone {
-  R px, py, pz;        // position (hi part)
-  R plx, ply, plz;     // position low-order part (float mode; always 0 in double mode)
+  double px, py, pz;   // position at the last fold (start of the current outer period)
+  R dx, dy, dz;        // displacement accumulated since the last fold
   R q0, q1, q2, q3;    // attitude, scalar first, FRD->NED
   R vx, vy, vz;        // world velocity
   R wx, wy, wz;        // body rates p q r
   R om0, om1, om2, om3;  // rotor speeds (quad.py:85)
   R integral;          // altitude integrator (controller.py:20)
   R thrust_cmd;        // main.py:26
+  R coll;              // clip(thrust_cmd, 4 fmin, 4 fmax) / 4 (quad.py:107,113), refreshed with thrust_cmd
   R pc, qc, rc;        // pqr_cmd (main.py:27)
   R zbx, zby, zbz;     // thrust direction MuJoCo last computed (stale body z axis)
 };
@@ -114,15 +147,27 @@ struct Target {
   double yaw;
 };
 
-// Third column of R(q) for a normalised quaternion (quad.py:153): body z axis in the world frame.
-template <class R> UAVB_HD void body_z(const Drone<R>& d, R* zx, R* zy, R* zz) {
-  *zx = R(2) * (d.q1 * d.q3 + d.q0 * d.q2);
-  *zy = R(2) * (d.q2 * d.q3 - d.q0 * d.q1);
-  *zz = R(1) - R(2) * (d.q1 * d.q1 + d.q2 * d.q2);
+template <class R> UAVB_HD void set_thrust_cmd(Drone<R>& d, const VehU<R>& u, R c) {
+  d.thrust_cmd = c;
+  d.coll = R(0.25) * clampr<R>(c, u.fmin4, u.fmax4);
 }
 
-// Position error p_des - p formed in fp64 from the hi+lo pair, then rounded once.
-template <class R> UAVB_HD R pos_err(double des, R hi, R lo) { return (R)((des - (double)hi) - (double)lo); }
+// Fold the displacement into the fp64 position (done at outer-period boundaries).
+template <class R> UAVB_HD void fold_position(Drone<R>& d) {
+  d.px += (double)d.dx; d.py += (double)d.dy; d.pz += (double)d.dz;
+  d.dx = d.dy = d.dz = R(0);
+}
+
+// Third column of R(q) for a normalised quaternion (quad.py:153): body z axis in the world frame.
+template <class R> UAVB_HD void body_z(const Drone<R>& d, R* zx, R* zy, R* zz) {
+  typedef Math<R> M;
+  const R a = M::fma(d.q1, d.q3, d.q0 * d.q2);
+  const R b = M::fma(d.q2, d.q3, -(d.q0 * d.q1));
+  const R c = M::fma(d.q1, d.q1, d.q2 * d.q2);
+  *zx = a + a;
+  *zy = b + b;
+  *zz = M::fma(R(-2), c, R(1));
+}
 
 // yaw error: wrap_to_pi(wrap_to_2pi(psi_des) - psi) (controller.py:164-165, :170-178).  Python's %
 // is a floored modulo, reproduced with floor().
@@ -136,42 +181,43 @@ template <class R> UAVB_HD R yaw_error(R psi_des, R psi) {
 
 // ---------------------------------------------------------------------------------------------
 // Outer loop: TrajectoryController._update_outer_loop (main.py:47-61) on the fresh state.
-template <class R> UAVB_HD void outer_update(Drone<R>& d, const Veh<R>& v, const Target& t) {
+// Requires a folded position (d.dx = d.dy = d.dz = 0).
+template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, const Target& t) {
   typedef Math<R> M;
   const R q0 = d.q0, q1 = d.q1, q2 = d.q2, q3 = d.q3;
   // quad.py:153 for a unit quaternion (the state is re-normalised every tick)
   const R R00 = R(1) - R(2) * (q2 * q2 + q3 * q3), R01 = R(2) * (q1 * q2 - q0 * q3), R02 = R(2) * (q1 * q3 + q0 * q2);
   const R R10 = R(2) * (q1 * q2 + q0 * q3), R11 = R(1) - R(2) * (q1 * q1 + q3 * q3), R12 = R(2) * (q2 * q3 - q0 * q1);
   const R R22 = R(1) - R(2) * (q1 * q1 + q2 * q2);
-  const R inv_R22 = R(1) / R22;
+  const R inv_R22 = M::rcp_fast(R22);
 
-  // altitude (controller.py:26-56)
-  const R climb = clampr<R>((R)t.vz, -v.max_ascent, v.max_descent);
-  const R ez = pos_err<R>(t.z, d.pz, d.plz);
+  // altitude (controller.py:26-56); position errors are formed in fp64 and rounded once
+  const R climb = clampr<R>((R)t.vz, -u.max_ascent, u.max_descent);
+  const R ez = (R)(t.z - d.pz);
   const R ezd = climb - d.vz;
-  d.integral = clampr<R>(d.integral + ez * v.dt_outer, -v.integral_limit, v.integral_limit);
-  R acc_z = v.kp_z * ez + v.ki_z * d.integral + v.kd_z * ezd + (R)t.az - v.g;
+  d.integral = clampr<R>(d.integral + ez * u.dt_outer, -u.integral_limit, u.integral_limit);
+  R acc_z = v.kp_z * ez + v.ki_z * d.integral + v.kd_z * ezd + (R)t.az - u.g;
   acc_z = acc_z * inv_R22;
-  const R c = clampr<R>(-v.mass * acc_z, R(4) * v.fmin, R(4) * v.fmax);
-  d.thrust_cmd = c;
+  const R c = clampr<R>(-v.mass * acc_z, u.fmin4, u.fmax4);
+  set_thrust_cmd<R>(d, u, c);
 
   // lateral (controller.py:58-97)
   R vxd = (R)t.vx, vyd = (R)t.vy;
-  const R vmag = M::sqrt(vxd * vxd + vyd * vyd);
-  if (vmag > v.max_speed_xy) {
-    const R s = v.max_speed_xy / vmag;
+  const R vm2 = vxd * vxd + vyd * vyd;
+  if (vm2 > u.max_speed_xy * u.max_speed_xy) {
+    const R s = u.max_speed_xy * M::rsqrt(vm2);
     vxd *= s; vyd *= s;
   }
-  R ax = v.kp_xy * pos_err<R>(t.x, d.px, d.plx) + v.kd_xy * (vxd - d.vx) + (R)t.ax;
-  R ay = v.kp_xy * pos_err<R>(t.y, d.py, d.ply) + v.kd_xy * (vyd - d.vy) + (R)t.ay;
-  const R amag = M::sqrt(ax * ax + ay * ay);
-  if (amag > v.max_acc_xy) {
-    const R s = v.max_acc_xy / amag;
+  R ax = v.kp_xy * (R)(t.x - d.px) + v.kd_xy * (vxd - d.vx) + (R)t.ax;
+  R ay = v.kp_xy * (R)(t.y - d.py) + v.kd_xy * (vyd - d.vy) + (R)t.ay;
+  const R am2 = ax * ax + ay * ay;
+  if (am2 > u.max_acc_xy * u.max_acc_xy) {
+    const R s = u.max_acc_xy * M::rsqrt(am2);
     ax *= s; ay *= s;
   }
-  const R inv_accz = -v.mass / c;                 // 1 / (-c/m)
-  const R bx = clampr<R>(ax * inv_accz, -v.max_tilt, v.max_tilt);
-  const R by = clampr<R>(ay * inv_accz, -v.max_tilt, v.max_tilt);
+  const R inv_accz = -v.mass * M::rcp_fast(c);    // 1 / (-c/m)
+  const R bx = clampr<R>(ax * inv_accz, -u.max_tilt, u.max_tilt);
+  const R by = clampr<R>(ay * inv_accz, -u.max_tilt, u.max_tilt);
 
   // roll / pitch rates (controller.py:132-154)
   const R bdx = v.kp_roll * (bx - R02);
@@ -185,10 +231,10 @@ template <class R> UAVB_HD void outer_update(Drone<R>& d, const Veh<R>& v, const
   const R ih = M::rsqrt(sa * sa + R22 * R22);
   const R sin_phi = sa * ih, cos_phi = R22 * ih;
   const R sin_th = clampr<R>(R(2) * (q0 * q2 - q3 * q1), R(-1), R(1));
-  const R cos_th = M::sqrt(R(1) - sin_th * sin_th);
+  const R cos_th = M::sqrt_fast(R(1) - sin_th * sin_th);
   const R psi = M::atan2(R(2) * (q0 * q3 + q1 * q2), R(1) - R(2) * (q2 * q2 + q3 * q3));
   const R e_yaw = yaw_error<R>((R)t.yaw, psi);
-  const R r_c = (v.kp_yaw * e_yaw * cos_th - q_c * sin_phi) / cos_phi;
+  const R r_c = (v.kp_yaw * e_yaw * cos_th - q_c * sin_phi) * M::rcp_fast(cos_phi);
 
   d.pc = p_c; d.qc = q_c; d.rc = r_c;
 }
@@ -197,82 +243,75 @@ template <class R> UAVB_HD void outer_update(Drone<R>& d, const Veh<R>& v, const
 // Inner loop, part 1: body-rate controller + allocation + motor lag (main.py:42-44).
 // Returns the gyroscopic term w x (I w) of the CURRENT state, which the physics step reuses.
 template <class R>
-UAVB_HD void inner_control(Drone<R>& d, const Veh<R>& v, R* gx, R* gy, R* gz, R* moment_out, R* forces_out) {
+UAVB_HD void inner_control(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R* gx, R* gy, R* gz, R* moment_out, R* forces_out) {
   typedef Math<R> M;
-  // controller.py:115-130
-  const R Iwx = v.Ix * d.wx, Iwy = v.Iy * d.wy, Iwz = v.Iz * d.wz;
-  *gx = d.wy * Iwz - d.wz * Iwy;
-  *gy = d.wz * Iwx - d.wx * Iwz;
-  *gz = d.wx * Iwy - d.wy * Iwx;
-  const R Mx = v.Ikp_p * (d.pc - d.wx) + *gx;
-  const R My = v.Ikp_q * (d.qc - d.wy) + *gy;
-  const R Mz = v.Ikp_r * (d.rc - d.wz) + *gz;
-  // quad.py:105-122
-  const R c_bar = clampr<R>(d.thrust_cmd, R(4) * v.fmin, R(4) * v.fmax);
-  const R coll = R(0.25) * c_bar;
-  const R pb = Mx * v.inv_arm4, qb = My * v.inv_arm4, rb = -Mz * v.inv_kappa4;
-  const R m0 = pb + qb + rb, m1 = qb - pb - rb, m2 = rb - pb - qb, m3 = pb - qb - rb;
-  const R room_hi = v.fmax - coll, room_lo = v.fmin - coll;
-  R s = R(1);
-  {
+  // controller.py:115-130; diagonal inertia => w x (I w) = (dIx wy wz, dIy wz wx, dIz wx wy)
+  const R gx_ = v.dIx * (d.wy * d.wz), gy_ = v.dIy * (d.wz * d.wx), gz_ = v.dIz * (d.wx * d.wy);
+  *gx = gx_; *gy = gy_; *gz = gz_;
+  const R Mx = M::fma(v.Ikp_p, d.pc - d.wx, gx_);
+  const R My = M::fma(v.Ikp_q, d.qc - d.wy, gy_);
+  const R Mz = M::fma(v.Ikp_r, d.rc - d.wz, gz_);
+  // quad.py:105-122: mixer rows (+,+,+) (-,+,-) (-,-,+) (+,-,-) on [p_bar q_bar r_bar] / 4
+  const R coll = d.coll;
+  const R pb = Mx * u.inv_arm4, qb = My * u.inv_arm4, rb = -Mz * u.inv_kappa4;
+  const R s1 = pb + qb, s2 = pb - qb;
+  const R m0 = s1 + rb, m1 = -(s2 + rb), m2 = rb - s1, m3 = s2 - rb;
+  const R room_hi = u.fmax - coll, room_lo = u.fmin - coll;
+  const R m_hi = M::fmax(M::fmax(m0, m1), M::fmax(m2, m3)), m_lo = M::fmin(M::fmin(m0, m1), M::fmin(m2, m3));
+  R f0, f1, f2, f3;
+  if (m_hi <= room_hi && m_lo >= room_lo) {
+    // no rotor limit binds: every ratio of quad.py:116-119 is >= 1, the scale is 1 and the final clip is the identity
+    f0 = coll + m0; f1 = coll + m1; f2 = coll + m2; f3 = coll + m3;
+  } else {
     const R l0 = (m0 > R(0)) ? M::div(room_hi, m0) : ((m0 < R(0)) ? M::div(room_lo, m0) : R(1));
     const R l1 = (m1 > R(0)) ? M::div(room_hi, m1) : ((m1 < R(0)) ? M::div(room_lo, m1) : R(1));
     const R l2 = (m2 > R(0)) ? M::div(room_hi, m2) : ((m2 < R(0)) ? M::div(room_lo, m2) : R(1));
     const R l3 = (m3 > R(0)) ? M::div(room_hi, m3) : ((m3 < R(0)) ? M::div(room_lo, m3) : R(1));
-    s = clampr<R>(M::fmin(M::fmin(l0, l1), M::fmin(l2, l3)), R(0), R(1));
+    const R s = clampr<R>(M::fmin(M::fmin(l0, l1), M::fmin(l2, l3)), R(0), R(1));
+    f0 = clampr<R>(M::fma(s, m0, coll), u.fmin, u.fmax);
+    f1 = clampr<R>(M::fma(s, m1, coll), u.fmin, u.fmax);
+    f2 = clampr<R>(M::fma(s, m2, coll), u.fmin, u.fmax);
+    f3 = clampr<R>(M::fma(s, m3, coll), u.fmin, u.fmax);
   }
-  const R f0 = clampr<R>(coll + s * m0, v.fmin, v.fmax);
-  const R f1 = clampr<R>(coll + s * m1, v.fmin, v.fmax);
-  const R f2 = clampr<R>(coll + s * m2, v.fmin, v.fmax);
-  const R f3 = clampr<R>(coll + s * m3, v.fmin, v.fmax);
   // quad.py:88-103
-  const R c0 = M::sqrt(f0 * v.inv_kf), c1 = M::sqrt(f1 * v.inv_kf), c2 = M::sqrt(f2 * v.inv_kf), c3 = M::sqrt(f3 * v.inv_kf);
-  d.om0 += ((c0 > d.om0) ? v.a_rise : v.a_fall) * (c0 - d.om0);
-  d.om1 += ((c1 > d.om1) ? v.a_rise : v.a_fall) * (c1 - d.om1);
-  d.om2 += ((c2 > d.om2) ? v.a_rise : v.a_fall) * (c2 - d.om2);
-  d.om3 += ((c3 > d.om3) ? v.a_rise : v.a_fall) * (c3 - d.om3);
+  const R c0 = M::sqrt_fast(f0 * u.inv_kf), c1 = M::sqrt_fast(f1 * u.inv_kf), c2 = M::sqrt_fast(f2 * u.inv_kf), c3 = M::sqrt_fast(f3 * u.inv_kf);
+  d.om0 = M::fma((c0 > d.om0) ? u.a_rise : u.a_fall, c0 - d.om0, d.om0);
+  d.om1 = M::fma((c1 > d.om1) ? u.a_rise : u.a_fall, c1 - d.om1, d.om1);
+  d.om2 = M::fma((c2 > d.om2) ? u.a_rise : u.a_fall, c2 - d.om2, d.om2);
+  d.om3 = M::fma((c3 > d.om3) ? u.a_rise : u.a_fall, c3 - d.om3, d.om3);
   if (moment_out) { moment_out[0] = Mx; moment_out[1] = My; moment_out[2] = Mz; }
   if (forces_out) { forces_out[0] = f0; forces_out[1] = f1; forces_out[2] = f2; forces_out[3] = f3; }
 }
 
-// compensated p += inc for the hi+lo pair (float mode); plain add in double mode
-UAVB_HD void pos_add(float& hi, float& lo, float inc) {
-  const float y = inc + lo;
-  const float t = hi + y;
-  lo = y - (t - hi);
-  hi = t;
-}
-UAVB_HD void pos_add(double& hi, double& lo, double inc) { hi += inc; (void)lo; }
-
 // Inner loop, part 2: rotor wrench with the given thrust axis + free-body semi-implicit Euler step
 // (mujoco_sim.py:232-255 + MuJoCo Euler; oracle/freebody.py states the same equations in fp64).
 template <class R>
-UAVB_HD void physics_step(Drone<R>& d, const Veh<R>& v, R zx, R zy, R zz, R gx, R gy, R gz) {
+UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx, R zy, R zz, R gx, R gy, R gz) {
   typedef Math<R> M;
-  const R F0 = v.kf * d.om0 * d.om0, F1 = v.kf * d.om1 * d.om1, F2 = v.kf * d.om2 * d.om2, F3 = v.kf * d.om3 * d.om3;
-  const R a_t = -(F0 + F1 + F2 + F3) * v.inv_mass;          // specific thrust along -z body
-  const R tx = v.arm * ((F0 + F3) - (F1 + F2));
-  const R ty = v.arm * ((F0 + F1) - (F2 + F3));
-  const R tz = v.kappa * ((F1 + F3) - (F0 + F2));
-  // velocities first
-  d.vx += v.dt * (zx * a_t + v.wax);
-  d.vy += v.dt * (zy * a_t + v.way);
-  d.vz += v.dt * (zz * a_t + v.waz + v.g);
-  d.wx += v.dt * ((tx - gx) * v.inv_Ix);
-  d.wy += v.dt * ((ty - gy) * v.inv_Iy);
-  d.wz += v.dt * ((tz - gz) * v.inv_Iz);
+  // f_i = kf w_i^2; collective and body torques from the sums of squares (mujoco_sim.py:235-247)
+  const R s0 = d.om0 * d.om0, s1 = d.om1 * d.om1, s2 = d.om2 * d.om2, s3 = d.om3 * d.om3;
+  const R s03 = s0 + s3, s12 = s1 + s2, s01 = s0 + s1, s23 = s2 + s3, s13 = s1 + s3, s02 = s0 + s2;
+  const R dvt = -(s01 + s23) * v.kf_dt_over_m;                 // dt * specific thrust along -z body
+  // velocities first (semi-implicit Euler)
+  // (the per-tick increment is formed first and added once: near hover thrust and gravity cancel inside it)
+  d.vx += M::fma(zx, dvt, v.dvx);
+  d.vy += M::fma(zy, dvt, v.dvy);
+  d.vz += M::fma(zz, dvt, v.dvz);
+  d.wx = M::fma(v.dt_invIx, M::fma(u.arm_kf, s03 - s12, -gx), d.wx);
+  d.wy = M::fma(v.dt_invIy, M::fma(u.arm_kf, s01 - s23, -gy), d.wy);
+  d.wz = M::fma(v.dt_invIz, M::fma(u.kappa_kf, s13 - s02, -gz), d.wz);
   // positions with the new velocity
-  pos_add(d.px, d.plx, v.dt * d.vx);
-  pos_add(d.py, d.ply, v.dt * d.vy);
-  pos_add(d.pz, d.plz, v.dt * d.vz);
+  d.dx = M::fma(u.dt, d.vx, d.dx);
+  d.dy = M::fma(u.dt, d.vy, d.dy);
+  d.dz = M::fma(u.dt, d.vz, d.dz);
   // q <- q * [cos(a/2), sin(a/2) w/|w|], a = dt |w|   (mju_quatIntegrate), written as q += q*(dq-1)
-  const R wn2 = d.wx * d.wx + d.wy * d.wy + d.wz * d.wz;
-  const R h = R(0.5) * v.dt;
-  const R x2 = h * h * wn2;                                  // (a/2)^2
+  const R wn2 = M::fma(d.wx, d.wx, M::fma(d.wy, d.wy, d.wz * d.wz));
+  const R h = u.half_dt;
+  const R x2 = (h * h) * wn2;                                // (a/2)^2
   R sf, cm1;
   if (x2 < R(1e-3)) {                                        // |a/2| < 0.0316: series exact to < 1e-13 relative
-    sf = h * (R(1) - x2 * (R(1.0 / 6) - x2 * (R(1.0 / 120) - x2 * R(1.0 / 5040))));
-    cm1 = -x2 * (R(0.5) - x2 * (R(1.0 / 24) - x2 * (R(1.0 / 720) - x2 * R(1.0 / 40320))));
+    sf = h * M::fma(x2, M::fma(x2, M::fma(x2, R(-1.0 / 5040), R(1.0 / 120)), R(-1.0 / 6)), R(1));
+    cm1 = x2 * M::fma(x2, M::fma(x2, M::fma(x2, R(1.0 / 40320), R(-1.0 / 720)), R(1.0 / 24)), R(-0.5));
   } else {
     const R wn = M::sqrt(wn2);
     R sn, cs;
@@ -282,24 +321,28 @@ UAVB_HD void physics_step(Drone<R>& d, const Veh<R>& v, R zx, R zy, R zz, R gx, 
   }
   const R bx = sf * d.wx, by = sf * d.wy, bz = sf * d.wz;
   const R q0 = d.q0, q1 = d.q1, q2 = d.q2, q3 = d.q3;
-  R n0 = q0 + (q0 * cm1 - q1 * bx - q2 * by - q3 * bz);
-  R n1 = q1 + (q1 * cm1 + q0 * bx + q2 * bz - q3 * by);
-  R n2 = q2 + (q2 * cm1 + q0 * by - q1 * bz + q3 * bx);
-  R n3 = q3 + (q3 * cm1 + q0 * bz + q1 * by - q2 * bx);
-  const R rn = M::rsqrt(n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3);
+  const R n0 = q0 + M::fma(-q3, bz, M::fma(-q2, by, M::fma(-q1, bx, q0 * cm1)));
+  const R n1 = q1 + M::fma(-q3, by, M::fma(q2, bz, M::fma(q0, bx, q1 * cm1)));
+  const R n2 = q2 + M::fma(q3, bx, M::fma(-q1, bz, M::fma(q0, by, q2 * cm1)));
+  const R n3 = q3 + M::fma(-q2, bx, M::fma(q1, by, M::fma(q0, bz, q3 * cm1)));
+  // re-normalise (mujoco_sim.py:36-42).  The input quaternion is unit and dq is unit up to the series remainder, so
+  // |n|^2 = 1 + e with |e| at rounding level (~1e-7 in fp32) and 1/sqrt(1+e) = 1.5 - 0.5 |n|^2 + O(e^2) is exact to
+  // working precision -- no MUFU, and no drift: the correction is re-applied every tick.
+  const R nn = M::fma(n0, n0, M::fma(n1, n1, M::fma(n2, n2, n3 * n3)));
+  const R rn = M::fma(R(-0.5), nn, R(1.5));
   d.q0 = n0 * rn; d.q1 = n1 * rn; d.q2 = n2 * rn; d.q3 = n3 * rn;
 }
 
 // One full inner tick in the reference order (SURVEY 8(a) "exact tick order"): body-rate loop,
 // allocation, motor lag, wrench with the stale (lag=1) or fresh (lag=0) thrust axis, integration.
-template <class R> UAVB_HD void inner_tick(Drone<R>& d, const Veh<R>& v, int thrust_frame_lag) {
+template <class R> UAVB_HD void inner_tick(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, int thrust_frame_lag) {
   R gx, gy, gz;
-  inner_control<R>(d, v, &gx, &gy, &gz, nullptr, nullptr);
+  inner_control<R>(d, u, v, &gx, &gy, &gz, nullptr, nullptr);
   R zx, zy, zz;
   body_z<R>(d, &zx, &zy, &zz);                               // axis of X_k: what mj_step's forward pass will compute
   const R ux = thrust_frame_lag ? d.zbx : zx, uy = thrust_frame_lag ? d.zby : zy, uz = thrust_frame_lag ? d.zbz : zz;
   d.zbx = zx; d.zby = zy; d.zbz = zz;
-  physics_step<R>(d, v, ux, uy, uz, gx, gy, gz);
+  physics_step<R>(d, u, v, ux, uy, uz, gx, gy, gz);
 }
 
 // ---------------------------------------------------------------------------------------------

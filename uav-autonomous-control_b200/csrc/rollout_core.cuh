@@ -44,6 +44,8 @@ struct NoLog {
 };
 
 struct NoObstacles {
+  static constexpr bool kAny = false;
+  template <class R> UAVB_HD bool within(R, R, R, R) const { return false; }
   template <class R> UAVB_HD bool hit(R, R, R) const { return false; }
 };
 
@@ -73,49 +75,75 @@ template <class R> UAVB_HD void cursor_target(Cursor<R>& c, const MissionView& m
 // n_ticks ticks of the closed loop for one drone.  `tick0` is the global index of the first tick
 // (first_hit and the log phase are relative to the start of the mission, not of this launch).
 // The tick loop is split at outer-period boundaries so the 1 kHz body stays branch-light.
+//
+// Obstacle culling: at the start of every stretch of n <= freq ticks the drone can move at most
+//     reach = (|v| + acc_max n dt) n dt
+// (acc_max bounds gravity + full thrust + wind), so boxes farther than that from the body origin in
+// any axis cannot be entered before the next check and the per-tick inclusive point-in-AABB test
+// (minimum_snap.py:352-357) is skipped for the stretch.  The flag and first-hit tick are those of the
+// per-tick test; only the work changes.
 template <class R, class OBST, class LOG>
-UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const Veh<R>& v, const MissionView& m, int tick0,
-                         int n_ticks, int freq, int lag, const OBST& obst, LOG& logger) {
+UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& u, const VehP<R>& v, const MissionView& m,
+                         int tick0, int n_ticks, int freq, int lag, const OBST& obst, LOG& logger) {
   typedef Math<R> M;
   int k = 0;
   while (k < n_ticks) {
     if (c.phase == 0) {
       Target t;
       cursor_target<R>(c, m, &t);
-      outer_update<R>(d, v, t);
+      outer_update<R>(d, u, v, t);
       c.tx = t.x; c.ty = t.y; c.tz = t.z;
       cursor_advance(&c.seg, &c.row, m);
     }
     const int n = (freq - c.phase < n_ticks - k) ? (freq - c.phase) : (n_ticks - k);
-    for (int j = 0; j < n; ++j) {
-      inner_tick<R>(d, v, lag);
-      if (!a.collided && obst.hit(d.px, d.py, d.pz)) { a.collided = 1; a.first_hit = tick0 + k + j; }
-      logger.tick(d);
+    bool watch = false;
+    if (OBST::kAny && !a.collided) {
+      const R T = (R)n * u.dt;
+      const R speed = M::sqrt_fast(d.vx * d.vx + d.vy * d.vy + d.vz * d.vz);
+      const R reach = R(1.01) * (speed + v.acc_max * T) * T + R(1e-4);
+      watch = obst.within((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz), reach);
+    }
+    if (watch) {
+      for (int j = 0; j < n; ++j) {
+        inner_tick<R>(d, u, v, lag);
+        if (!a.collided && obst.hit((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz))) {
+          a.collided = 1; a.first_hit = tick0 + k + j;
+        }
+        logger.tick(d);
+      }
+    } else {
+      for (int j = 0; j < n; ++j) {
+        inner_tick<R>(d, u, v, lag);
+        logger.tick(d);
+      }
     }
     k += n;
     c.phase += n;
     if (c.phase == freq) {
       c.phase = 0;
-      const R ex = pos_err<R>(c.tx, d.px, d.plx), ey = pos_err<R>(c.ty, d.py, d.ply), ez = pos_err<R>(c.tz, d.pz, d.plz);
+      fold_position<R>(d);
+      const R ex = (R)(c.tx - d.px), ey = (R)(c.ty - d.py), ez = (R)(c.tz - d.pz);
       const R e2 = ex * ex + ey * ey + ez * ez;
       const R e = M::sqrt(e2);
       a.sum_e += e; a.sum_e2 += e2; a.max_e = M::fmax(a.max_e, e);
       ++a.periods;
+      const R fx = (R)d.px, fy = (R)d.py, fz = (R)d.pz;
       if (!M::finite(e2)) a.status |= 1;
-      else if (d.px * d.px + d.py * d.py + d.pz * d.pz > R(1e8)) a.status |= 2;
+      else if (fx * fx + fy * fy + fz * fz > R(1e8)) a.status |= 2;
     }
   }
 }
 
-template <class R> UAVB_HD void drone_init(Drone<R>& d, double sx, double sy, double sz) {
-  d.px = (R)sx; d.py = (R)sy; d.pz = (R)sz;
-  d.plx = (R)(sx - (double)d.px); d.ply = (R)(sy - (double)d.py); d.plz = (R)(sz - (double)d.pz);
+template <class R> UAVB_HD void drone_init(Drone<R>& d, const VehU<R>& u, double sx, double sy, double sz) {
+  d.px = sx; d.py = sy; d.pz = sz;
+  d.dx = d.dy = d.dz = R(0);
   d.q0 = R(1); d.q1 = d.q2 = d.q3 = R(0);            // quad.py:78-80
   d.vx = d.vy = d.vz = R(0);
   d.wx = d.wy = d.wz = R(0);
   d.om0 = d.om1 = d.om2 = d.om3 = R(0);              // quad.py:85
   d.integral = R(0);                                 // controller.py:20
-  d.thrust_cmd = R(0); d.pc = d.qc = d.rc = R(0);    // main.py:26-27
+  set_thrust_cmd<R>(d, u, R(0));                     // main.py:26
+  d.pc = d.qc = d.rc = R(0);                         // main.py:27
   body_z<R>(d, &d.zbx, &d.zby, &d.zbz);              // mj_forward in MujocoSimulation.__init__ (mujoco_sim.py:81)
 }
 

@@ -17,17 +17,21 @@
 
 namespace uavb {
 
-constexpr int kRolloutThreads = 128;
+constexpr int kRolloutThreads = 64;
+// 12 CTAs x 64 threads per SM => at most 85 registers per thread: 24 resident warps per SM, so the
+// 100 000 rollouts of BASELINE configs[2] (3 125 warps, 21.1 per SM) are resident in a single wave.
+constexpr int kRolloutCtasPerSm = 12;
 
-struct RolloutDev {
+template <class R> struct RolloutDev {
   uavb_rollout_args a;
-  VehDerived dv;
-  int tick0;  // unused when resuming (taken from the carry block)
+  VehU<R> u;      // launch-uniform constants (constant bank)
+  VehP<R> vp;     // per-rollout constants when no Monte-Carlo override is given (constant bank)
 };
 
 // Shared obstacle set staged in shared memory (broadcast reads) or a per-rollout set in global
 // memory; inclusive bounds exactly as is_collision_cuboid (minimum_snap.py:352-357).
 struct Boxes {
+  static constexpr bool kAny = true;
   const float* b;
   int n;
   template <class R> __device__ __forceinline__ bool hit(R x, R y, R z) const {
@@ -37,6 +41,16 @@ struct Boxes {
       h |= (q[0] <= x) & (x <= q[1]) & (q[2] <= y) & (y <= q[3]) & (q[4] <= z) & (z <= q[5]);
     }
     return h;
+  }
+  // true when some box comes within `reach` of the point in every axis (conservative: Chebyshev gap)
+  template <class R> __device__ __forceinline__ bool within(R x, R y, R z, R reach) const {
+    bool w = false;
+    for (int i = 0; i < n; ++i) {
+      const float* q = b + 6 * i;
+      const R gx = fmax((R)q[0] - x, x - (R)q[1]), gy = fmax((R)q[2] - y, y - (R)q[3]), gz = fmax((R)q[4] - z, z - (R)q[5]);
+      w |= !(fmax(gx, fmax(gy, gz)) > reach);          // NaN positions keep watching
+    }
+    return w;
   }
 };
 
@@ -49,7 +63,7 @@ template <class R> struct GlobalLog {
     if (--left) return;
     left = stride;
     R* o = out;
-    o[0 * B] = d.px; o[1 * B] = d.py; o[2 * B] = d.pz;
+    o[0 * B] = (R)(d.px + (double)d.dx); o[1 * B] = (R)(d.py + (double)d.dy); o[2 * B] = (R)(d.pz + (double)d.dz);
     o[3 * B] = d.q0; o[4 * B] = d.q1; o[5 * B] = d.q2; o[6 * B] = d.q3;
     o[7 * B] = d.vx; o[8 * B] = d.vy; o[9 * B] = d.vz;
     o[10 * B] = d.wx; o[11 * B] = d.wy; o[12 * B] = d.wz;
@@ -65,40 +79,42 @@ struct Carry {
   float* p;
   long long B;
   __device__ __forceinline__ float& w(int k) const { return p[(long long)k * B]; }
+  __device__ __forceinline__ void put64(int k, double x) const { w(k) = i2f(__double2loint(x)); w(k + 1) = i2f(__double2hiint(x)); }
+  __device__ __forceinline__ double get64(int k) const { return __hiloint2double(f2i(w(k + 1)), f2i(w(k))); }
   __device__ void store(const Drone<float>& d, const Cursor<float>& c, const Accum<float>& a, int tick) const {
-    w(0) = d.px; w(1) = d.py; w(2) = d.pz; w(3) = d.plx; w(4) = d.ply; w(5) = d.plz;
+    put64(0, d.px); put64(2, d.py); put64(4, d.pz);
     w(6) = d.q0; w(7) = d.q1; w(8) = d.q2; w(9) = d.q3;
     w(10) = d.vx; w(11) = d.vy; w(12) = d.vz; w(13) = d.wx; w(14) = d.wy; w(15) = d.wz;
     w(16) = d.om0; w(17) = d.om1; w(18) = d.om2; w(19) = d.om3;
     w(20) = d.integral; w(21) = d.thrust_cmd; w(22) = d.pc; w(23) = d.qc; w(24) = d.rc;
     w(25) = d.zbx; w(26) = d.zby; w(27) = d.zbz; w(28) = c.yaw_hold;
     w(29) = i2f(c.seg); w(30) = i2f(c.row); w(31) = i2f(c.phase);
-    w(32) = i2f(__double2loint(c.tx)); w(33) = i2f(__double2hiint(c.tx));
-    w(34) = i2f(__double2loint(c.ty)); w(35) = i2f(__double2hiint(c.ty));
-    w(36) = i2f(__double2loint(c.tz)); w(37) = i2f(__double2hiint(c.tz));
+    put64(32, c.tx); put64(34, c.ty); put64(36, c.tz);
     w(38) = a.sum_e; w(39) = a.sum_e2; w(40) = a.max_e;
     w(41) = i2f(a.periods); w(42) = i2f(a.collided); w(43) = i2f(a.first_hit); w(44) = i2f(a.status);
     w(45) = i2f(tick);
+    w(46) = d.dx; w(47) = d.dy; w(48) = d.dz;
   }
-  __device__ void load(Drone<float>& d, Cursor<float>& c, Accum<float>& a, int* tick) const {
-    d.px = w(0); d.py = w(1); d.pz = w(2); d.plx = w(3); d.ply = w(4); d.plz = w(5);
+  __device__ void load(Drone<float>& d, Cursor<float>& c, Accum<float>& a, const VehU<float>& u, int* tick) const {
+    d.px = get64(0); d.py = get64(2); d.pz = get64(4);
     d.q0 = w(6); d.q1 = w(7); d.q2 = w(8); d.q3 = w(9);
     d.vx = w(10); d.vy = w(11); d.vz = w(12); d.wx = w(13); d.wy = w(14); d.wz = w(15);
     d.om0 = w(16); d.om1 = w(17); d.om2 = w(18); d.om3 = w(19);
-    d.integral = w(20); d.thrust_cmd = w(21); d.pc = w(22); d.qc = w(23); d.rc = w(24);
+    d.integral = w(20); set_thrust_cmd<float>(d, u, w(21)); d.pc = w(22); d.qc = w(23); d.rc = w(24);
     d.zbx = w(25); d.zby = w(26); d.zbz = w(27); c.yaw_hold = w(28);
     c.seg = f2i(w(29)); c.row = f2i(w(30)); c.phase = f2i(w(31));
-    c.tx = __hiloint2double(f2i(w(33)), f2i(w(32)));
-    c.ty = __hiloint2double(f2i(w(35)), f2i(w(34)));
-    c.tz = __hiloint2double(f2i(w(37)), f2i(w(36)));
+    c.tx = get64(32); c.ty = get64(34); c.tz = get64(36);
     a.sum_e = w(38); a.sum_e2 = w(39); a.max_e = w(40);
     a.periods = f2i(w(41)); a.collided = f2i(w(42)); a.first_hit = f2i(w(43)); a.status = f2i(w(44));
     *tick = f2i(w(45));
+    d.dx = w(46); d.dy = w(47); d.dz = w(48);
   }
 };
 
-template <class R, bool LOG>
-__global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutDev p) {
+// MC: some per-rollout override (mass / inertia / gains / wind) is present; otherwise every vehicle
+// constant is a constant-bank operand.
+template <class R, bool LOG, bool MC>
+__global__ void __launch_bounds__(kRolloutThreads, kRolloutCtasPerSm) rollout_kernel(const __grid_constant__ RolloutDev<R> p) {
   extern __shared__ float s_boxes[];
   const uavb_rollout_args& a = p.a;
   const bool shared_boxes = a.n_obs > 0 && a.aabb_set == nullptr;
@@ -111,23 +127,21 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutD
   const long long B = a.B;
 
   // per-rollout constants
-  McValues<float> mc;
-  mc_from_vehicle(mc, a.veh);
-  if (a.mc_mass) mc.mass = a.mc_mass[i];
-  if (a.mc_inertia) { mc.inertia[0] = a.mc_inertia[i]; mc.inertia[1] = a.mc_inertia[B + i]; mc.inertia[2] = a.mc_inertia[2 * B + i]; }
-  if (a.mc_gains) {
+  VehP<R> vloc;
+  if constexpr (MC) {
+    McValues mc;
+    mc_from_vehicle(mc, a.veh);
+    if (a.mc_mass) mc.mass = (double)a.mc_mass[i];
+    if (a.mc_inertia) { mc.inertia[0] = (double)a.mc_inertia[i]; mc.inertia[1] = (double)a.mc_inertia[B + i]; mc.inertia[2] = (double)a.mc_inertia[2 * B + i]; }
+    if (a.mc_gains) {
 #pragma unroll
-    for (int k = 0; k < UAVB_N_GAINS; ++k) mc.gains[k] = a.mc_gains[k * B + i];
+      for (int k = 0; k < UAVB_N_GAINS; ++k) mc.gains[k] = (double)a.mc_gains[k * B + i];
+    }
+    if (a.mc_wind) { mc.wind[0] = (double)a.mc_wind[i]; mc.wind[1] = (double)a.mc_wind[B + i]; mc.wind[2] = (double)a.mc_wind[2 * B + i]; }
+    make_vehp<R>(vloc, a.veh, mc);
   }
-  if (a.mc_wind) { mc.wind[0] = a.mc_wind[i]; mc.wind[1] = a.mc_wind[B + i]; mc.wind[2] = a.mc_wind[2 * B + i]; }
-  Veh<R> v;
-  if (a.mc_mass || a.mc_inertia || a.mc_gains || a.mc_wind) {
-    make_veh<R>(v, a.veh, p.dv, mc, a.inner_per_outer);
-  } else {                       // no overrides: derive from the fp64 defaults, not their fp32 roundings
-    McValues<double> md;
-    mc_from_vehicle(md, a.veh);
-    make_veh<R>(v, a.veh, p.dv, md, a.inner_per_outer);
-  }
+  const VehP<R>& v = MC ? vloc : p.vp;
+  const VehU<R>& u = p.u;
 
   MissionView m;
   m.coeffs = a.seg_coeffs; m.rows = a.seg_rows; m.table = a.seg_table; m.yaw0 = a.seg_yaw0;
@@ -143,29 +157,35 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutD
   if constexpr (sizeof(R) == 4) {
     if (a.resume) {
       Carry cb{a.carry + i, B};
-      cb.load(d, c, acc, &tick0);
+      cb.load(d, c, acc, u, &tick0);
       resumed = true;
     }
   }
   if (!resumed) {
     const double* s = a.start + (size_t)a.start_stride * i;
-    drone_init<R>(d, s[0], s[1], s[2]);
+    drone_init<R>(d, u, s[0], s[1], s[2]);
     cursor_init<R>(c);
     accum_init<R>(acc);
   }
 
-  Boxes boxes;
-  boxes.n = a.n_obs;
-  boxes.b = shared_boxes ? s_boxes : (a.n_obs > 0 ? a.aabbs + (size_t)a.aabb_set[i] * a.n_obs * 6 : nullptr);
-
-  if constexpr (LOG) {
-    GlobalLog<R> lg;
-    lg.out = reinterpret_cast<R*>(a.log_out) + i;
-    lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride;
-    rollout_run<R>(d, c, acc, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, boxes, lg);
+  auto fly = [&](const auto& obst) {
+    if constexpr (LOG) {
+      GlobalLog<R> lg;
+      lg.out = reinterpret_cast<R*>(a.log_out) + i;
+      lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride;
+      rollout_run<R>(d, c, acc, u, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+    } else {
+      NoLog lg;
+      rollout_run<R>(d, c, acc, u, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+    }
+  };
+  if (a.n_obs > 0) {
+    Boxes boxes;
+    boxes.n = a.n_obs;
+    boxes.b = shared_boxes ? s_boxes : a.aabbs + (size_t)a.aabb_set[i] * a.n_obs * 6;
+    fly(boxes);
   } else {
-    NoLog lg;
-    rollout_run<R>(d, c, acc, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, boxes, lg);
+    fly(NoObstacles{});
   }
 
   if constexpr (sizeof(R) == 4) {
@@ -174,9 +194,10 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutD
       cb.store(d, c, acc, tick0 + a.n_ticks);
     }
   }
+  const double fx = d.px + (double)d.dx, fy = d.py + (double)d.dy, fz = d.pz + (double)d.dz;
   if (a.state_out) {
     R* o = reinterpret_cast<R*>(a.state_out) + i;
-    o[0 * B] = d.px; o[1 * B] = d.py; o[2 * B] = d.pz;
+    o[0 * B] = (R)fx; o[1 * B] = (R)fy; o[2 * B] = (R)fz;
     o[3 * B] = d.q0; o[4 * B] = d.q1; o[5 * B] = d.q2; o[6 * B] = d.q3;
     o[7 * B] = d.vx; o[8 * B] = d.vy; o[9 * B] = d.vz;
     o[10 * B] = d.wx; o[11 * B] = d.wy; o[12 * B] = d.wz;
@@ -185,7 +206,7 @@ __global__ void __launch_bounds__(kRolloutThreads) rollout_kernel(const RolloutD
     R fd = R(0);
     if (a.goal) {
       const double* g = a.goal + (size_t)a.goal_stride * i;
-      const R ex = pos_err<R>(g[0], d.px, d.plx), ey = pos_err<R>(g[1], d.py, d.ply), ez = pos_err<R>(g[2], d.pz, d.plz);
+      const R ex = (R)(g[0] - fx), ey = (R)(g[1] - fy), ez = (R)(g[2] - fz);
       fd = Math<R>::sqrt(ex * ex + ey * ey + ez * ez);
     }
     const R np = acc.periods > 0 ? R(1) / (R)acc.periods : R(0);
@@ -228,17 +249,21 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   rc = require_device();
   if (rc) return rc;
   if (a->B == 0) return UAVB_OK;
-  RolloutDev p;
+  RolloutDev<R> p;
   p.a = *a;
-  p.dv = derive_vehicle(a->veh);
-  p.tick0 = 0;
+  make_vehu<R>(p.u, a->veh, a->dt_outer);
+  McValues mc;
+  mc_from_vehicle(mc, a->veh);
+  make_vehp<R>(p.vp, a->veh, mc);
   const int grid = div_up(a->B, kRolloutThreads);
   const size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->log_stride > 0)
-    rollout_kernel<R, true><<<grid, kRolloutThreads, smem, st>>>(p);
-  else
-    rollout_kernel<R, false><<<grid, kRolloutThreads, smem, st>>>(p);
+  const bool mc_any = a->mc_mass || a->mc_inertia || a->mc_gains || a->mc_wind;
+  const bool log = a->log_stride > 0;
+  if (log && mc_any) rollout_kernel<R, true, true><<<grid, kRolloutThreads, smem, st>>>(p);
+  else if (log) rollout_kernel<R, true, false><<<grid, kRolloutThreads, smem, st>>>(p);
+  else if (mc_any) rollout_kernel<R, false, true><<<grid, kRolloutThreads, smem, st>>>(p);
+  else rollout_kernel<R, false, false><<<grid, kRolloutThreads, smem, st>>>(p);
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }

@@ -1,6 +1,7 @@
 // veh_setup.cuh -- turn the ABI vehicle description (+ optional per-rollout Monte-Carlo overrides)
-// into the per-drone constant set of flight_core.cuh.  Derived constants are formed in fp64 and
-// rounded once.  Reference: Quad.__init__ (uav_ac/quadrotor/quad.py:36-73), motor lag response
+// into the constant sets of flight_core.cuh: VehU (uniform across a launch, passed in the kernel
+// parameter block) and VehP (per rollout).  Derived constants are formed in fp64 and rounded once.
+// Reference: Quad.__init__ (uav_ac/quadrotor/quad.py:36-73), motor lag response
 // 1 - exp(-dt/tau) (quad.py:102), lab_course.xml:3,8-13,100,116-119.
 #pragma once
 
@@ -9,11 +10,12 @@
 
 namespace uavb {
 
-template <class T> struct McValues {
-  T mass;
-  T inertia[3];
-  T gains[UAVB_N_GAINS];
-  T wind[3];
+// Values that may be overridden per rollout (BASELINE configs[2..3]); wind is a force in N.
+struct McValues {
+  double mass;
+  double inertia[3];
+  double gains[UAVB_N_GAINS];
+  double wind[3];
 };
 
 UAVB_HD void vehicle_defaults(uavb_vehicle* v) {
@@ -32,41 +34,36 @@ UAVB_HD void vehicle_defaults(uavb_vehicle* v) {
   v->integral_limit = 10.0;                         // controller.py:10
 }
 
-template <class T> UAVB_HD void mc_from_vehicle(McValues<T>& o, const uavb_vehicle& u) {
-  o.mass = (T)u.mass;
-  for (int i = 0; i < 3; ++i) { o.inertia[i] = (T)u.inertia[i]; o.wind[i] = T(0); }
-  for (int i = 0; i < UAVB_N_GAINS; ++i) o.gains[i] = (T)u.gains[i];
+UAVB_HD void mc_from_vehicle(McValues& o, const uavb_vehicle& u) {
+  o.mass = u.mass;
+  for (int i = 0; i < 3; ++i) { o.inertia[i] = u.inertia[i]; o.wind[i] = 0.0; }
+  for (int i = 0; i < UAVB_N_GAINS; ++i) o.gains[i] = u.gains[i];
 }
 
-// Motor-lag responses 1 - exp(-dt/tau) (quad.py:102) are uniform per launch: computed once on the host.
-struct VehDerived {
-  double a_rise, a_fall;
-};
-inline VehDerived derive_vehicle(const uavb_vehicle& u) {
-  VehDerived d;
-  d.a_rise = 1.0 - exp(-u.dt / u.tau_rise);
-  d.a_fall = 1.0 - exp(-u.dt / u.tau_fall);
-  return d;
-}
-
-template <class R, class T>
-UAVB_HD void make_veh(Veh<R>& v, const uavb_vehicle& u, const VehDerived& dv, const McValues<T>& o, int freq) {
-  const double mass = (double)o.mass;
-  const double Ix = (double)o.inertia[0], Iy = (double)o.inertia[1], Iz = (double)o.inertia[2];
-  v.mass = (R)mass; v.inv_mass = (R)(1.0 / mass);
-  v.Ix = (R)Ix; v.Iy = (R)Iy; v.Iz = (R)Iz;
-  v.inv_Ix = (R)(1.0 / Ix); v.inv_Iy = (R)(1.0 / Iy); v.inv_Iz = (R)(1.0 / Iz);
-  v.kp_xy = (R)o.gains[0]; v.kd_xy = (R)o.gains[1]; v.kp_z = (R)o.gains[2]; v.kd_z = (R)o.gains[3]; v.ki_z = (R)o.gains[4];
-  v.kp_roll = (R)o.gains[5]; v.kp_pitch = (R)o.gains[6]; v.kp_yaw = (R)o.gains[7];
-  v.Ikp_p = (R)(Ix * (double)o.gains[8]); v.Ikp_q = (R)(Iy * (double)o.gains[9]); v.Ikp_r = (R)(Iz * (double)o.gains[10]);
-  v.wax = (R)((double)o.wind[0] / mass); v.way = (R)((double)o.wind[1] / mass); v.waz = (R)((double)o.wind[2] / mass);
-  v.g = (R)u.g; v.dt = (R)u.dt; v.dt_outer = (R)(u.dt * freq);
-  v.arm = (R)u.arm; v.inv_arm4 = (R)(0.25 / u.arm); v.kf = (R)u.kf; v.inv_kf = (R)(1.0 / u.kf);
-  v.kappa = (R)u.kappa; v.inv_kappa4 = (R)(0.25 / u.kappa);
-  v.fmin = (R)u.min_thrust; v.fmax = (R)u.max_thrust;
-  v.a_rise = (R)dv.a_rise; v.a_fall = (R)dv.a_fall;
+// Launch-uniform constants; built on the host (exp() for the motor-lag responses of quad.py:102).
+template <class R> inline void make_vehu(VehU<R>& v, const uavb_vehicle& u, double dt_outer) {
+  v.dt = (R)u.dt; v.half_dt = (R)(0.5 * u.dt); v.dt_outer = (R)dt_outer; v.g = (R)u.g;
+  v.kf = (R)u.kf; v.inv_kf = (R)(1.0 / u.kf); v.arm_kf = (R)(u.arm * u.kf); v.kappa_kf = (R)(u.kappa * u.kf);
+  v.inv_arm4 = (R)(0.25 / u.arm); v.inv_kappa4 = (R)(0.25 / u.kappa);
+  v.fmin = (R)u.min_thrust; v.fmax = (R)u.max_thrust; v.fmin4 = (R)(4.0 * u.min_thrust); v.fmax4 = (R)(4.0 * u.max_thrust);
+  v.a_rise = (R)(1.0 - exp(-u.dt / u.tau_rise)); v.a_fall = (R)(1.0 - exp(-u.dt / u.tau_fall));
   v.max_ascent = (R)u.max_ascent; v.max_descent = (R)u.max_descent; v.max_speed_xy = (R)u.max_speed_xy;
   v.max_acc_xy = (R)u.max_horiz_accel; v.max_tilt = (R)u.max_tilt; v.integral_limit = (R)u.integral_limit;
+}
+
+// Per-rollout constants from the (possibly perturbed) mass, inertia, gains and wind.
+template <class R> UAVB_HD void make_vehp(VehP<R>& v, const uavb_vehicle& u, const McValues& o) {
+  const double m = o.mass, Ix = o.inertia[0], Iy = o.inertia[1], Iz = o.inertia[2];
+  v.kf_dt_over_m = (R)(u.kf * u.dt / m);
+  v.dIx = (R)(Iz - Iy); v.dIy = (R)(Ix - Iz); v.dIz = (R)(Iy - Ix);
+  v.Ikp_p = (R)(Ix * o.gains[8]); v.Ikp_q = (R)(Iy * o.gains[9]); v.Ikp_r = (R)(Iz * o.gains[10]);
+  v.dt_invIx = (R)(u.dt / Ix); v.dt_invIy = (R)(u.dt / Iy); v.dt_invIz = (R)(u.dt / Iz);
+  v.dvx = (R)(u.dt * o.wind[0] / m); v.dvy = (R)(u.dt * o.wind[1] / m); v.dvz = (R)(u.dt * (o.wind[2] / m + u.g));
+  v.mass = (R)m;
+  v.kp_xy = (R)o.gains[0]; v.kd_xy = (R)o.gains[1]; v.kp_z = (R)o.gains[2]; v.kd_z = (R)o.gains[3]; v.ki_z = (R)o.gains[4];
+  v.kp_roll = (R)o.gains[5]; v.kp_pitch = (R)o.gains[6]; v.kp_yaw = (R)o.gains[7];
+  const double wn = sqrt(o.wind[0] * o.wind[0] + o.wind[1] * o.wind[1] + o.wind[2] * o.wind[2]);
+  v.acc_max = (R)((4.0 * u.max_thrust + wn) / m + u.g);
 }
 
 }  // namespace uavb
