@@ -17,7 +17,7 @@ all-gathered over NCCL inside the timed region.
 `e2e`    : same metric through the public API with HOST buffers: per step the Monte-Carlo arrays and the
            waypoints are copied from pinned host memory, the metrics are copied back.
 `roofline`: K2 is FP32-issue bound (no dense contraction => no tensor path, ~0 HBM bytes per tick in
-           metrics-only mode); `achieved` = 306 algorithmic flop/tick x ticks / K2 time,
+           metrics-only mode); `achieved` = 269 algorithmic flop/tick x ticks / K2 time,
            `peak` = FP32 FMA rate measured in this run by uavb_measure_fma_peak.  `roofline_log` is the
            HBM roofline of the full-rate state-log mode (52 B/tick) against MEASURED_PEAKS.json.
 """
@@ -34,7 +34,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_TICK = 306          # algorithmic fp32-equivalent flop per drone tick with 4 AABBs (DESIGN.md "K2 work per tick")
+FLOP_PER_TICK = 269          # algorithmic flop per drone tick with 4 AABBs: 239 in the 1 kHz body + 298/10 from the 100 Hz loop (DESIGN.md "K2 work per tick")
 LOG_BYTES_PER_TICK = 52      # 13 fp32 state words
 ROLLOUTS_PER_GPU = 100_000   # BASELINE configs[2]
 VELOCITY = 3.0               # config.ini:7
@@ -137,47 +137,83 @@ def workload_name(rollouts):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+
+    A thread polls NVML (nvidia-ml-py) every ~2 ms -- the timed region of the default run lasts tens of
+    milliseconds, too short for `nvidia-smi -lms`; nvidia-smi is the fallback when NVML cannot be loaded."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, f"/tmp/uavb_clocks_{os.getpid()}.csv"
+        import threading
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(local):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                return int(ids[local])
+        return local
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    why = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    why = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((sm, why, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+        import threading
+        if self.nvml is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons, power = [], [], set(), []
-        for ln in open(self.path):
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if val.lower().startswith("active"):
+        if self.nvml is None:
+            return self._smi_once()
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return self._smi_once()
+        reasons = set()
+        for _, why, _ in self.samples:
+            for name, bit in self.REASONS.items():
+                if why & bit:
                     reasons.add(name)
-        os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "power_w_max": max(power),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": float(self.max_sm), "reasons": sorted(reasons),
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples), "source": "nvml, 2 ms poll during the timed region"}
+
+    def _smi_once(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            p = [x.strip() for x in out.split(",")]
+            reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]) if v.lower().startswith("active")]
+            return {"sm_mhz": float(p[0]), "sm_max_mhz": float(p[1]), "reasons": reasons, "power_w_max": float(p[2]), "samples": 1,
+                    "source": "nvidia-smi, one sample right after the timed region (NVML unavailable)"}
+        except Exception as e:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock sampling unavailable: {e}"]}
 
 
 def run_b200(args):

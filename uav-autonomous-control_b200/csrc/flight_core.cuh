@@ -142,9 +142,10 @@ template <class R> struct Drone {
 };
 
 // Set-point of one table row (minimum_snap.py:122-123 columns 0..9), fp64 from the Horner evaluation.
+// The yaw column (:9) travels as a heading direction (yc, ys) = k (cos yaw, sin yaw), k > 0 arbitrary.
 struct Target {
   double x, y, z, vx, vy, vz, ax, ay, az;
-  double yaw;
+  double yc, ys;
 };
 
 template <class R> UAVB_HD void set_thrust_cmd(Drone<R>& d, const VehU<R>& u, R c) {
@@ -167,16 +168,6 @@ template <class R> UAVB_HD void body_z(const Drone<R>& d, R* zx, R* zy, R* zz) {
   *zx = a + a;
   *zy = b + b;
   *zz = M::fma(R(-2), c, R(1));
-}
-
-// yaw error: wrap_to_pi(wrap_to_2pi(psi_des) - psi) (controller.py:164-165, :170-178).  Python's %
-// is a floored modulo, reproduced with floor().
-template <class R> UAVB_HD R yaw_error(R psi_des, R psi) {
-  const R two_pi = (R)kTwoPi, pi = (R)kPi;
-  R a = psi_des - two_pi * Math<R>::floor(psi_des / two_pi);        // [0, 2pi)
-  R e = a - psi + pi;
-  e = e - two_pi * Math<R>::floor(e / two_pi);
-  return e - pi;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -232,8 +223,12 @@ template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, cons
   const R sin_phi = sa * ih, cos_phi = R22 * ih;
   const R sin_th = clampr<R>(R(2) * (q0 * q2 - q3 * q1), R(-1), R(1));
   const R cos_th = M::sqrt_fast(R(1) - sin_th * sin_th);
-  const R psi = M::atan2(R(2) * (q0 * q3 + q1 * q2), R(1) - R(2) * (q2 * q2 + q3 * q3));
-  const R e_yaw = yaw_error<R>((R)t.yaw, psi);
+  // yaw error wrap_to_pi(wrap_to_2pi(psi_des) - psi) (controller.py:164-165) as ONE atan2 of the rotated heading:
+  // with (cp, sp) ~ (cos psi, sin psi) from quad.py:208-213, atan2(ys cp - yc sp, yc cp + ys sp) is the angle from
+  // psi to psi_des in (-pi, pi] (the reference's floored modulo gives [-pi, pi): they differ only at exactly +-pi).
+  const R sp = R(2) * (q0 * q3 + q1 * q2), cp = R(1) - R(2) * (q2 * q2 + q3 * q3);
+  const R yc = (R)t.yc, ys = (R)t.ys;
+  const R e_yaw = M::atan2(ys * cp - yc * sp, yc * cp + ys * sp);
   const R r_c = (v.kp_yaw * e_yaw * cos_th - q_c * sin_phi) * M::rcp_fast(cos_phi);
 
   d.pc = p_c; d.qc = q_c; d.rc = r_c;
@@ -348,17 +343,25 @@ template <class R> UAVB_HD void inner_tick(Drone<R>& d, const VehU<R>& u, const 
 // ---------------------------------------------------------------------------------------------
 // Table row on the fly (minimum_snap.py:104-110): t = j*dt in fp64, Horner in fp64.
 // c points at the 24 coefficients of the segment in the reference layout [power][axis].
+// Position, velocity and acceleration come from one pass of the nested Horner recurrence
+//   d2 <- d2 t + d1 ; d1 <- d1 t + p ; p <- p t + c_k      (k = 6 .. 0;  p' = d1, p'' = 2 d2)
+// i.e. 3 FMAs per coefficient and no multiplications by the derivative factors k, k(k-1).
 template <class LOAD> UAVB_HD void eval_row(LOAD ld, double t, Target* out) {
   double p[3], v[3], a[3];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int ax = 0; ax < 3; ++ax) {
-    const double c7 = ld(21 + ax), c6 = ld(18 + ax), c5 = ld(15 + ax), c4 = ld(12 + ax);
-    const double c3 = ld(9 + ax), c2 = ld(6 + ax), c1 = ld(3 + ax), c0 = ld(ax);
-    p[ax] = ((((((c7 * t + c6) * t + c5) * t + c4) * t + c3) * t + c2) * t + c1) * t + c0;
-    v[ax] = (((((7.0 * c7 * t + 6.0 * c6) * t + 5.0 * c5) * t + 4.0 * c4) * t + 3.0 * c3) * t + 2.0 * c2) * t + c1;
-    a[ax] = ((((42.0 * c7 * t + 30.0 * c6) * t + 20.0 * c5) * t + 12.0 * c4) * t + 6.0 * c3) * t + 2.0 * c2;
+    double pp = ld(21 + ax), d1 = 0.0, d2 = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 6; k >= 0; --k) {
+      d2 = ::fma(d2, t, d1);
+      d1 = ::fma(d1, t, pp);
+      pp = ::fma(pp, t, ld(3 * k + ax));
+    }
+    p[ax] = pp; v[ax] = d1; a[ax] = d2 + d2;
   }
   out->x = p[0]; out->y = p[1]; out->z = p[2];
   out->vx = v[0]; out->vy = v[1]; out->vz = v[2];

@@ -25,10 +25,22 @@ struct MissionView {
   double dt_outer;
 };
 
+constexpr double kSpeed2Min = 0x1.0c6f7a0b5ed8dp-20;
+
+UAVB_HD double speed2_unfused(double vx, double vy) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy));
+#else
+  volatile double a = vx * vx, b = vy * vy;          // keep the two products rounded separately (no FMA contraction)
+  return a + b;
+#endif
+}
+
 template <class R> struct Cursor {
   int seg, row;           // table row the NEXT outer update will use (main.py:48 trajectory_index)
   int phase;              // inner_step % frequency (main.py:25,39), kept incrementally
-  R yaw_hold;             // yaw of the last valid row (minimum_snap.py:126-136 hold-last-valid)
+  R hx, hy;               // heading direction of the last valid row (minimum_snap.py:126-136 hold-last-valid),
+                          // any positive multiple of (cos yaw, sin yaw)
   double tx, ty, tz;      // position set-point of the row used by the current outer period
 };
 
@@ -67,9 +79,16 @@ template <class R> UAVB_HD void cursor_target(Cursor<R>& c, const MissionView& m
   auto ld = [cf](int i) { return cf[i]; };
 #endif
   eval_row(ld, (double)c.row * m.dt_outer, t);
-  if (c.row == 0 && m.table[sg]) c.yaw_hold = (R)m.yaw0[sg];
-  if (sqrt(t->vx * t->vx + t->vy * t->vy) >= 1e-3) c.yaw_hold = Math<R>::atan2((R)t->vy, (R)t->vx);
-  t->yaw = (double)c.yaw_hold;
+  if (c.row == 0 && m.table[sg]) {                       // a new table starts: rows before its first valid row take yaw0
+    double s0, c0;
+    const double y0 = m.yaw0[sg];
+    s0 = sin(y0); c0 = cos(y0);
+    c.hx = (R)c0; c.hy = (R)s0;
+  }
+  // valid iff np.linalg.norm(v_xy) >= 1e-3 (:128-129): norm = sqrt(fl(fl(vx^2) + fl(vy^2))), and sqrt is monotonic, so the
+  // test is s >= kSpeed2Min with kSpeed2Min the smallest double whose square root rounds to >= 1e-3.
+  if (speed2_unfused(t->vx, t->vy) >= kSpeed2Min) { c.hx = (R)t->vx; c.hy = (R)t->vy; }
+  t->yc = (double)c.hx; t->ys = (double)c.hy;
 }
 
 // n_ticks ticks of the closed loop for one drone.  `tick0` is the global index of the first tick
@@ -124,7 +143,7 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
       fold_position<R>(d);
       const R ex = (R)(c.tx - d.px), ey = (R)(c.ty - d.py), ez = (R)(c.tz - d.pz);
       const R e2 = ex * ex + ey * ey + ez * ez;
-      const R e = M::sqrt(e2);
+      const R e = M::sqrt_fast(e2);
       a.sum_e += e; a.sum_e2 += e2; a.max_e = M::fmax(a.max_e, e);
       ++a.periods;
       const R fx = (R)d.px, fy = (R)d.py, fz = (R)d.pz;
@@ -148,7 +167,7 @@ template <class R> UAVB_HD void drone_init(Drone<R>& d, const VehU<R>& u, double
 }
 
 template <class R> UAVB_HD void cursor_init(Cursor<R>& c) {
-  c.seg = 0; c.row = 0; c.phase = 0; c.yaw_hold = R(0); c.tx = c.ty = c.tz = 0.0;
+  c.seg = 0; c.row = 0; c.phase = 0; c.hx = R(1); c.hy = R(0); c.tx = c.ty = c.tz = 0.0;
 }
 
 template <class R> UAVB_HD void accum_init(Accum<R>& a) {

@@ -18,9 +18,12 @@
 namespace uavb {
 
 constexpr int kRolloutThreads = 64;
-// 12 CTAs x 64 threads per SM => at most 85 registers per thread: 24 resident warps per SM, so the
-// 100 000 rollouts of BASELINE configs[2] (3 125 warps, 21.1 per SM) are resident in a single wave.
-constexpr int kRolloutCtasPerSm = 12;
+// Residency.  The kernel is compiled for K = 8..12 CTAs of 64 threads per SM (register cap 128 .. 80).  K = 12 keeps
+// 24 warps per SM resident, so the 100 000 rollouts of BASELINE configs[2] (1 563 CTAs, 10.6 per SM) fit in one wave --
+// but the hardware then places up to 12 CTAs on some SMs and 9-10 on others, and the launch lasts as long as the
+// fullest SM.  The launcher therefore picks K = ceil(CTAs / SMs) when that lies in 8..11: the register cap of that
+// variant makes K+1 CTAs impossible, every SM receives at most K, and the extra registers remove spills.
+constexpr int kRolloutCtasMin = 8, kRolloutCtasMax = 12;
 
 template <class R> struct RolloutDev {
   uavb_rollout_args a;
@@ -87,13 +90,13 @@ struct Carry {
     w(10) = d.vx; w(11) = d.vy; w(12) = d.vz; w(13) = d.wx; w(14) = d.wy; w(15) = d.wz;
     w(16) = d.om0; w(17) = d.om1; w(18) = d.om2; w(19) = d.om3;
     w(20) = d.integral; w(21) = d.thrust_cmd; w(22) = d.pc; w(23) = d.qc; w(24) = d.rc;
-    w(25) = d.zbx; w(26) = d.zby; w(27) = d.zbz; w(28) = c.yaw_hold;
+    w(25) = d.zbx; w(26) = d.zby; w(27) = d.zbz; w(28) = c.hx;
     w(29) = i2f(c.seg); w(30) = i2f(c.row); w(31) = i2f(c.phase);
     put64(32, c.tx); put64(34, c.ty); put64(36, c.tz);
     w(38) = a.sum_e; w(39) = a.sum_e2; w(40) = a.max_e;
     w(41) = i2f(a.periods); w(42) = i2f(a.collided); w(43) = i2f(a.first_hit); w(44) = i2f(a.status);
     w(45) = i2f(tick);
-    w(46) = d.dx; w(47) = d.dy; w(48) = d.dz;
+    w(46) = d.dx; w(47) = d.dy; w(48) = d.dz; w(49) = c.hy;
   }
   __device__ void load(Drone<float>& d, Cursor<float>& c, Accum<float>& a, const VehU<float>& u, int* tick) const {
     d.px = get64(0); d.py = get64(2); d.pz = get64(4);
@@ -101,20 +104,23 @@ struct Carry {
     d.vx = w(10); d.vy = w(11); d.vz = w(12); d.wx = w(13); d.wy = w(14); d.wz = w(15);
     d.om0 = w(16); d.om1 = w(17); d.om2 = w(18); d.om3 = w(19);
     d.integral = w(20); set_thrust_cmd<float>(d, u, w(21)); d.pc = w(22); d.qc = w(23); d.rc = w(24);
-    d.zbx = w(25); d.zby = w(26); d.zbz = w(27); c.yaw_hold = w(28);
+    d.zbx = w(25); d.zby = w(26); d.zbz = w(27); c.hx = w(28);
     c.seg = f2i(w(29)); c.row = f2i(w(30)); c.phase = f2i(w(31));
     c.tx = get64(32); c.ty = get64(34); c.tz = get64(36);
     a.sum_e = w(38); a.sum_e2 = w(39); a.max_e = w(40);
     a.periods = f2i(w(41)); a.collided = f2i(w(42)); a.first_hit = f2i(w(43)); a.status = f2i(w(44));
     *tick = f2i(w(45));
-    d.dx = w(46); d.dy = w(47); d.dz = w(48);
+    d.dx = w(46); d.dy = w(47); d.dz = w(48); c.hy = w(49);
   }
 };
 
 // MC: some per-rollout override (mass / inertia / gains / wind) is present; otherwise every vehicle
 // constant is a constant-bank operand.
-template <class R, bool LOG, bool MC>
-__global__ void __launch_bounds__(kRolloutThreads, kRolloutCtasPerSm) rollout_kernel(const __grid_constant__ RolloutDev<R> p) {
+// registers per thread that let exactly K CTAs of 64 threads share the 64 K-register file of an SM
+constexpr int rollout_regs(int K) { return K >= 12 ? 80 : K == 11 ? 88 : K == 10 ? 96 : K == 9 ? 112 : 128; }
+
+template <class R, bool LOG, bool MC, int K>
+__global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constant__ RolloutDev<R> p) {
   extern __shared__ float s_boxes[];
   const uavb_rollout_args& a = p.a;
   const bool shared_boxes = a.n_obs > 0 && a.aabb_set == nullptr;
@@ -243,6 +249,22 @@ static int check_args(const uavb_rollout_args* a, bool f64) {
   return UAVB_OK;
 }
 
+// SM count of the current device (one query per device and process).
+static int sm_count_cached(int* sms) {
+  static int cache[64] = {0};
+  int dev = 0;
+  UAVB_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || cache[dev] == 0) {
+    int n = 0;
+    UAVB_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+    *sms = n;
+    return UAVB_OK;
+  }
+  *sms = cache[dev];
+  return UAVB_OK;
+}
+
 template <class R> static int launch_rollout(const uavb_rollout_args* a, void* stream) {
   int rc = check_args(a, sizeof(R) == 8);
   if (rc) return rc;
@@ -260,10 +282,30 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool mc_any = a->mc_mass || a->mc_inertia || a->mc_gains || a->mc_wind;
   const bool log = a->log_stride > 0;
-  if (log && mc_any) rollout_kernel<R, true, true><<<grid, kRolloutThreads, smem, st>>>(p);
-  else if (log) rollout_kernel<R, true, false><<<grid, kRolloutThreads, smem, st>>>(p);
-  else if (mc_any) rollout_kernel<R, false, true><<<grid, kRolloutThreads, smem, st>>>(p);
-  else rollout_kernel<R, false, false><<<grid, kRolloutThreads, smem, st>>>(p);
+  if constexpr (sizeof(R) == 8) {                      // validation build: one residency variant
+    if (log && mc_any) rollout_kernel<R, true, true, 8><<<grid, kRolloutThreads, smem, st>>>(p);
+    else if (log) rollout_kernel<R, true, false, 8><<<grid, kRolloutThreads, smem, st>>>(p);
+    else if (mc_any) rollout_kernel<R, false, true, 8><<<grid, kRolloutThreads, smem, st>>>(p);
+    else rollout_kernel<R, false, false, 8><<<grid, kRolloutThreads, smem, st>>>(p);
+  } else if (log) {
+    if (mc_any) rollout_kernel<R, true, true, 12><<<grid, kRolloutThreads, smem, st>>>(p);
+    else rollout_kernel<R, true, false, 12><<<grid, kRolloutThreads, smem, st>>>(p);
+  } else {
+    int sms = 0;
+    rc = sm_count_cached(&sms);
+    if (rc) return rc;
+    int k = div_up(grid, sms);
+    k = k < kRolloutCtasMin ? kRolloutCtasMin : (k > kRolloutCtasMax ? kRolloutCtasMax : k);
+#define UAVB_LAUNCH_K(KK)                                                                       \
+  case KK:                                                                                      \
+    if (mc_any) rollout_kernel<R, false, true, KK><<<grid, kRolloutThreads, smem, st>>>(p);     \
+    else rollout_kernel<R, false, false, KK><<<grid, kRolloutThreads, smem, st>>>(p);           \
+    break;
+    switch (k) {
+      UAVB_LAUNCH_K(8) UAVB_LAUNCH_K(9) UAVB_LAUNCH_K(10) UAVB_LAUNCH_K(11) UAVB_LAUNCH_K(12)
+    }
+#undef UAVB_LAUNCH_K
+  }
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }

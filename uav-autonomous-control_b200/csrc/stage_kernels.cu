@@ -46,7 +46,11 @@ __global__ void __launch_bounds__(128) stage_kernel(const StageDev p) {
     t.x = a.target[0 * B + i]; t.y = a.target[1 * B + i]; t.z = a.target[2 * B + i];
     t.vx = a.target[3 * B + i]; t.vy = a.target[4 * B + i]; t.vz = a.target[5 * B + i];
     t.ax = a.target[6 * B + i]; t.ay = a.target[7 * B + i]; t.az = a.target[8 * B + i];
-    t.yaw = a.target[9 * B + i];
+    {
+      float sy, cy;
+      sincosf(a.target[9 * B + i], &sy, &cy);
+      t.yc = cy; t.ys = sy;
+    }
     d.integral = a.integral[i];
     outer_update<float>(d, u, v, t);
     a.integral[i] = d.integral;
