@@ -14,8 +14,9 @@ min-snap solve of the mission (K1, take-off + course tables), table geometry, pe
 all-gathered over NCCL inside the timed region.
 
 `value`  : steps/s with inputs resident in HBM (CUDA events around the K timed steps, max over ranks).
-`e2e`    : same metric through the public API with HOST buffers: per step the Monte-Carlo arrays and the
-           waypoints are copied from pinned host memory, the metrics are copied back.
+`e2e`    : same metric through the reference-facing C-ABI call uavb_fly_mission_host with HOST buffers: per step
+           the waypoints and the Monte-Carlo arrays are copied from pinned host memory, the mission is planned and
+           flown, the metrics are copied back and the call synchronises.
 `roofline`: K2 is FP32-issue bound (no dense contraction => no tensor path, ~0 HBM bytes per tick in
            metrics-only mode); `achieved` = 269 algorithmic flop/tick x ticks / K2 time,
            `peak` = FP32 FMA rate measured in this run by uavb_measure_fma_peak.  `roofline_log` is the
@@ -220,7 +221,7 @@ def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from uav_ac_b200 import _native as nat, kernels, sharding
+    from uav_ac_b200 import _native as nat, host_api, kernels, sharding
     from uav_ac_b200.simulation.scene import LAB_COURSE_GOAL, LAB_COURSE_OBSTACLES, LAB_COURSE_START, LAB_COURSE_WAYPOINTS
 
     rank, local, world = sharding.init_from_env("nccl")
@@ -266,19 +267,21 @@ def run_b200(args):
         m = hot_path(wp_dev, vel_dev, mc_dev)
         return sharding.gather_metrics(m, total) if world > 1 else m
 
+    mc_mass_h, mc_inertia_h, mc_gains_h = mc_host[11], mc_host[12:15], mc_host[:11]     # contiguous pinned views, SoA
+    wp_np = np.ascontiguousarray(LAB_COURSE_WAYPOINTS, dtype=np.float64)
+
     def step_e2e():
-        wp = wp_host.to(dev, non_blocking=True)
-        vel = vel_host.to(dev, non_blocking=True)
-        mc = mc_host.to(dev, non_blocking=True)
-        m = hot_path(wp, vel, mc)
-        if world > 1:
-            m = sharding.gather_metrics(m, total)
-            m = m[begin:end]
-        metrics_host.copy_(m, non_blocking=True)
+        """The reference-facing call: uavb_fly_mission_host (C ABI, HOST buffers).  Inside the call: H2D of the
+        waypoints and the Monte-Carlo arrays, K1 x2, table geometry, K2, D2H of the metrics, synchronisation."""
+        host_api.fly_mission_host(wp_np, VELOCITY, B, n_takeoff_waypoints=2, frequency=FREQUENCY, vehicle=veh, mc_mass=mc_mass_h,
+                                  mc_inertia=mc_inertia_h, mc_gains=mc_gains_h, obstacles=LAB_COURSE_OBSTACLES, start=LAB_COURSE_START,
+                                  goal=LAB_COURSE_GOAL, metrics_out=metrics_host)
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)                    # > 126 MB L2
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, wall=False):
+        """K timed steps between barriers + synchronize; device time from CUDA events on the launching (current torch)
+        stream, or host wall-clock for the synchronous host-buffer call (wall=True); max over ranks."""
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -288,17 +291,24 @@ def run_b200(args):
         if sampler:
             sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall_ms = 0.0
         for s in range(steps):
             flush.fill_(s & 0xFF)                                                           # flush L2 between timed iterations
-            ev[s][0].record()
-            fn()
-            ev[s][1].record()
+            if wall:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                wall_ms += (time.perf_counter() - t0) * 1e3
+            else:
+                ev[s][0].record()
+                fn()
+                ev[s][1].record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
-        ms = sum(a.elapsed_time(b) for a, b in ev)
+        ms = wall_ms if wall else sum(a.elapsed_time(b) for a, b in ev)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,7 +318,7 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, clocks = timed(step_device, args.steps, W, sampler)
     n_ticks = n_ticks_holder["n"]
-    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    ms_e2e, _ = timed(step_e2e, args.steps, 2, wall=True)
     torch.cuda.synchronize()
     sim_steps = float(total) * n_ticks                                                       # whole job, one step
     value = sim_steps * args.steps / (ms_dev * 1e-3)
@@ -346,7 +356,8 @@ def run_b200(args):
                        "l2": "256 MB buffer written between timed iterations (L2 flush)", "fp64_parts": "K1 solve and 100 Hz set-point evaluation"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(mc_host.numel() * 4 + wp_host.numel() * 8 + 8),
-                    "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
+                    "call": "uavb_fly_mission_host (C ABI, pinned host buffers, synchronous); host wall-clock, max over ranks"},
             "gpu_launches": 5 * args.steps,        # per step: 2x minsnap_solve, 2x table_meta, 1x rollout (torch glue kernels not counted)
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "traffic": None, "kernel": "rollout_kernel<float,false>", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,

@@ -261,6 +261,40 @@ int uavb_minsnap_solve_f64_host(const double* waypoints, const double* velocity,
                                 double start_end_time_factor, double* coeffs_out, double* times_out,
                                 int* status_out);
 
+/* One mission flown by B drones, HOST buffers in and out -- the call a reference-side binding makes.
+ * Replaces, for B drones at once, what uav_ac/main.py:main() and the headless loop of
+ * tests/integration/test_mujoco_trajectory_tracking.py:11-36 do for one:
+ *     trajectory = _generate_mission_trajectory(waypoints, obstacles, velocity, quad.dt * frequency)   (main.py:73-84)
+ *     for target in trajectory: for _ in range(frequency): trajectory_controller.step(); simulation.step()
+ *     final distance to goal / collision flag / tracking error                                          (main.py:115-120)
+ * The mission is planned on the device (K1 per table + table geometry), every drone flies it in the
+ * persistent rollout kernel (K2) with its own Monte-Carlo overrides, and the per-rollout metrics
+ * (and optionally the final states) are copied back.  Synchronous. */
+typedef struct uavb_mission_host {
+  int B;                        /* drones                                                                */
+  int n_waypoints;              /* rows of `waypoints`                                                   */
+  int n_takeoff_waypoints;      /* leading waypoints of the first (take-off) table: 2 for main.py:80-81;
+                                   the second table starts at waypoint n_takeoff_waypoints-1 (:82-83).
+                                   0 = a single table over all waypoints                                  */
+  const double* waypoints;      /* [n_waypoints][3] NED                                                  */
+  double velocity;              /* config.ini [SIM_FLIGHT] velocity                                      */
+  double start_end_time_factor; /* MinimumSnap.START_END_TIME_FACTOR (1.5)                               */
+  int frequency;                /* config.ini [DEFAULT] frequency: inner ticks per outer period          */
+  int n_ticks;                  /* ticks to fly; 0 = the whole table (frequency * rows)                  */
+  int thrust_frame_lag;         /* 1 = headless loop, 0 = viewer path                       */
+  uavb_vehicle veh;
+  const float* mc_mass;         /* [B]      optional per-drone overrides, SoA, NULL = veh defaults        */
+  const float* mc_inertia;      /* [3][B]                                                                */
+  const float* mc_gains;        /* [UAVB_N_GAINS][B]                                                     */
+  const float* mc_wind;         /* [3][B]   N, world frame (extension)                                   */
+  const float* aabbs;           /* [n_obs][6] or NULL                                                    */
+  int n_obs;
+  const double* start;          /* [3] or NULL = waypoints[0]                                            */
+  const double* goal;           /* [3] or NULL = last waypoint                                           */
+} uavb_mission_host;
+int uavb_fly_mission_host(const uavb_mission_host* mission, float* metrics_out /* [B][UAVB_N_METRICS] */,
+                          float* state_out /* [13][B] or NULL */, int* n_ticks_out /* or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

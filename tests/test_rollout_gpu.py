@@ -271,3 +271,31 @@ def test_argument_errors_are_reported_not_ignored(cuda):
         kernels.rollout(plan, 4, 100, start=torch.zeros(3, dtype=torch.float64, device=cuda), frequency=0)
     with pytest.raises(ValueError):
         kernels.rollout(plan, 4, 100, start=torch.zeros(3, dtype=torch.float64, device=cuda), mc_mass=torch.ones(3, device=cuda))
+
+
+def test_host_buffer_entry_point_matches_device_path_and_reference(cuda, golden):
+    """uavb_fly_mission_host (the call a reference-side binding makes): NumPy arrays in, metrics out; same result as the
+    device-pointer path bit for bit, and the reference closed-loop metrics within the stated tolerances."""
+    import torch
+    from uav_ac_b200 import host_api
+    from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES, LAB_COURSE_WAYPOINTS
+    gold = golden["closed_loop_v3"]
+    var = golden["closed_loop_variants"]
+    B = 300
+    gs, ms, ins = np.ones((B, 11)), np.ones(B), np.ones((B, 3))
+    gs[7], ms[7], ins[7] = var["mc0_gain_scale"], float(var["mc0_mass_scale"]), var["mc0_inertia_scale"]
+    mc = mc_arrays(cuda, B, gs, ms, ins)
+    met, state, n_ticks = host_api.fly_mission_host(LAB_COURSE_WAYPOINTS, 3.0, B, obstacles=LAB_COURSE_OBSTACLES, want_state=True,
+                                                    mc_mass=mc["mc_mass"].cpu().numpy(), mc_inertia=mc["mc_inertia"].cpu().numpy(),
+                                                    mc_gains=mc["mc_gains"].cpu().numpy())
+    assert n_ticks == 10 * len(gold["X"]) and met.shape == (B, 8) and state.shape == (13, B)
+    plan = lab_course_plan(cuda, 3.0)
+    res = _fly(cuda, plan, B, n_ticks, obstacles=torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=cuda), **mc)
+    assert np.array_equal(met, res.metrics.cpu().numpy()) and np.array_equal(state, res.state.cpu().numpy())
+    _check_metrics(torch.tensor(met[0]), gold)
+    assert abs(met[7, 0] - float(var["mc0_final_dist"])) < POS_TOL and abs(met[7, 3] - float(var["mc0_mean_err"])) < 2e-5
+    # single table (no take-off split) and a bounded number of ticks
+    met1, _, n1 = host_api.fly_mission_host(LAB_COURSE_WAYPOINTS[1:], 3.0, 2, n_takeoff_waypoints=0, n_ticks=500)
+    assert n1 == 500 and met1[0, 7] == 50 and np.isfinite(met1).all()
+    with pytest.raises(Exception):
+        host_api.fly_mission_host(np.array([[0.0, 0, 0], [0, 0, 0], [1, 0, 0]]), 3.0, 2, n_takeoff_waypoints=2)   # zero-length take-off

@@ -29,7 +29,7 @@ SYMBOLS = (
     "uavb_version", "uavb_last_error", "uavb_device_count", "uavb_device_info", "uavb_minsnap_solve_f64",
     "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_table_hits_f64",
     "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
-    "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_minsnap_solve_f64_host",
+    "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host",
 )
 
 
@@ -72,6 +72,16 @@ class StageArgs(Structure):
     ]
 
 
+class MissionHost(Structure):
+    """struct uavb_mission_host (include/uavb.h): one mission, B drones, host buffers."""
+    _fields_ = [
+        ("B", c_int), ("n_waypoints", c_int), ("n_takeoff_waypoints", c_int), ("waypoints", c_void_p), ("velocity", c_double),
+        ("start_end_time_factor", c_double), ("frequency", c_int), ("n_ticks", c_int), ("thrust_frame_lag", c_int), ("veh", Vehicle),
+        ("mc_mass", c_void_p), ("mc_inertia", c_void_p), ("mc_gains", c_void_p), ("mc_wind", c_void_p), ("aabbs", c_void_p),
+        ("n_obs", c_int), ("start", c_void_p), ("goal", c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -102,6 +112,7 @@ def lib() -> ctypes.CDLL:
     L.uavb_mc_missions_f64.argtypes = [c_ulonglong, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.uavb_measure_fma_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
     L.uavb_minsnap_solve_f64_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]
+    L.uavb_fly_mission_host.argtypes = [POINTER(MissionHost), c_void_p, c_void_p, POINTER(c_int)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("uavb_last_error", "uavb_vehicle_defaults"):

@@ -1,0 +1,132 @@
+// host_api.cu -- host-buffer (end-to-end) entry point: one mission, B drones, numpy-style arrays in,
+// metrics out.  Only plumbing lives here: device allocation from the stream-ordered pool, copies,
+// and calls into the device-pointer entry points (K1, table geometry, K2).
+#include <vector>
+
+#include "uavb_common.cuh"
+
+namespace uavb {
+
+// Stream-ordered device buffer that frees itself; allocation failures are recorded, not thrown.
+struct DevPool {
+  cudaStream_t st;
+  std::vector<void*> owned;
+  cudaError_t err = cudaSuccess;
+  explicit DevPool(cudaStream_t s) : st(s) {}
+  ~DevPool() {
+    for (void* p : owned) cudaFreeAsync(p, st);
+  }
+  template <class T> T* alloc(size_t n) {
+    void* p = nullptr;
+    if (err == cudaSuccess) err = cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
+    if (err == cudaSuccess) owned.push_back(p);
+    return static_cast<T*>(p);
+  }
+  template <class T> T* upload(const T* host, size_t n) {
+    if (!host) return nullptr;
+    T* d = alloc<T>(n);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return d;
+  }
+};
+
+}  // namespace uavb
+
+using namespace uavb;
+
+extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_out, float* state_out, int* n_ticks_out) {
+  UAVB_REQUIRE(m != nullptr && metrics_out != nullptr, "fly_mission_host: mission and metrics_out are required");
+  UAVB_REQUIRE(m->B >= 0, "fly_mission_host: B must be >= 0");
+  UAVB_REQUIRE(m->waypoints != nullptr && m->n_waypoints >= 2, "fly_mission_host: at least two waypoints are required");
+  UAVB_REQUIRE(m->n_takeoff_waypoints == 0 || (m->n_takeoff_waypoints >= 2 && m->n_takeoff_waypoints < m->n_waypoints),
+               "fly_mission_host: n_takeoff_waypoints must be 0 or in [2, n_waypoints)");
+  UAVB_REQUIRE(m->frequency >= 1 && m->velocity > 0.0 && m->n_ticks >= 0, "fly_mission_host: frequency >= 1, velocity > 0, n_ticks >= 0 required");
+  UAVB_REQUIRE(m->n_obs >= 0 && (m->n_obs == 0 || m->aabbs != nullptr), "fly_mission_host: n_obs > 0 needs aabbs");
+  const int n_tab = m->n_takeoff_waypoints ? 2 : 1;
+  const int S0 = m->n_takeoff_waypoints ? m->n_takeoff_waypoints - 1 : m->n_waypoints - 1;
+  const int S1 = m->n_takeoff_waypoints ? m->n_waypoints - m->n_takeoff_waypoints : 0;
+  UAVB_REQUIRE(S0 <= UAVB_MAX_SPLINES && S1 <= UAVB_MAX_SPLINES, "fly_mission_host: too many splines in one table");
+  int rc = require_device();
+  if (rc) return rc;
+  const int n_seg = S0 + S1;
+  const size_t B = (size_t)m->B;
+  const double dt_outer = m->veh.dt * m->frequency;
+
+  cudaStream_t st = nullptr;
+  UAVB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int result = UAVB_OK;
+  {
+    DevPool pool(st);
+    double* d_wp = pool.upload(m->waypoints, (size_t)m->n_waypoints * 3);
+    const double vel2[2] = {m->velocity, m->velocity};
+    double* d_vel = pool.upload(vel2, 2);
+    double* d_coeffs = pool.alloc<double>((size_t)n_seg * 24);
+    double* d_times = pool.alloc<double>(n_seg);
+    int* d_status = pool.alloc<int>(2);
+    int* d_rows = pool.alloc<int>(n_seg);
+    double* d_yaw0 = pool.alloc<double>(2);
+    int* d_total = pool.alloc<int>(2);
+    const int offs[3] = {0, S0, n_seg};
+    int* d_offs = pool.upload(offs, 3);
+    if (pool.err != cudaSuccess) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
+    // plan: one K1 launch per table (main.py:80-83), then the table geometry of both
+    if (!result) result = uavb_minsnap_solve_f64(d_wp, d_vel, 1, S0, m->start_end_time_factor, d_coeffs, d_times, d_status, st);
+    if (!result && n_tab == 2)
+      result = uavb_minsnap_solve_f64(d_wp + 3 * (size_t)(m->n_takeoff_waypoints - 1), d_vel + 1, 1, S1, m->start_end_time_factor,
+                                      d_coeffs + (size_t)S0 * 24, d_times + S0, d_status + 1, st);
+    if (!result) result = uavb_minsnap_table_meta_f64(d_coeffs, d_times, d_offs, n_tab, dt_outer, d_rows, d_yaw0, d_total, st);
+    std::vector<int> rows(n_seg), seg_table(n_seg, 0);
+    std::vector<double> seg_yaw0(n_seg, 0.0);
+    double yaw0[2] = {0.0, 0.0};
+    int status[2] = {0, 0};
+    if (!result) {
+      cudaError_t e = cudaMemcpyAsync(rows.data(), d_rows, sizeof(int) * n_seg, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(yaw0, d_yaw0, sizeof(double) * n_tab, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, sizeof(int) * n_tab, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
+      else if (status[0] || status[1])
+        result = set_error(UAVB_EINVAL, "fly_mission_host: degenerate mission (zero-length spline): the reference's KKT matrix is singular");
+    }
+    if (!result) {
+      long long total_rows = 0;
+      for (int s = 0; s < n_seg; ++s) total_rows += rows[s];
+      seg_table[0] = 1; seg_yaw0[0] = yaw0[0];
+      if (n_tab == 2) { seg_table[S0] = 1; seg_yaw0[S0] = yaw0[1]; }
+      const long long whole = total_rows * m->frequency;
+      const int n_ticks = m->n_ticks ? m->n_ticks : (int)(whole < 2147483647LL ? whole : 2147483647LL);
+      if (n_ticks_out) *n_ticks_out = n_ticks;
+
+      uavb_rollout_args a = {};
+      a.B = m->B; a.n_ticks = n_ticks; a.inner_per_outer = m->frequency; a.thrust_frame_lag = m->thrust_frame_lag;
+      a.n_obs = m->n_obs; a.n_obs_sets = m->n_obs > 0 ? 1 : 0;
+      a.veh = m->veh;
+      a.mc_mass = pool.upload(m->mc_mass, B);
+      a.mc_inertia = pool.upload(m->mc_inertia, 3 * B);
+      a.mc_gains = pool.upload(m->mc_gains, UAVB_N_GAINS * B);
+      a.mc_wind = pool.upload(m->mc_wind, 3 * B);
+      a.seg_coeffs = d_coeffs; a.seg_rows = d_rows;
+      a.seg_table = pool.upload(seg_table.data(), n_seg);
+      a.seg_yaw0 = pool.upload(seg_yaw0.data(), n_seg);
+      a.n_seg_shared = n_seg;
+      a.dt_outer = dt_outer;
+      a.start = m->start ? pool.upload(m->start, 3) : d_wp;
+      a.goal = m->goal ? pool.upload(m->goal, 3) : d_wp + 3 * (size_t)(m->n_waypoints - 1);
+      a.aabbs = m->n_obs > 0 ? pool.upload(m->aabbs, (size_t)m->n_obs * 6) : nullptr;
+      float* d_metrics = pool.alloc<float>(B * UAVB_N_METRICS);
+      float* d_state = state_out ? pool.alloc<float>(B * UAVB_STATE_DIM) : nullptr;
+      a.metrics_out = d_metrics; a.state_out = d_state;
+      if (pool.err != cudaSuccess) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
+      if (!result) result = uavb_rollout_f32(&a, st);
+      if (!result && B > 0) {
+        cudaError_t e = cudaMemcpyAsync(metrics_out, d_metrics, sizeof(float) * B * UAVB_N_METRICS, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && state_out) e = cudaMemcpyAsync(state_out, d_state, sizeof(float) * B * UAVB_STATE_DIM, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  return result;
+}
