@@ -122,6 +122,12 @@ int uavb_minsnap_sample_f64(const double* coeffs, const double* times, const int
                             const int* seg_rows, const int* row_offsets, int B, double dt,
                             double* table_out, void* stream);
 
+/* MinimumSnap._calculate_yaws (minimum_snap.py:126-136) on bare velocity rows: heading of the horizontal velocity where
+ * its norm reaches 1e-3, np.unwrap over the valid rows, hold-last-valid, first-valid look-ahead, zeros if none is
+ * valid.  velocities [n_rows][3]; sequence b owns rows [row_offsets[b], row_offsets[b+1]); yaws_out [n_rows]. */
+int uavb_minsnap_yaw_profile_f64(const double* velocities, const int* row_offsets, int B, long long n_rows,
+                                 double* yaws_out, void* stream);
+
 /* Inclusive point-in-AABB over sampled tables, the test of the correction loop
  * (minimum_snap.py:84-87 with is_collision_cuboid :327-357).  For every mission b, ORs into
  * hit_mask_out[b] (uint64, bit s) the splines s that have a sampled row inside `cuboid` (6 doubles,
@@ -205,34 +211,63 @@ int uavb_rollout_f64(const uavb_rollout_args* args, void* stream);
 void uavb_vehicle_defaults(uavb_vehicle* veh);
 
 /* ------------------------------------------------------------------------------------------------
- * Stage-level entry points: one controller / vehicle method for B drones (unit-test granularity).
- * All arrays fp32 SoA of length B unless noted; X is [13][B].
+ * Stage-level entry points: one controller / vehicle method for B drones (unit-test granularity; the
+ * batched Python classes CascadedController / Quad / TrajectoryController call these).
+ * All arrays fp32 SoA with the drone index fastest; X is [13][B].
  *
- *   stage                replaces                                          in                     out
- *   UAVB_STAGE_OUTER     TrajectoryController._update_outer_loop           X, target[10][B],      thrust[B], pqr_cmd[3][B],
- *                        (main.py:47-61)                                   integral[B]            integral (updated)
- *   UAVB_STAGE_INNER     body_rate_controller + set_propeller_speed        X, thrust, pqr_cmd,    moment[3][B], forces[4][B],
- *                        (controller.py:115-130, quad.py:88-122)           omega[4][B]            omega (updated)
- *   UAVB_STAGE_PHYSICS   MujocoSimulation.step (mujoco_sim.py:144-151)     X, omega, zb[3][B]     X (updated)
+ *   stage        replaces                                                  reads                      writes
+ *   OUTER        TrajectoryController._update_outer_loop (main.py:47-61)   X target integral          thrust pqr_cmd integral
+ *   INNER        body_rate_controller + set_propeller_speed (main.py:42-44) X thrust pqr_cmd omega     moment forces omega omega_cmd
+ *   PHYSICS      MujocoSimulation.step (mujoco_sim.py:144-151, free body)  X omega [zb] [wind] [aabbs] X [zb_out] [collided]
+ *   ALTITUDE     CascadedController.altitude (controller.py:26-56)         X target[2,5,8] [rot] integral   thrust integral
+ *   LATERAL      CascadedController.lateral (controller.py:58-97)          X target[0,1,3,4,6,7] thrust     bxy
+ *   ROLL_PITCH   roll_pitch_controller (controller.py:132-154)             bxy, rot or X              pqr_cmd[0..1]
+ *   YAW          yaw_controller (controller.py:156-168)                    X target[9] pqr_cmd[1]     pqr_cmd[2]
+ *   BODY_RATE    body_rate_controller (controller.py:115-130)              X pqr_cmd                  moment
+ *   ALLOCATE     Quad._allocate_rotor_forces (quad.py:105-122)             thrust moment              forces
+ *   PROPELLER    Quad.set_propeller_speed (quad.py:88-103)                 thrust moment omega        forces omega omega_cmd
+ *   ATTITUDE     Quad.R() and phi/theta/psi (quad.py:129-155, 189-213)     X                          rot euler
+ * Arrays a stage does not use may be NULL.  Outputs marked optional in the struct may be NULL as well.
  */
-#define UAVB_STAGE_OUTER   1
-#define UAVB_STAGE_INNER   2
-#define UAVB_STAGE_PHYSICS 3
+#define UAVB_STAGE_OUTER       1
+#define UAVB_STAGE_INNER       2
+#define UAVB_STAGE_PHYSICS     3
+#define UAVB_STAGE_ALTITUDE    4
+#define UAVB_STAGE_LATERAL     5
+#define UAVB_STAGE_ROLL_PITCH  6
+#define UAVB_STAGE_YAW         7
+#define UAVB_STAGE_BODY_RATE   8
+#define UAVB_STAGE_ALLOCATE    9
+#define UAVB_STAGE_PROPELLER  10
+#define UAVB_STAGE_ATTITUDE   11
 typedef struct uavb_stage_args {
   int B;
   int stage;
   uavb_vehicle veh;
-  double dt_outer;
-  float* X;            /* [13][B] */
-  const float* target; /* [10][B]: x y z vx vy vz ax ay az yaw of the table row */
-  float* integral;     /* [B] */
-  float* thrust;       /* [B] */
-  float* pqr_cmd;      /* [3][B] */
-  float* moment;       /* [3][B] */
-  float* forces;       /* [4][B] */
-  float* omega;        /* [4][B] */
-  const float* zb;     /* [3][B] thrust direction (third column of the body rotation) or NULL = from X */
-  const float* wind;   /* [3][B] or NULL */
+  double dt_outer;           /* CascadedController.dt (controller.py:18) */
+  /* optional per-drone overrides, as in uavb_rollout_args (the reference passes gains as method arguments) */
+  const float* mc_mass;      /* [B] */
+  const float* mc_inertia;   /* [3][B] */
+  const float* mc_gains;     /* [UAVB_N_GAINS][B] */
+  const float* wind;         /* [3][B] */
+  float* X;                  /* [13][B] */
+  const float* target;       /* [10][B]: x y z vx vy vz ax ay az yaw of the table row */
+  const float* rot;          /* [9][B] row-major rotation matrix argument of altitude / roll_pitch_controller; NULL = from X */
+  float* integral;           /* [B] CascadedController.integral_error */
+  float* thrust;             /* [B] */
+  float* bxy;                /* [2][B] */
+  float* pqr_cmd;            /* [3][B] */
+  float* moment;             /* [3][B] (optional output of INNER) */
+  float* forces;             /* [4][B] (optional output of INNER / PROPELLER) */
+  float* omega;              /* [4][B] Quad.omega */
+  float* omega_cmd;          /* [4][B] Quad.omega_command (optional output) */
+  const float* zb;           /* [3][B] thrust direction for PHYSICS (third column of the stale body rotation); NULL = from X */
+  float* zb_out;             /* [3][B] PHYSICS: body z axis of the state BEFORE the step (the next call's stale thrust frame) */
+  const float* aabbs;        /* [n_obs][6] PHYSICS: obstacles for the sticky collision flag (minimum_snap.py:327-357) */
+  int n_obs;
+  float* collided;           /* [B] PHYSICS: set to 1 when the body origin is inside a box after the step (never cleared) */
+  float* rot_out;            /* [9][B] ATTITUDE */
+  float* euler_out;          /* [3][B] ATTITUDE: phi theta psi */
 } uavb_stage_args;
 int uavb_stage_f32(const uavb_stage_args* args, void* stream);
 

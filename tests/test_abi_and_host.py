@@ -58,12 +58,12 @@ def test_struct_layouts_match_the_header(nat, tmp_path):
     probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uavb.h"\nint main(void){'
                      'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uavb_vehicle), sizeof(uavb_rollout_args), sizeof(uavb_stage_args),'
                      'offsetof(uavb_vehicle, gains), offsetof(uavb_rollout_args, veh), offsetof(uavb_rollout_args, seg_coeffs),'
-                     'offsetof(uavb_rollout_args, log_out), offsetof(uavb_stage_args, wind));return 0;}\n')
+                     'offsetof(uavb_rollout_args, log_out), offsetof(uavb_stage_args, euler_out));return 0;}\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(nat.Vehicle), ctypes.sizeof(nat.RolloutArgs), ctypes.sizeof(nat.StageArgs), nat.Vehicle.gains.offset,
-            nat.RolloutArgs.veh.offset, nat.RolloutArgs.seg_coeffs.offset, nat.RolloutArgs.log_out.offset, nat.StageArgs.wind.offset]
+            nat.RolloutArgs.veh.offset, nat.RolloutArgs.seg_coeffs.offset, nat.RolloutArgs.log_out.offset, nat.StageArgs.euler_out.offset]
     assert got == want
 
 

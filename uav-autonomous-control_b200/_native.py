@@ -22,12 +22,14 @@ STATE_DIM = 13
 MAX_SPLINES = 64
 GAIN_NAMES = ("kp_xy", "kd_xy", "kp_z", "kd_z", "ki_z", "kp_roll", "kp_pitch", "kp_yaw", "kp_p", "kp_q", "kp_r")
 M_FINAL_DIST, M_COLLISION, M_RMSE, M_MEAN_ERR, M_MAX_ERR, M_STATUS, M_FIRST_HIT, M_PERIODS = range(8)
-STAGE_OUTER, STAGE_INNER, STAGE_PHYSICS = 1, 2, 3
+(STAGE_OUTER, STAGE_INNER, STAGE_PHYSICS, STAGE_ALTITUDE, STAGE_LATERAL, STAGE_ROLL_PITCH, STAGE_YAW, STAGE_BODY_RATE, STAGE_ALLOCATE,
+ STAGE_PROPELLER, STAGE_ATTITUDE) = range(1, 12)
 
 # every symbol include/uavb.h declares (tests check the library exports all of them)
 SYMBOLS = (
     "uavb_version", "uavb_last_error", "uavb_device_count", "uavb_device_info", "uavb_minsnap_solve_f64",
-    "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_table_hits_f64",
+    "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_yaw_profile_f64",
+    "uavb_minsnap_table_hits_f64",
     "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
     "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host",
 )
@@ -67,8 +69,10 @@ class StageArgs(Structure):
     """struct uavb_stage_args (include/uavb.h)."""
     _fields_ = [
         ("B", c_int), ("stage", c_int), ("veh", Vehicle), ("dt_outer", c_double),
-        ("X", c_void_p), ("target", c_void_p), ("integral", c_void_p), ("thrust", c_void_p), ("pqr_cmd", c_void_p),
-        ("moment", c_void_p), ("forces", c_void_p), ("omega", c_void_p), ("zb", c_void_p), ("wind", c_void_p),
+        ("mc_mass", c_void_p), ("mc_inertia", c_void_p), ("mc_gains", c_void_p), ("wind", c_void_p),
+        ("X", c_void_p), ("target", c_void_p), ("rot", c_void_p), ("integral", c_void_p), ("thrust", c_void_p), ("bxy", c_void_p),
+        ("pqr_cmd", c_void_p), ("moment", c_void_p), ("forces", c_void_p), ("omega", c_void_p), ("omega_cmd", c_void_p), ("zb", c_void_p),
+        ("zb_out", c_void_p), ("aabbs", c_void_p), ("n_obs", c_int), ("collided", c_void_p), ("rot_out", c_void_p), ("euler_out", c_void_p),
     ]
 
 
@@ -102,6 +106,7 @@ def lib() -> ctypes.CDLL:
     L.uavb_minsnap_solve_ragged_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]
     L.uavb_minsnap_table_meta_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]
     L.uavb_minsnap_sample_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]
+    L.uavb_minsnap_yaw_profile_f64.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]
     L.uavb_minsnap_table_hits_f64.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
     L.uavb_rollout_f32.argtypes = [POINTER(RolloutArgs), c_void_p]
     L.uavb_rollout_f64.argtypes = [POINTER(RolloutArgs), c_void_p]

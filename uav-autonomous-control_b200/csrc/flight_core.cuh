@@ -171,111 +171,155 @@ template <class R> UAVB_HD void body_z(const Drone<R>& d, R* zx, R* zy, R* zz) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Outer loop: TrajectoryController._update_outer_loop (main.py:47-61) on the fresh state.
-// Requires a folded position (d.dx = d.dy = d.dz = 0).
-template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, const Target& t) {
-  typedef Math<R> M;
-  const R q0 = d.q0, q1 = d.q1, q2 = d.q2, q3 = d.q3;
-  // quad.py:153 for a unit quaternion (the state is re-normalised every tick)
-  const R R00 = R(1) - R(2) * (q2 * q2 + q3 * q3), R01 = R(2) * (q1 * q2 - q0 * q3), R02 = R(2) * (q1 * q3 + q0 * q2);
-  const R R10 = R(2) * (q1 * q2 + q0 * q3), R11 = R(1) - R(2) * (q1 * q1 + q3 * q3), R12 = R(2) * (q2 * q3 - q0 * q1);
-  const R R22 = R(1) - R(2) * (q1 * q1 + q2 * q2);
-  const R inv_R22 = M::rcp_fast(R22);
+// Outer-loop stages.  Each is one method of CascadedController; outer_update chains them exactly like
+// TrajectoryController._update_outer_loop (main.py:47-61), and the stage kernels expose them one by one.
 
-  // altitude (controller.py:26-56); position errors are formed in fp64 and rounded once
-  const R climb = clampr<R>((R)t.vz, -u.max_ascent, u.max_descent);
-  const R ez = (R)(t.z - d.pz);
-  const R ezd = climb - d.vz;
-  d.integral = clampr<R>(d.integral + ez * u.dt_outer, -u.integral_limit, u.integral_limit);
-  R acc_z = v.kp_z * ez + v.ki_z * d.integral + v.kd_z * ezd + (R)t.az - u.g;
+// Entries of R(q) the outer loop reads (quad.py:153, unit quaternion).
+template <class R> struct RotE {
+  R R00, R01, R02, R10, R11, R12, R22;
+};
+template <class R> UAVB_HD RotE<R> rot_entries(R q0, R q1, R q2, R q3) {
+  RotE<R> r;
+  r.R00 = R(1) - R(2) * (q2 * q2 + q3 * q3); r.R01 = R(2) * (q1 * q2 - q0 * q3); r.R02 = R(2) * (q1 * q3 + q0 * q2);
+  r.R10 = R(2) * (q1 * q2 + q0 * q3); r.R11 = R(1) - R(2) * (q1 * q1 + q3 * q3); r.R12 = R(2) * (q2 * q3 - q0 * q1);
+  r.R22 = R(1) - R(2) * (q1 * q1 + q2 * q2);
+  return r;
+}
+
+// CascadedController.altitude (controller.py:26-56): collective thrust command; updates the integrator.
+// ez = z_des - z (formed in fp64 by the caller and rounded once).
+template <class R>
+UAVB_HD R altitude_cmd(R& integral, const VehU<R>& u, const VehP<R>& v, R ez, R vz, R vz_des, R az_des, R inv_R22) {
+  const R climb = clampr<R>(vz_des, -u.max_ascent, u.max_descent);
+  const R ezd = climb - vz;
+  integral = clampr<R>(integral + ez * u.dt_outer, -u.integral_limit, u.integral_limit);
+  R acc_z = v.kp_z * ez + v.ki_z * integral + v.kd_z * ezd + az_des - u.g;
   acc_z = acc_z * inv_R22;
-  const R c = clampr<R>(-v.mass * acc_z, u.fmin4, u.fmax4);
-  set_thrust_cmd<R>(d, u, c);
+  return clampr<R>(-v.mass * acc_z, u.fmin4, u.fmax4);
+}
 
-  // lateral (controller.py:58-97)
-  R vxd = (R)t.vx, vyd = (R)t.vy;
+// CascadedController.lateral (controller.py:58-97): commanded R02, R12.  ex, ey = p_des - p.
+template <class R>
+UAVB_HD void lateral_cmd(const VehU<R>& u, const VehP<R>& v, R ex, R ey, R vx, R vy, R vxd, R vyd, R axd, R ayd, R c, R* bx, R* by) {
+  typedef Math<R> M;
   const R vm2 = vxd * vxd + vyd * vyd;
   if (vm2 > u.max_speed_xy * u.max_speed_xy) {
     const R s = u.max_speed_xy * M::rsqrt(vm2);
     vxd *= s; vyd *= s;
   }
-  R ax = v.kp_xy * (R)(t.x - d.px) + v.kd_xy * (vxd - d.vx) + (R)t.ax;
-  R ay = v.kp_xy * (R)(t.y - d.py) + v.kd_xy * (vyd - d.vy) + (R)t.ay;
+  R ax = v.kp_xy * ex + v.kd_xy * (vxd - vx) + axd;
+  R ay = v.kp_xy * ey + v.kd_xy * (vyd - vy) + ayd;
   const R am2 = ax * ax + ay * ay;
   if (am2 > u.max_acc_xy * u.max_acc_xy) {
     const R s = u.max_acc_xy * M::rsqrt(am2);
     ax *= s; ay *= s;
   }
   const R inv_accz = -v.mass * M::rcp_fast(c);    // 1 / (-c/m)
-  const R bx = clampr<R>(ax * inv_accz, -u.max_tilt, u.max_tilt);
-  const R by = clampr<R>(ay * inv_accz, -u.max_tilt, u.max_tilt);
+  *bx = clampr<R>(ax * inv_accz, -u.max_tilt, u.max_tilt);
+  *by = clampr<R>(ay * inv_accz, -u.max_tilt, u.max_tilt);
+}
 
-  // roll / pitch rates (controller.py:132-154)
-  const R bdx = v.kp_roll * (bx - R02);
-  const R bdy = v.kp_pitch * (by - R12);
-  const R p_c = (R10 * bdx - R00 * bdy) * inv_R22;
-  const R q_c = (R11 * bdx - R01 * bdy) * inv_R22;
+// CascadedController.roll_pitch_controller (controller.py:132-154).
+template <class R> UAVB_HD void roll_pitch_cmd(const VehP<R>& v, R bx, R by, const RotE<R>& r, R inv_R22, R* p_c, R* q_c) {
+  const R bdx = v.kp_roll * (bx - r.R02);
+  const R bdy = v.kp_pitch * (by - r.R12);
+  *p_c = (r.R10 * bdx - r.R00 * bdy) * inv_R22;
+  *q_c = (r.R11 * bdx - r.R01 * bdy) * inv_R22;
+}
 
-  // yaw rate (controller.py:156-168); Euler angles of quad.py:189-213 without the trig round trip:
-  // phi = atan2(a, b) -> sin = a/h, cos = b/h; theta = asin(s) -> cos = sqrt(1-s^2)
+// CascadedController.yaw_controller (controller.py:156-168) with the Euler angles of quad.py:189-213 taken without the
+// trig round trip: phi = atan2(a, b) -> sin = a/h, cos = b/h; theta = asin(s) -> cos = sqrt(1 - s^2).
+// The yaw error wrap_to_pi(wrap_to_2pi(psi_des) - psi) (controller.py:164-165) is ONE atan2 of the rotated heading:
+// with (cp, sp) ~ (cos psi, sin psi) from quad.py:208-213, atan2(ys cp - yc sp, yc cp + ys sp) is the angle from psi
+// to psi_des in (-pi, pi] (the reference's floored modulo gives [-pi, pi): they differ only at exactly +-pi).
+template <class R> UAVB_HD R yaw_rate_cmd(const VehP<R>& v, R q0, R q1, R q2, R q3, R yc, R ys, R q_c) {
+  typedef Math<R> M;
+  const R R22 = R(1) - R(2) * (q1 * q1 + q2 * q2);
   const R sa = R(2) * (q0 * q1 + q2 * q3);
   const R ih = M::rsqrt(sa * sa + R22 * R22);
   const R sin_phi = sa * ih, cos_phi = R22 * ih;
   const R sin_th = clampr<R>(R(2) * (q0 * q2 - q3 * q1), R(-1), R(1));
   const R cos_th = M::sqrt_fast(R(1) - sin_th * sin_th);
-  // yaw error wrap_to_pi(wrap_to_2pi(psi_des) - psi) (controller.py:164-165) as ONE atan2 of the rotated heading:
-  // with (cp, sp) ~ (cos psi, sin psi) from quad.py:208-213, atan2(ys cp - yc sp, yc cp + ys sp) is the angle from
-  // psi to psi_des in (-pi, pi] (the reference's floored modulo gives [-pi, pi): they differ only at exactly +-pi).
   const R sp = R(2) * (q0 * q3 + q1 * q2), cp = R(1) - R(2) * (q2 * q2 + q3 * q3);
-  const R yc = (R)t.yc, ys = (R)t.ys;
   const R e_yaw = M::atan2(ys * cp - yc * sp, yc * cp + ys * sp);
-  const R r_c = (v.kp_yaw * e_yaw * cos_th - q_c * sin_phi) * M::rcp_fast(cos_phi);
+  return (v.kp_yaw * e_yaw * cos_th - q_c * sin_phi) * M::rcp_fast(cos_phi);
+}
 
-  d.pc = p_c; d.qc = q_c; d.rc = r_c;
+// TrajectoryController._update_outer_loop (main.py:47-61) on the fresh state.
+// Requires a folded position (d.dx = d.dy = d.dz = 0).
+template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, const Target& t) {
+  const RotE<R> r = rot_entries<R>(d.q0, d.q1, d.q2, d.q3);
+  const R inv_R22 = Math<R>::rcp_fast(r.R22);
+  // position errors are formed in fp64 and rounded once
+  const R c = altitude_cmd<R>(d.integral, u, v, (R)(t.z - d.pz), d.vz, (R)t.vz, (R)t.az, inv_R22);
+  set_thrust_cmd<R>(d, u, c);
+  R bx, by;
+  lateral_cmd<R>(u, v, (R)(t.x - d.px), (R)(t.y - d.py), d.vx, d.vy, (R)t.vx, (R)t.vy, (R)t.ax, (R)t.ay, c, &bx, &by);
+  R p_c, q_c;
+  roll_pitch_cmd<R>(v, bx, by, r, inv_R22, &p_c, &q_c);
+  d.pc = p_c; d.qc = q_c;
+  d.rc = yaw_rate_cmd<R>(v, d.q0, d.q1, d.q2, d.q3, (R)t.yc, (R)t.ys, q_c);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Inner loop, part 1: body-rate controller + allocation + motor lag (main.py:42-44).
-// Returns the gyroscopic term w x (I w) of the CURRENT state, which the physics step reuses.
-template <class R>
-UAVB_HD void inner_control(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R* gx, R* gy, R* gz, R* moment_out, R* forces_out) {
+// Inner-loop stages (main.py:42-44).
+
+// CascadedController.body_rate_controller (controller.py:115-130): M = I kp (cmd - w) + w x (I w).  With a diagonal
+// inertia w x (I w) = (dIx wy wz, dIy wz wx, dIz wx wy); it is returned because the physics step reuses it.
+template <class R> UAVB_HD void body_rate_moment(const Drone<R>& d, const VehP<R>& v, R* g, R* Mo) {
   typedef Math<R> M;
-  // controller.py:115-130; diagonal inertia => w x (I w) = (dIx wy wz, dIy wz wx, dIz wx wy)
-  const R gx_ = v.dIx * (d.wy * d.wz), gy_ = v.dIy * (d.wz * d.wx), gz_ = v.dIz * (d.wx * d.wy);
-  *gx = gx_; *gy = gy_; *gz = gz_;
-  const R Mx = M::fma(v.Ikp_p, d.pc - d.wx, gx_);
-  const R My = M::fma(v.Ikp_q, d.qc - d.wy, gy_);
-  const R Mz = M::fma(v.Ikp_r, d.rc - d.wz, gz_);
-  // quad.py:105-122: mixer rows (+,+,+) (-,+,-) (-,-,+) (+,-,-) on [p_bar q_bar r_bar] / 4
-  const R coll = d.coll;
-  const R pb = Mx * u.inv_arm4, qb = My * u.inv_arm4, rb = -Mz * u.inv_kappa4;
+  g[0] = v.dIx * (d.wy * d.wz); g[1] = v.dIy * (d.wz * d.wx); g[2] = v.dIz * (d.wx * d.wy);
+  Mo[0] = M::fma(v.Ikp_p, d.pc - d.wx, g[0]);
+  Mo[1] = M::fma(v.Ikp_q, d.qc - d.wy, g[1]);
+  Mo[2] = M::fma(v.Ikp_r, d.rc - d.wz, g[2]);
+}
+
+// Quad._allocate_rotor_forces (quad.py:105-122): mixer rows (+,+,+) (-,+,-) (-,-,+) (+,-,-) on [p_bar q_bar r_bar] / 4;
+// `coll` = clip(thrust_cmd, 4 fmin, 4 fmax) / 4.
+template <class R> UAVB_HD void allocate_forces(const VehU<R>& u, R coll, const R* Mo, R* f) {
+  typedef Math<R> M;
+  const R pb = Mo[0] * u.inv_arm4, qb = Mo[1] * u.inv_arm4, rb = -Mo[2] * u.inv_kappa4;
   const R s1 = pb + qb, s2 = pb - qb;
   const R m0 = s1 + rb, m1 = -(s2 + rb), m2 = rb - s1, m3 = s2 - rb;
   const R room_hi = u.fmax - coll, room_lo = u.fmin - coll;
   const R m_hi = M::fmax(M::fmax(m0, m1), M::fmax(m2, m3)), m_lo = M::fmin(M::fmin(m0, m1), M::fmin(m2, m3));
-  R f0, f1, f2, f3;
   if (m_hi <= room_hi && m_lo >= room_lo) {
     // no rotor limit binds: every ratio of quad.py:116-119 is >= 1, the scale is 1 and the final clip is the identity
-    f0 = coll + m0; f1 = coll + m1; f2 = coll + m2; f3 = coll + m3;
+    f[0] = coll + m0; f[1] = coll + m1; f[2] = coll + m2; f[3] = coll + m3;
   } else {
     const R l0 = (m0 > R(0)) ? M::div(room_hi, m0) : ((m0 < R(0)) ? M::div(room_lo, m0) : R(1));
     const R l1 = (m1 > R(0)) ? M::div(room_hi, m1) : ((m1 < R(0)) ? M::div(room_lo, m1) : R(1));
     const R l2 = (m2 > R(0)) ? M::div(room_hi, m2) : ((m2 < R(0)) ? M::div(room_lo, m2) : R(1));
     const R l3 = (m3 > R(0)) ? M::div(room_hi, m3) : ((m3 < R(0)) ? M::div(room_lo, m3) : R(1));
     const R s = clampr<R>(M::fmin(M::fmin(l0, l1), M::fmin(l2, l3)), R(0), R(1));
-    f0 = clampr<R>(M::fma(s, m0, coll), u.fmin, u.fmax);
-    f1 = clampr<R>(M::fma(s, m1, coll), u.fmin, u.fmax);
-    f2 = clampr<R>(M::fma(s, m2, coll), u.fmin, u.fmax);
-    f3 = clampr<R>(M::fma(s, m3, coll), u.fmin, u.fmax);
+    f[0] = clampr<R>(M::fma(s, m0, coll), u.fmin, u.fmax);
+    f[1] = clampr<R>(M::fma(s, m1, coll), u.fmin, u.fmax);
+    f[2] = clampr<R>(M::fma(s, m2, coll), u.fmin, u.fmax);
+    f[3] = clampr<R>(M::fma(s, m3, coll), u.fmin, u.fmax);
   }
-  // quad.py:88-103
-  const R c0 = M::sqrt_fast(f0 * u.inv_kf), c1 = M::sqrt_fast(f1 * u.inv_kf), c2 = M::sqrt_fast(f2 * u.inv_kf), c3 = M::sqrt_fast(f3 * u.inv_kf);
+}
+
+// Quad.set_propeller_speed after the allocation (quad.py:95-103): w_cmd = sqrt(f / kf), asymmetric first-order lag.
+template <class R> UAVB_HD void motor_lag(Drone<R>& d, const VehU<R>& u, const R* f, R* cmd_out) {
+  typedef Math<R> M;
+  const R c0 = M::sqrt_fast(f[0] * u.inv_kf), c1 = M::sqrt_fast(f[1] * u.inv_kf), c2 = M::sqrt_fast(f[2] * u.inv_kf), c3 = M::sqrt_fast(f[3] * u.inv_kf);
   d.om0 = M::fma((c0 > d.om0) ? u.a_rise : u.a_fall, c0 - d.om0, d.om0);
   d.om1 = M::fma((c1 > d.om1) ? u.a_rise : u.a_fall, c1 - d.om1, d.om1);
   d.om2 = M::fma((c2 > d.om2) ? u.a_rise : u.a_fall, c2 - d.om2, d.om2);
   d.om3 = M::fma((c3 > d.om3) ? u.a_rise : u.a_fall, c3 - d.om3, d.om3);
-  if (moment_out) { moment_out[0] = Mx; moment_out[1] = My; moment_out[2] = Mz; }
-  if (forces_out) { forces_out[0] = f0; forces_out[1] = f1; forces_out[2] = f2; forces_out[3] = f3; }
+  if (cmd_out) { cmd_out[0] = c0; cmd_out[1] = c1; cmd_out[2] = c2; cmd_out[3] = c3; }
+}
+
+// Body-rate controller + allocation + motor lag; returns the gyroscopic term of the CURRENT state.
+template <class R>
+UAVB_HD void inner_control(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R* gx, R* gy, R* gz, R* moment_out, R* forces_out) {
+  R g[3], Mo[3], f[4];
+  body_rate_moment<R>(d, v, g, Mo);
+  *gx = g[0]; *gy = g[1]; *gz = g[2];
+  allocate_forces<R>(u, d.coll, Mo, f);
+  motor_lag<R>(d, u, f, nullptr);
+  if (moment_out) { moment_out[0] = Mo[0]; moment_out[1] = Mo[1]; moment_out[2] = Mo[2]; }
+  if (forces_out) { forces_out[0] = f[0]; forces_out[1] = f[1]; forces_out[2] = f[2]; forces_out[3] = f[3]; }
 }
 
 // Inner loop, part 2: rotor wrench with the given thrust axis + free-body semi-implicit Euler step

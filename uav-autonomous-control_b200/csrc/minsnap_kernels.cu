@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(128) sample_rows_kernel(const double* __restri
   }
 }
 
-__global__ void __launch_bounds__(128) sample_yaw_kernel(const int* __restrict__ row_offsets, int B, double* __restrict__ table) {
+// `col` points at the yaw entry of row 0 and consecutive rows are `stride` doubles apart (11 inside a table, 1 for a
+// bare yaw vector).
+__global__ void __launch_bounds__(128) sample_yaw_kernel(const int* __restrict__ row_offsets, int B, double* __restrict__ col, int stride) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const long long r0 = row_offsets[b], r1 = row_offsets[b + 1];
@@ -162,16 +164,16 @@ __global__ void __launch_bounds__(128) sample_yaw_kernel(const int* __restrict__
   double first = 0.0;
   long long rf = r1;
   for (long long r = r0; r < r1; ++r) {
-    const double y = table[(size_t)r * 11 + 9];
+    const double y = col[(size_t)r * stride];
     if (y == y) { first = y; rf = r; break; }
   }
   if (rf == r1) {                       // no valid row: all zeros (minimum_snap.py:130-131)
-    for (long long r = r0; r < r1; ++r) table[(size_t)r * 11 + 9] = 0.0;
+    for (long long r = r0; r < r1; ++r) col[(size_t)r * stride] = 0.0;
     return;
   }
   double prev_raw = first, hold = first;
   for (long long r = r0; r < r1; ++r) {
-    double* y = table + (size_t)r * 11 + 9;
+    double* y = col + (size_t)r * stride;
     const double raw = *y;
     if (r > rf && raw == raw) {
       // np.unwrap: dd = raw - prev_raw; ddmod = mod(dd + pi, 2 pi) - pi, with -pi -> +pi when dd > 0;
@@ -187,6 +189,14 @@ __global__ void __launch_bounds__(128) sample_yaw_kernel(const int* __restrict__
     }
     *y = hold;
   }
+}
+
+// Raw heading of every velocity row: atan2(vy, vx) where the horizontal speed reaches the threshold, NaN elsewhere.
+__global__ void __launch_bounds__(256) yaw_raw_kernel(const double* __restrict__ vel, long long n, double* __restrict__ yaw) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double vx = vel[3 * r], vy = vel[3 * r + 1];
+  yaw[r] = (sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy))) >= 1e-3) ? atan2(vy, vx) : nan("");
 }
 
 // Sampled-point AABB test of the correction loop (minimum_snap.py:84-87): one warp per mission.
@@ -276,7 +286,22 @@ extern "C" int uavb_minsnap_sample_f64(const double* coeffs, const double* times
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sample_rows_kernel<<<div_up((long long)B * 32, 128), 128, 0, st>>>(coeffs, seg_offsets, seg_rows, row_offsets, B, dt, table_out);
   UAVB_CUDA_OK(cudaGetLastError());
-  sample_yaw_kernel<<<div_up(B, 128), 128, 0, st>>>(row_offsets, B, table_out);
+  sample_yaw_kernel<<<div_up(B, 128), 128, 0, st>>>(row_offsets, B, table_out + 9, 11);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+extern "C" int uavb_minsnap_yaw_profile_f64(const double* velocities, const int* row_offsets, int B, long long n_rows, double* yaws_out,
+                                            void* stream) {
+  UAVB_REQUIRE(velocities && row_offsets && yaws_out, "yaw_profile: NULL pointer");
+  UAVB_REQUIRE(B >= 0 && n_rows >= 0, "yaw_profile: B and n_rows must be >= 0");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0 || n_rows == 0) return UAVB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  yaw_raw_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(velocities, n_rows, yaws_out);
+  UAVB_CUDA_OK(cudaGetLastError());
+  sample_yaw_kernel<<<div_up(B, 128), 128, 0, st>>>(row_offsets, B, yaws_out, 1);
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }
