@@ -299,3 +299,41 @@ def test_host_buffer_entry_point_matches_device_path_and_reference(cuda, golden)
     assert n1 == 500 and met1[0, 7] == 50 and np.isfinite(met1).all()
     with pytest.raises(Exception):
         host_api.fly_mission_host(np.array([[0.0, 0, 0], [0, 0, 0], [1, 0, 0]]), 3.0, 2, n_takeoff_waypoints=2)   # zero-length take-off
+
+
+def test_montecarlo_batch_matches_c_oracle_on_every_rollout(cuda, golden):
+    """BASELINE configs[2] at reduced size with EVERY rollout checked: 2 048 perturbed vehicles (counter-based generator)
+    fly the whole lab_course mission on the GPU and in the C twin of the oracle (fp64, same fp32-rounded inputs)."""
+    import os
+    import torch
+    from oracle import c_port, flight_np
+    from uav_ac_b200 import kernels, _native as nat
+    g = golden["planning"]
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * int(plan.total_rows.item())
+    B = 2048
+    sc = kernels.mc_uniform(77, B, [0.8] * 11 + [0.9] * 4, [1.2] * 11 + [1.1] * 4)
+    v = nat.default_vehicle()
+    base = torch.tensor(list(v.gains) + [v.mass] + list(v.inertia), dtype=torch.float32, device=cuda)[:, None]
+    vals = (sc * base).contiguous()
+    obs = torch.tensor(g["obstacles"], dtype=torch.float32, device=cuda)
+    res = _fly(cuda, plan, B, n, obstacles=obs, mc_gains=vals[:11].contiguous(), mc_mass=vals[11].contiguous(), mc_inertia=vals[12:15].contiguous())
+    met, X = res.metrics.double().cpu().numpy(), res.state.double().cpu().numpy().T
+    vals = vals.double().cpu().numpy()
+    vehs = []
+    for b in range(B):
+        kw = {k: getattr(flight_np.Vehicle(), k) for k in flight_np.Vehicle.__dataclass_fields__}
+        for k, name in enumerate(flight_np.Vehicle.GAIN_NAMES):
+            kw[name] = vals[k, b]
+        kw["mass"], kw["inertia"] = vals[11, b], vals[12:15, b]
+        vehs.append(flight_np.Vehicle(**kw))
+    tab = c_port.mission_table(g["waypoints"], 3.0, 0.01)                      # solve-branch coefficients, like K1
+    m_ref, X_ref = c_port.closed_loop_batch(vehs, tab, g["waypoints"][0], obstacles=g["obstacles"], goal=GOAL, threads=os.cpu_count() or 1)
+    dp = np.abs(X[:, :3] - X_ref[:, :3]).max(axis=1)
+    da = rotation_angle(X[:, 3:7], X_ref[:, 3:7])
+    print(f"2048 rollouts: max |dpos| {dp.max():.2e} m (median {np.median(dp):.2e}), max attitude {da.max():.2e} rad")
+    assert dp.max() < POS_TOL and da.max() < ANG_TOL
+    assert np.array_equal(met[:, 1], m_ref[:, 1])                              # collision flags bit-exact
+    assert np.abs(met[:, 0] - m_ref[:, 0]).max() < POS_TOL and np.abs(met[:, 3] - m_ref[:, 3]).max() < 2e-5
+    assert np.abs(met[:, 2] - m_ref[:, 2]).max() < 2e-5 and np.abs(met[:, 4] - m_ref[:, 4]).max() < POS_TOL
+    assert (met[:, 7] == m_ref[:, 7]).all() and (met[:, 5] == 0).all()
