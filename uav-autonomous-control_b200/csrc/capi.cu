@@ -27,6 +27,30 @@ int require_device() {
   return UAVB_OK;
 }
 
+cudaMemPool_t scratch_pool() {
+  static cudaMemPool_t pools[64] = {nullptr};
+  static bool tried[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!tried[dev]) {
+    tried[dev] = true;
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      pools[dev] = pool;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return pools[dev];
+}
+
 // Dependent-chain-free FMA loops: 8 independent accumulators per thread, enough CTAs to fill the chip.
 template <class T> __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
   T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -18,7 +18,10 @@ struct DevPool {
   }
   template <class T> T* alloc(size_t n) {
     void* p = nullptr;
-    if (err == cudaSuccess) err = cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
+    if (err == cudaSuccess) {
+      cudaMemPool_t pool = scratch_pool();
+      err = pool ? cudaMallocFromPoolAsync(&p, (n ? n : 1) * sizeof(T), pool, st) : cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
+    }
     if (err == cudaSuccess) owned.push_back(p);
     return static_cast<T*>(p);
   }

@@ -11,6 +11,8 @@
 //   * metrics / final state / carry (once).
 // Nothing here is a dense contraction, so no tensor-core path exists; the bound is the FP32 issue
 // rate (metrics-only) or HBM (full-rate log).  See DESIGN.md "K2".
+#include <stdlib.h>
+
 #include "rollout_core.cuh"
 #include "uavb_common.cuh"
 #include "veh_setup.cuh"
@@ -18,12 +20,13 @@
 namespace uavb {
 
 constexpr int kRolloutThreads = 64;
-// Residency.  The kernel is compiled for K = 8..12 CTAs of 64 threads per SM (register cap 128 .. 80).  K = 12 keeps
-// 24 warps per SM resident, so the 100 000 rollouts of BASELINE configs[2] (1 563 CTAs, 10.6 per SM) fit in one wave --
-// but the hardware then places up to 12 CTAs on some SMs and 9-10 on others, and the launch lasts as long as the
-// fullest SM.  The launcher therefore picks K = ceil(CTAs / SMs) when that lies in 8..11: the register cap of that
-// variant makes K+1 CTAs impossible, every SM receives at most K, and the extra registers remove spills.
+// Residency variants: K CTAs of 64 threads per SM, i.e. a register cap of 128 (K = 8), 96 (K = 10) or 80 (K = 12).
+// Measured on B200 (tools/k_sweep.py, profiles/): K = 8 sustains the highest tick rate -- the spill-free 128-register
+// body with 16 warps per SM beats 24 warps at 80 registers (139 vs 126 G ticks/s at 5e5 rollouts) -- so it is the
+// default; the other variants remain selectable for experiments (UAVB_ROLLOUT_K).
 constexpr int kRolloutCtasMin = 8, kRolloutCtasMax = 12;
+// registers per thread for K resident CTAs (allocated per warp in units of 512, i.e. 16 per thread: 80 -> 12 CTAs, 96 -> 10, 128 -> 8)
+constexpr int rollout_regs(int K) { return K >= 12 ? 80 : K >= 10 ? 96 : 128; }
 
 template <class R> struct RolloutDev {
   uavb_rollout_args a;
@@ -114,23 +117,16 @@ struct Carry {
   }
 };
 
-// MC: some per-rollout override (mass / inertia / gains / wind) is present; otherwise every vehicle
-// constant is a constant-bank operand.
-// registers per thread that let exactly K CTAs of 64 threads share the 64 K-register file of an SM
-constexpr int rollout_regs(int K) { return K >= 12 ? 80 : K == 11 ? 88 : K == 10 ? 96 : K == 9 ? 112 : 128; }
-
-template <class R, bool LOG, bool MC, int K>
-__global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constant__ RolloutDev<R> p) {
-  extern __shared__ float s_boxes[];
+// One drone, one slice of its mission: `n_ticks` ticks starting from the carry block (from_carry) or from the start
+// pose; writes the carry block (to_carry) and / or the final outputs (finish).
+// MC: some per-rollout override (mass / inertia / gains / wind) is present; otherwise every vehicle constant is a
+// constant-bank operand.
+template <class R, bool LOG, bool MC>
+__device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float* s_boxes, long long i, int n_ticks, bool from_carry,
+                                            bool to_carry, bool finish) {
   const uavb_rollout_args& a = p.a;
-  const bool shared_boxes = a.n_obs > 0 && a.aabb_set == nullptr;
-  if (shared_boxes) {
-    for (int j = threadIdx.x; j < a.n_obs * 6; j += blockDim.x) s_boxes[j] = a.aabbs[j];
-    __syncthreads();
-  }
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.B) return;
   const long long B = a.B;
+  const bool shared_boxes = a.n_obs > 0 && a.aabb_set == nullptr;
 
   // per-rollout constants
   VehP<R> vloc;
@@ -161,7 +157,7 @@ __global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constan
   int tick0 = 0;
   bool resumed = false;
   if constexpr (sizeof(R) == 4) {
-    if (a.resume) {
+    if (from_carry) {
       Carry cb{a.carry + i, B};
       cb.load(d, c, acc, u, &tick0);
       resumed = true;
@@ -179,10 +175,10 @@ __global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constan
       GlobalLog<R> lg;
       lg.out = reinterpret_cast<R*>(a.log_out) + i;
       lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride;
-      rollout_run<R>(d, c, acc, u, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+      rollout_run<R>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
     } else {
       NoLog lg;
-      rollout_run<R>(d, c, acc, u, v, m, tick0, a.n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+      rollout_run<R>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
     }
   };
   if (a.n_obs > 0) {
@@ -195,11 +191,12 @@ __global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constan
   }
 
   if constexpr (sizeof(R) == 4) {
-    if (a.carry) {
+    if (to_carry) {
       Carry cb{a.carry + i, B};
-      cb.store(d, c, acc, tick0 + a.n_ticks);
+      cb.store(d, c, acc, tick0 + n_ticks);
     }
   }
+  if (!finish) return;
   const double fx = d.px + (double)d.dx, fy = d.py + (double)d.dy, fz = d.pz + (double)d.dz;
   if (a.state_out) {
     R* o = reinterpret_cast<R*>(a.state_out) + i;
@@ -225,6 +222,76 @@ __global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constan
     o[UAVB_M_STATUS] = (R)acc.status;
     o[UAVB_M_FIRST_HIT] = (R)acc.first_hit;
     o[UAVB_M_PERIODS] = (R)acc.periods;
+  }
+}
+
+__device__ __forceinline__ void stage_shared_boxes(const uavb_rollout_args& a, float* s_boxes) {
+  if (a.n_obs > 0 && a.aabb_set == nullptr) {
+    for (int j = threadIdx.x; j < a.n_obs * 6; j += blockDim.x) s_boxes[j] = a.aabbs[j];
+    __syncthreads();
+  }
+}
+
+// One-shot launch: thread i flies drone i for the whole launch.  K = residency variant (CTAs per SM).
+template <class R, bool LOG, bool MC, int K>
+__global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constant__ RolloutDev<R> p) {
+  extern __shared__ float s_boxes[];
+  stage_shared_boxes(p.a, s_boxes);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.a.B) return;
+  drone_slice<R, LOG, MC>(p, s_boxes, i, p.a.n_ticks, p.a.resume != 0, p.a.carry != nullptr, true);
+}
+
+// Time-sliced persistent launch (every metrics-only fp32 rollout).  When the batch needs between one and a few waves of
+// CTAs, a one-shot launch ends with a long tail: every CTA lives for the whole mission, so the last partial wave costs a full
+// mission time at a fraction of the machine.  Here the grid is exactly the resident capacity, the mission is cut into
+// `n_chunks` slices of `chunk_ticks` ticks, and CTAs pull (chunk, group) items from an atomic counter in chunk-major
+// order; between slices a drone's state rests in the carry block (208 B per drone and slice, ~0.2 B per tick).  Item
+// (c, g) needs (c-1, g), which was handed out one full sweep of the groups earlier, so the wait on its completion flag
+// practically never spins -- and cannot deadlock, because whoever holds the earlier item is running.  The tail shrinks
+// from one mission to one slice.
+struct SliceSched {
+  int* counter;        // next item
+  int* done;           // [n_groups] slices completed per group
+  int n_groups, n_chunks, chunk_ticks;
+  int final_carry;     // the caller asked for the carry block of the end state
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <bool MC, int K>
+__global__ void __maxnreg__(rollout_regs(K)) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
+  extern __shared__ float s_boxes[];
+  __shared__ int s_item;
+  stage_shared_boxes(p.a, s_boxes);
+  const int n_items = sch.n_groups * sch.n_chunks;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const int it = atomicAdd(sch.counter, 1);
+      if (it < n_items) {
+        const int c = it / sch.n_groups, g = it - c * sch.n_groups;
+        while (ld_acquire_gpu(sch.done + g) < c) __nanosleep(200);
+      }
+      s_item = it;
+    }
+    __syncthreads();
+    const int it = s_item;
+    if (it >= n_items) return;
+    const int c = it / sch.n_groups, g = it - c * sch.n_groups;
+    const long long i = (long long)g * blockDim.x + threadIdx.x;
+    if (i < p.a.B) {
+      const bool last = c == sch.n_chunks - 1;
+      const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
+      drone_slice<float, false, MC>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(sch.done + g, c + 1);
   }
 }
 
@@ -265,6 +332,26 @@ static int sm_count_cached(int* sms) {
   return UAVB_OK;
 }
 
+// Stream-ordered scratch that frees itself when the launcher returns (the free is ordered after the kernel).
+struct StreamScratch {
+  cudaStream_t st;
+  void* p = nullptr;
+  explicit StreamScratch(cudaStream_t s) : st(s) {}
+  ~StreamScratch() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t bytes) {
+    cudaMemPool_t pool = scratch_pool();
+    return pool ? cudaMallocFromPoolAsync(&p, bytes, pool, st) : cudaMallocAsync(&p, bytes, st);
+  }
+};
+
+template <bool MC> static void launch_sliced(int k, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch) {
+  switch (k) {
+    case 8: rollout_sliced_kernel<MC, 8><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
+    case 10: rollout_sliced_kernel<MC, 10><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
+    default: rollout_sliced_kernel<MC, 12><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
+  }
+}
+
 template <class R> static int launch_rollout(const uavb_rollout_args* a, void* stream) {
   int rc = check_args(a, sizeof(R) == 8);
   if (rc) return rc;
@@ -294,17 +381,46 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     int sms = 0;
     rc = sm_count_cached(&sms);
     if (rc) return rc;
-    int k = div_up(grid, sms);
-    k = k < kRolloutCtasMin ? kRolloutCtasMin : (k > kRolloutCtasMax ? kRolloutCtasMax : k);
-#define UAVB_LAUNCH_K(KK)                                                                       \
-  case KK:                                                                                      \
-    if (mc_any) rollout_kernel<R, false, true, KK><<<grid, kRolloutThreads, smem, st>>>(p);     \
-    else rollout_kernel<R, false, false, KK><<<grid, kRolloutThreads, smem, st>>>(p);           \
-    break;
-    switch (k) {
-      UAVB_LAUNCH_K(8) UAVB_LAUNCH_K(9) UAVB_LAUNCH_K(10) UAVB_LAUNCH_K(11) UAVB_LAUNCH_K(12)
+    // Metrics-only fp32 launches ALWAYS run the time-sliced persistent kernel at K = 8 (128 registers, no spills: the
+    // highest sustained tick rate), with a single slice when slicing has nothing to gain.  One compiled body for every
+    // batch size keeps per-rollout results independent of how a job is sharded (ptxas fuses mul+add differently under
+    // different register caps, so the residency variants are NOT bit-identical to each other).
+    int k = 8;
+    if (const char* force = getenv("UAVB_ROLLOUT_K")) {                  // development override for residency experiments
+      const int f = atoi(force);
+      if (f >= kRolloutCtasMin && f <= kRolloutCtasMax) k = f;
     }
-#undef UAVB_LAUNCH_K
+    if (k != 8 && k != 10) k = 12;
+    const int slots = sms * k;
+    // ~32 items per resident CTA keep the tail near 3 % of the launch; slices are whole outer periods of >= 100 ticks
+    constexpr int kMinChunkTicks = 100;
+    long long want = grid > slots ? (32LL * slots + grid - 1) / grid : 1;
+    if (const char* force = getenv("UAVB_ROLLOUT_CHUNKS")) want = atoi(force) > 0 ? atoi(force) : want;   // development override
+    const int period = a->inner_per_outer;
+    int chunk = (int)((a->n_ticks + want - 1) / want);
+    chunk = ((chunk + period - 1) / period) * period;
+    if (chunk < kMinChunkTicks) chunk = ((kMinChunkTicks + period - 1) / period) * period;
+    const int n_chunks = a->n_ticks > 0 ? (a->n_ticks + chunk - 1) / chunk : 1;
+    StreamScratch flags(st), carry(st);
+    const size_t n_flags = (size_t)grid + 1;
+    cudaError_t e = flags.alloc(n_flags * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(flags.p, 0, n_flags * sizeof(int), st);
+    SliceSched sch;
+    sch.final_carry = a->carry != nullptr;
+    if (e == cudaSuccess && a->carry == nullptr && n_chunks > 1) {
+      e = carry.alloc(sizeof(float) * UAVB_CARRY_WORDS * (size_t)a->B);
+      p.a.carry = static_cast<float*>(carry.p);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(UAVB_ENOMEM, "rollout: scratch allocation failed: %s", cudaGetErrorString(e));
+    }
+    sch.counter = static_cast<int*>(flags.p);
+    sch.done = sch.counter + 1;
+    sch.n_groups = grid; sch.n_chunks = n_chunks; sch.chunk_ticks = chunk;
+    const int pgrid = slots < grid ? slots : grid;
+    if (mc_any) launch_sliced<true>(k, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
+    else launch_sliced<false>(k, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
   }
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;

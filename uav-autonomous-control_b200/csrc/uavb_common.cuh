@@ -29,6 +29,12 @@ int require_device();
     if (!(cond)) return ::uavb::set_error(UAVB_EINVAL, "%s", msg);      \
   } while (0)
 
+// Library-private stream-ordered memory pool of the current device (scratch for the *_host entry points and the
+// time-sliced rollout).  Its release threshold is unlimited, so scratch freed after one launch is reused by the next
+// instead of being returned to the driver at every synchronisation (the default pool does that, which costs
+// milliseconds per 100 MB).  Returns nullptr if pools are unavailable; callers then fall back to the default pool.
+cudaMemPool_t scratch_pool();
+
 inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace uavb

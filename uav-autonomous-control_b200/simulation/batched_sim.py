@@ -25,11 +25,17 @@ from . import scene
 class BatchedSimulation:
     TAKEOFF_HEIGHT = 0.1   # mujoco_sim.py:17 (ground-contact amnesty; unused by the free-body model)
 
-    def __init__(self, batch: int = 1, device=None, *, waypoints=None, obstacles=None, thrust_frame_lag: int = 1,
+    def __init__(self, batch: int = 1, device=None, *, model_path=None, waypoints=None, obstacles=None, thrust_frame_lag: int = 1,
                  mass=None, inertia=None):
-        """lab_course scene by default (constants transcribed from lab_course.xml, ``simulation/scene.py``).
+        """lab_course scene by default (constants transcribed from lab_course.xml, ``simulation/scene.py``); ``model_path``
+        reads any MJCF scene of the same conventions with the stdlib reader (``scene.load_scene``; the reference passes
+        the path to ``MujocoSimulation(model_path)``, mujoco_sim.py:51).
         ``thrust_frame_lag=1`` reproduces the headless loop (stale ``data.xmat``), 0 the viewer callback path."""
         self.batch = int(batch)
+        self._scene = scene.load_scene(model_path) if model_path is not None else None
+        if self._scene is not None:
+            waypoints = self._scene.mission_waypoints if waypoints is None else waypoints
+            obstacles = self._scene.obstacles if obstacles is None else obstacles
         self.mission_waypoints = np.array(scene.LAB_COURSE_WAYPOINTS if waypoints is None else waypoints, dtype=float)
         self.obstacles = np.array(scene.LAB_COURSE_OBSTACLES if obstacles is None else obstacles, dtype=float).reshape(-1, 6)
         self.goal_position = self.mission_waypoints[-1].copy()
@@ -46,6 +52,13 @@ class BatchedSimulation:
 
     def _create_quad(self, device, mass, inertia) -> Quad:
         """Arguments of ``_create_quad`` for lab_course.xml (mujoco_sim.py:258-279)."""
+        if self._scene is not None:
+            kw = self._scene.quad_kwargs()
+            if mass is not None:
+                kw["mass"] = mass
+            if inertia is not None:
+                kw["inertia"] = inertia
+            return Quad(batch=self.batch, device=device, **kw)
         d = nat.default_vehicle()
         return Quad(g=d.g, dt=d.dt, mass=d.mass if mass is None else mass, inertia=list(d.inertia) if inertia is None else inertia,
                     arm_length=d.arm, force_coefficient=d.kf, drag_to_thrust=d.kappa, thrust_limits=[d.min_thrust, d.max_thrust],
