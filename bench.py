@@ -411,11 +411,14 @@ def run_b200(args):
 def log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush):
     """Full-rate state log (52 B/tick): HBM roofline of the logging epilogue (north_star)."""
     import torch
-    Bl = 16384
-    ticks = 4000                                          # 16384 x 4000 x 52 B = 3.4 GB of log per launch
+    Bl = 151552                                           # two full waves of 148 SMs x 8 CTAs x 64 drones
+    ticks = 400                                           # 151552 x 400 x 52 B = 3.15 GB of log per launch
+    from uav_ac_b200 import _native as nat
     kw = dict(kw)
-    for k in ("mc_gains", "mc_mass", "mc_inertia"):
-        kw[k] = kw[k][..., :Bl].contiguous()
+    veh = nat.default_vehicle()
+    base = torch.tensor(list(veh.gains) + [veh.mass] + list(veh.inertia), dtype=torch.float32, device=dev)[:, None]
+    mc = (kernels.mc_uniform(20261017, Bl, [0.8] * 11 + [0.9] * 4, [1.2] * 11 + [1.1] * 4, device=dev) * base).contiguous()
+    kw.update(mc_gains=mc[:11], mc_mass=mc[11], mc_inertia=mc[12:15])
     kw["out"] = None
     kw["want_metrics"] = False
     log = torch.empty((ticks, 13, Bl), dtype=torch.float32, device=dev)
@@ -433,9 +436,10 @@ def log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush):
     gbs = LOG_BYTES_PER_TICK * float(Bl) * ticks / t / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
     return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-            "kernel": "rollout_kernel<float,true>", "kernel_ms": t * 1e3, "ticks_per_s": float(Bl) * ticks / t,
+            "kernel": "rollout_kernel<float,LOG=true,MC,8>", "kernel_ms": t * 1e3, "ticks_per_s": float(Bl) * ticks / t,
+            "rollouts": Bl, "ticks": ticks,
             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
-            "note": "rollouts x ticks x 52 B of state log per launch; the kernel stays FP32-issue bound, so this fraction is the HBM share the log uses"}
+            "note": "full-rate state log: rollouts x ticks x 52 B written per launch (write-only traffic against the read+write copy peak)"}
 
 
 def solve_rate(kernels, dev, flush, peaks):

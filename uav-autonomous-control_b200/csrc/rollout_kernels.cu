@@ -68,11 +68,12 @@ template <class R> struct GlobalLog {
   __device__ __forceinline__ void tick(const Drone<R>& d) {
     if (--left) return;
     left = stride;
+    // streaming stores: the log is written once and never re-read by the kernel, keep it out of the L2 working set
     R* o = out;
-    o[0 * B] = (R)(d.px + (double)d.dx); o[1 * B] = (R)(d.py + (double)d.dy); o[2 * B] = (R)(d.pz + (double)d.dz);
-    o[3 * B] = d.q0; o[4 * B] = d.q1; o[5 * B] = d.q2; o[6 * B] = d.q3;
-    o[7 * B] = d.vx; o[8 * B] = d.vy; o[9 * B] = d.vz;
-    o[10 * B] = d.wx; o[11 * B] = d.wy; o[12 * B] = d.wz;
+    __stcs(o + 0 * B, (R)(d.px + (double)d.dx)); __stcs(o + 1 * B, (R)(d.py + (double)d.dy)); __stcs(o + 2 * B, (R)(d.pz + (double)d.dz));
+    __stcs(o + 3 * B, d.q0); __stcs(o + 4 * B, d.q1); __stcs(o + 5 * B, d.q2); __stcs(o + 6 * B, d.q3);
+    __stcs(o + 7 * B, d.vx); __stcs(o + 8 * B, d.vy); __stcs(o + 9 * B, d.vz);
+    __stcs(o + 10 * B, d.wx); __stcs(o + 11 * B, d.wy); __stcs(o + 12 * B, d.wz);
     out += 13 * B;
   }
 };
@@ -375,8 +376,8 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     else if (mc_any) rollout_kernel<R, false, true, 8><<<grid, kRolloutThreads, smem, st>>>(p);
     else rollout_kernel<R, false, false, 8><<<grid, kRolloutThreads, smem, st>>>(p);
   } else if (log) {
-    if (mc_any) rollout_kernel<R, true, true, 12><<<grid, kRolloutThreads, smem, st>>>(p);
-    else rollout_kernel<R, true, false, 12><<<grid, kRolloutThreads, smem, st>>>(p);
+    if (mc_any) rollout_kernel<R, true, true, 8><<<grid, kRolloutThreads, smem, st>>>(p);
+    else rollout_kernel<R, true, false, 8><<<grid, kRolloutThreads, smem, st>>>(p);
   } else {
     int sms = 0;
     rc = sm_count_cached(&sms);
