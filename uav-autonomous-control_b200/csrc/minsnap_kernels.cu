@@ -4,6 +4,8 @@
 // K1 is one thread per mission: ~2.5 k fp64 flops against 928 B of HBM traffic for S = 4
 // (SURVEY 8(d)), i.e. HBM-bound.  The per-mission output (8 S x 3 doubles, contiguous) is staged in
 // shared memory and leaves the CTA as one contiguous tile so every 32-byte sector is written whole.
+#include <stdlib.h>
+
 #include "minsnap_core.cuh"
 #include "uavb_common.cuh"
 
@@ -12,41 +14,65 @@ namespace uavb {
 constexpr int kSolveThreads = 64;
 
 // ---------------------------------------------------------------------------------------------
-// K1, uniform S.  STAGED: coefficients go to shared memory [thread][24 S + 1] (odd pitch in doubles:
-// consecutive threads start 2 banks apart, so a warp's 64-bit stores need the minimal 2 wavefronts)
-// and are then copied out by the whole CTA with consecutive threads writing consecutive doubles.
-// !STAGED (S > 8): per-thread direct stores, work arrays in local memory.
-template <int MAXS, bool STAGED>
-__global__ void __launch_bounds__(kSolveThreads) minsnap_solve_kernel(
+// K1, uniform S.  Output staging (MODE):
+//   kStageSpline  the 24 coefficients of ONE spline per thread go to shared memory [thread][25] (odd pitch in doubles:
+//                 a warp's 64-bit stores need the minimal 2 wavefronts) and leave the CTA after every spline, consecutive
+//                 threads writing consecutive doubles of the 192-byte (6-sector) chunk of each mission.  12.8 KB per CTA,
+//                 so residency is limited by registers only.
+//   kStageMission the whole mission ([thread][24 S + 1]) is staged and leaves as one contiguous tile (49.7 KB at S = 4).
+//   kDirect       per-thread stores straight from registers (S > 8: work arrays in local memory anyway).
+// Threads past the end of the batch run the solve on the last mission (they must reach the barriers) and store nothing.
+enum { kDirect = 0, kStageMission = 1, kStageSpline = 2 };
+
+template <int MAXS, int MODE, int MINB>
+__global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_kernel(
     const double* __restrict__ waypoints, const double* __restrict__ velocity, int B, int S, double factor,
     double* __restrict__ coeffs_out, double* __restrict__ times_out, int* __restrict__ status_out) {
   extern __shared__ double s_out[];
   const int per = 24 * S;              // doubles per mission
-  const int pitch = per + 1;
   const long long base = (long long)blockIdx.x * kSolveThreads;
   const long long b = base + threadIdx.x;
-  double* mine = STAGED ? s_out + (size_t)threadIdx.x * pitch : coeffs_out + (size_t)(b < B ? b : 0) * per;
-  if (b < B) {
-    const double* w = waypoints + (size_t)b * (S + 1) * 3;
-    double* tout = times_out + (size_t)b * S;
-    const int st = minsnap_solve_one<MAXS>(
-        S, velocity[b], factor, [w](int i, int ax) { return __ldg(w + 3 * i + ax); },
-        [mine](int seg, int j, int ax, double val) { mine[seg * 24 + j * 3 + ax] = val; },
-        [tout](int seg, double t) { tout[seg] = t; });
-    if (status_out) status_out[b] = st;
-  }
-  if (!STAGED) return;
-  __syncthreads();
+  const bool live = b < B;
+  const long long bb = live ? b : (long long)B - 1;
   const int n_here = (int)((B - base) < kSolveThreads ? (B - base) : kSolveThreads);
-  double* gout = coeffs_out + (size_t)base * per;
-  const int total = n_here * per;
-  int mi = 0, off = threadIdx.x;       // e = mi * per + off, advanced without a division
-  while (off >= per) { off -= per; ++mi; }
-  for (int e = threadIdx.x; e < total; e += kSolveThreads) {
-    gout[e] = s_out[(size_t)mi * pitch + off];
-    off += kSolveThreads;
+  const double* w = waypoints + (size_t)bb * (S + 1) * 3;
+  double* tout = times_out + (size_t)bb * S;
+  auto loadw = [w](int i, int ax) { return __ldg(w + 3 * i + ax); };
+  auto storet = [tout, live](int seg, double t) { if (live) tout[seg] = t; };
+  int st;
+  if constexpr (MODE == kStageSpline) {
+    double* mine = s_out + (size_t)threadIdx.x * 25;
+    double* gout = coeffs_out + (size_t)base * per;
+    st = minsnap_solve_one<MAXS>(
+        S, velocity[bb], factor, loadw, [mine](int, int j, int ax, double val) { mine[j * 3 + ax] = val; }, storet,
+        [&](int seg) {
+          __syncthreads();
+          for (int e = threadIdx.x; e < n_here * 24; e += kSolveThreads) {
+            const int m = e / 24, off = e - m * 24;
+            gout[(size_t)m * per + seg * 24 + off] = s_out[m * 25 + off];
+          }
+          __syncthreads();
+        });
+  } else if constexpr (MODE == kStageMission) {
+    const int pitch = per + 1;
+    double* mine = s_out + (size_t)threadIdx.x * pitch;
+    st = minsnap_solve_one<MAXS>(S, velocity[bb], factor, loadw, [mine](int seg, int j, int ax, double val) { mine[seg * 24 + j * 3 + ax] = val; }, storet);
+    __syncthreads();
+    double* gout = coeffs_out + (size_t)base * per;
+    const int total = n_here * per;
+    int mi = 0, off = threadIdx.x;       // e = mi * per + off, advanced without a division
     while (off >= per) { off -= per; ++mi; }
+    for (int e = threadIdx.x; e < total; e += kSolveThreads) {
+      gout[e] = s_out[(size_t)mi * pitch + off];
+      off += kSolveThreads;
+      while (off >= per) { off -= per; ++mi; }
+    }
+  } else {
+    double* mine = coeffs_out + (size_t)bb * per;
+    st = minsnap_solve_one<MAXS>(S, velocity[bb], factor, loadw, [mine, live](int seg, int j, int ax, double val) { if (live) mine[seg * 24 + j * 3 + ax] = val; },
+                                 storet);
   }
+  if (live && status_out) status_out[b] = st;
 }
 
 // K1, ragged S (obstacle-correction loop): per-thread direct stores, packed segments.
@@ -219,12 +245,13 @@ __global__ void __launch_bounds__(128) table_hits_kernel(const double* __restric
   if (lane == 0) hit_mask[b] |= m;
 }
 
-template <int MAXS, bool STAGED>
+template <int MAXS, int MODE, int MINB>
 static int launch_solve(const double* w, const double* vel, int B, int S, double factor, double* c, double* t, int* st, cudaStream_t stream) {
-  const size_t smem = STAGED ? sizeof(double) * (size_t)kSolveThreads * (24 * S + 1) : 0;
+  const size_t smem = MODE == kStageMission ? sizeof(double) * (size_t)kSolveThreads * (24 * S + 1)
+                                            : (MODE == kStageSpline ? sizeof(double) * (size_t)kSolveThreads * 25 : 0);
   if (smem > 48 * 1024)
-    UAVB_CUDA_OK(cudaFuncSetAttribute(minsnap_solve_kernel<MAXS, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  minsnap_solve_kernel<MAXS, STAGED><<<div_up(B, kSolveThreads), kSolveThreads, smem, stream>>>(w, vel, B, S, factor, c, t, st);
+    UAVB_CUDA_OK(cudaFuncSetAttribute(minsnap_solve_kernel<MAXS, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  minsnap_solve_kernel<MAXS, MODE, MINB><<<div_up(B, kSolveThreads), kSolveThreads, smem, stream>>>(w, vel, B, S, factor, c, t, st);
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }
@@ -242,11 +269,28 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
   if (rc) return rc;
   if (B == 0) return UAVB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (S == 1) return launch_solve<1, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
-  if (S == 2) return launch_solve<2, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
-  if (S <= 4) return launch_solve<4, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
-  if (S <= 8) return launch_solve<8, true>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
-  return launch_solve<UAVB_MAX_SPLINES, false>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  if (const char* dev_mode = getenv("UAVB_K1_VARIANT")) {             // development override: staging / residency experiments at S <= 4
+    const int v = atoi(dev_mode);
+    if (S <= 4 && S > 2) {
+      switch (v) {
+        case 1: return launch_solve<4, kStageMission, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 2: return launch_solve<4, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 3: return launch_solve<4, kStageSpline, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 4: return launch_solve<4, kStageSpline, 8>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 5: return launch_solve<4, kDirect, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 6: return launch_solve<4, kDirect, 8>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 7: return launch_solve<4, kStageSpline, 10>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        default: break;
+      }
+    }
+  }
+  if (S == 1) return launch_solve<1, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  if (S == 2) return launch_solve<2, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  // S <= 4 (BASELINE configs[1]): 6 CTAs per SM (168 registers) measured fastest -- 0.216 ms per 10^6 solves against 0.250 ms
+  // unconstrained (198 registers, 5 CTAs) and 0.238 ms at 8 CTAs (128 registers, spills); tools/k1_sweep.sh
+  if (S <= 4) return launch_solve<4, kStageSpline, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  if (S <= 8) return launch_solve<8, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  return launch_solve<UAVB_MAX_SPLINES, kDirect, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
 }
 
 extern "C" int uavb_minsnap_solve_ragged_f64(const double* waypoints, const int* wp_offsets, const double* velocity, int B,
