@@ -16,6 +16,7 @@
 using namespace uavb;
 
 template <class R> struct VecLog {
+  static constexpr bool kNormEveryTick = false;
   std::vector<double>* out; int stride; int left;
   void tick(const Drone<R>& d) {
     if (--left) return;

@@ -324,7 +324,19 @@ UAVB_HD void inner_control(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R* g
 
 // Inner loop, part 2: rotor wrench with the given thrust axis + free-body semi-implicit Euler step
 // (mujoco_sim.py:232-255 + MuJoCo Euler; oracle/freebody.py states the same equations in fp64).
-template <class R>
+// 1.5 - 0.5 |q|^2 = 1/|q| + O((|q|^2 - 1)^2): renormalisation of a quaternion whose norm is 1 up to accumulated rounding.
+template <class R> UAVB_HD void renormalise_q(Drone<R>& d) {
+  typedef Math<R> M;
+  const R nn = M::fma(d.q0, d.q0, M::fma(d.q1, d.q1, M::fma(d.q2, d.q2, d.q3 * d.q3)));
+  const R rn = M::fma(R(-0.5), nn, R(1.5));
+  d.q0 *= rn; d.q1 *= rn; d.q2 *= rn; d.q3 *= rn;
+}
+
+// NORM: renormalise the quaternion in this step (mujoco_sim.py:36-42 does so every tick).  The persistent rollout passes
+// false and renormalises once per outer period instead: q * dq of a unit q and the unit dq below stays unit up to
+// ~6e-8 per tick, the drift over 10 ticks (< 1e-6 in |q|^2) scales the thrust axis and R by the same factor, far inside
+// the fp32 noise of the step, and the outer loop always sees a freshly normalised q.
+template <class R, bool NORM = true>
 UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx, R zy, R zz, R gx, R gy, R gz) {
   typedef Math<R> M;
   // f_i = kf w_i^2; collective and body torques from the sums of squares (mujoco_sim.py:235-247)
@@ -348,9 +360,15 @@ UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx,
   const R h = u.half_dt;
   const R x2 = (h * h) * wn2;                                // (a/2)^2
   R sf, cm1;
-  if (x2 < R(1e-3)) {                                        // |a/2| < 0.0316: series exact to < 1e-13 relative
-    sf = h * M::fma(x2, M::fma(x2, M::fma(x2, R(-1.0 / 5040), R(1.0 / 120)), R(-1.0 / 6)), R(1));
-    cm1 = x2 * M::fma(x2, M::fma(x2, M::fma(x2, R(1.0 / 40320), R(-1.0 / 720)), R(1.0 / 24)), R(-0.5));
+  if (x2 < R(1e-3)) {                                        // |a/2| < 0.0316
+    if constexpr (sizeof(R) == 4) {
+      // fp32: the next series terms (x2^2/120, x2^3/720 < 1e-8 relative) are below half an ulp
+      sf = h * M::fma(x2, R(-1.0 / 6), R(1));
+      cm1 = x2 * M::fma(x2, R(1.0 / 24), R(-0.5));
+    } else {                                                 // series exact to < 1e-13 relative
+      sf = h * M::fma(x2, M::fma(x2, M::fma(x2, R(-1.0 / 5040), R(1.0 / 120)), R(-1.0 / 6)), R(1));
+      cm1 = x2 * M::fma(x2, M::fma(x2, M::fma(x2, R(1.0 / 40320), R(-1.0 / 720)), R(1.0 / 24)), R(-0.5));
+    }
   } else {
     const R wn = M::sqrt(wn2);
     R sn, cs;
@@ -364,24 +382,27 @@ UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx,
   const R n1 = q1 + M::fma(-q3, by, M::fma(q2, bz, M::fma(q0, bx, q1 * cm1)));
   const R n2 = q2 + M::fma(q3, bx, M::fma(-q1, bz, M::fma(q0, by, q2 * cm1)));
   const R n3 = q3 + M::fma(-q2, bx, M::fma(q1, by, M::fma(q0, bz, q3 * cm1)));
-  // re-normalise (mujoco_sim.py:36-42).  The input quaternion is unit and dq is unit up to the series remainder, so
-  // |n|^2 = 1 + e with |e| at rounding level (~1e-7 in fp32) and 1/sqrt(1+e) = 1.5 - 0.5 |n|^2 + O(e^2) is exact to
-  // working precision -- no MUFU, and no drift: the correction is re-applied every tick.
-  const R nn = M::fma(n0, n0, M::fma(n1, n1, M::fma(n2, n2, n3 * n3)));
-  const R rn = M::fma(R(-0.5), nn, R(1.5));
-  d.q0 = n0 * rn; d.q1 = n1 * rn; d.q2 = n2 * rn; d.q3 = n3 * rn;
+  if constexpr (NORM) {
+    // re-normalise (mujoco_sim.py:36-42).  The input quaternion is unit and dq is unit up to the series remainder, so
+    // |n|^2 = 1 + e with |e| at rounding level and 1/sqrt(1+e) = 1.5 - 0.5 |n|^2 + O(e^2) is exact to working precision.
+    const R nn = M::fma(n0, n0, M::fma(n1, n1, M::fma(n2, n2, n3 * n3)));
+    const R rn = M::fma(R(-0.5), nn, R(1.5));
+    d.q0 = n0 * rn; d.q1 = n1 * rn; d.q2 = n2 * rn; d.q3 = n3 * rn;
+  } else {
+    d.q0 = n0; d.q1 = n1; d.q2 = n2; d.q3 = n3;
+  }
 }
 
 // One full inner tick in the reference order (SURVEY 8(a) "exact tick order"): body-rate loop,
 // allocation, motor lag, wrench with the stale (lag=1) or fresh (lag=0) thrust axis, integration.
-template <class R> UAVB_HD void inner_tick(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, int thrust_frame_lag) {
+template <class R, bool NORM = true> UAVB_HD void inner_tick(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, int thrust_frame_lag) {
   R gx, gy, gz;
   inner_control<R>(d, u, v, &gx, &gy, &gz, nullptr, nullptr);
   R zx, zy, zz;
   body_z<R>(d, &zx, &zy, &zz);                               // axis of X_k: what mj_step's forward pass will compute
   const R ux = thrust_frame_lag ? d.zbx : zx, uy = thrust_frame_lag ? d.zby : zy, uz = thrust_frame_lag ? d.zbz : zz;
   d.zbx = zx; d.zby = zy; d.zbz = zz;
-  physics_step<R>(d, u, v, ux, uy, uz, gx, gy, gz);
+  physics_step<R, NORM>(d, u, v, ux, uy, uz, gx, gy, gz);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -51,7 +51,10 @@ template <class R> struct Accum {
   int status;
 };
 
+// Loggers see the state after every tick.  kNormEveryTick: renormalise the quaternion in every tick (what a per-tick log
+// must show, mujoco_sim.py:36-42) instead of once per outer period (metrics-only rollouts, see physics_step).
 struct NoLog {
+  static constexpr bool kNormEveryTick = false;
   template <class R> UAVB_HD void tick(const Drone<R>&) {}
 };
 
@@ -124,7 +127,7 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
     }
     if (watch) {
       for (int j = 0; j < n; ++j) {
-        inner_tick<R>(d, u, v, lag);
+        inner_tick<R, LOG::kNormEveryTick>(d, u, v, lag);
         if (!a.collided && obst.hit((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz))) {
           a.collided = 1; a.first_hit = tick0 + k + j;
         }
@@ -132,7 +135,7 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
       }
     } else {
       for (int j = 0; j < n; ++j) {
-        inner_tick<R>(d, u, v, lag);
+        inner_tick<R, LOG::kNormEveryTick>(d, u, v, lag);
         logger.tick(d);
       }
     }
@@ -140,6 +143,7 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
     c.phase += n;
     if (c.phase == freq) {
       c.phase = 0;
+      if (!LOG::kNormEveryTick) renormalise_q<R>(d);         // once per outer period (not per launch: chunked runs stay bit-identical)
       fold_position<R>(d);
       const R ex = (R)(c.tx - d.px), ey = (R)(c.ty - d.py), ez = (R)(c.tz - d.pz);
       const R e2 = ex * ex + ey * ey + ez * ez;

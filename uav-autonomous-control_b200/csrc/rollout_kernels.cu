@@ -62,6 +62,7 @@ struct Boxes {
 
 // [sample][13][B] state log, one sample after every `stride` ticks.
 template <class R> struct GlobalLog {
+  static constexpr bool kNormEveryTick = true;
   R* out;
   long long B;
   int stride, left;
@@ -202,6 +203,7 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
   if (a.state_out) {
     R* o = reinterpret_cast<R*>(a.state_out) + i;
     o[0 * B] = (R)fx; o[1 * B] = (R)fy; o[2 * B] = (R)fz;
+    if (!LOG && c.phase != 0) renormalise_q<R>(d);           // the reported state is unit even in the middle of an outer period
     o[3 * B] = d.q0; o[4 * B] = d.q1; o[5 * B] = d.q2; o[6 * B] = d.q3;
     o[7 * B] = d.vx; o[8 * B] = d.vy; o[9 * B] = d.vz;
     o[10 * B] = d.wx; o[11 * B] = d.wy; o[12 * B] = d.wz;
