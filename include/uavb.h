@@ -194,7 +194,14 @@ typedef struct uavb_rollout_args {
   float*        log_out;      /* [n_ticks / log_stride][13][B] SoA samples; required iff log_stride > 0 */
 } uavb_rollout_args;
 
-/* Replaces, for B drones and n_ticks ticks, the loop
+/* Execution (DESIGN.md "K2"): metrics-only fp32 launches run a persistent grid of 8 CTAs x 64 drones per SM at 128
+ * registers; when the batch exceeds that capacity the mission is cut into time slices that CTAs pull from an atomic work
+ * queue, a drone resting in the carry block between slices (scratch comes from a library-private stream-ordered pool when
+ * `carry` is NULL).  One compiled body serves every batch size, so per-rollout results do not depend on B, on index_base
+ * or on how a job is sharded over launches and GPUs.  Launches with a state log (log_stride > 0) run one-shot and
+ * renormalise the quaternion every tick; metrics-only launches renormalise once per outer period (state_out is unit).
+ *
+ * Replaces, for B drones and n_ticks ticks, the loop
  *     trajectory_controller.step(); simulation.step()
  * of tests/integration/test_mujoco_trajectory_tracking.py:27-31, i.e. TrajectoryController.step
  * (uav_ac/main.py:37-61), CascadedController.{altitude,lateral,reduced_attitude,body_rate_controller}
@@ -284,6 +291,30 @@ int uavb_mc_uniform_f32(unsigned long long seed, long long index_base, int strea
  * 0.4, step ~ U(2,5) m; velocity ~ U(2,3) m/s.  waypoints_out [B][S+1][3], velocity_out [B]. */
 int uavb_mc_missions_f64(unsigned long long seed, long long index_base, int B, int S,
                          double* waypoints_out, double* velocity_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RRT* path planning for B missions, fp64, one warp per mission.
+ *
+ * Replaces RRTStar(space_limits, start, goal, max_distance, max_iterations, obstacles).run() followed by
+ * .best_path and .simplify_path(best_path) (uav_ac/planning/rrt.py:12-118): goal bias 0.15, neighbourhood radius
+ * 1.5 x max_distance, coordinates rounded to 2 decimals, early stop after max_iterations/10 iterations without a better
+ * path.  Random numbers come from Philox keyed by (seed, index_base + mission), so results do not depend on batching.
+ *   space_limits [2][3] lower, upper (shared)      start, goal [B][3]      obstacles [n_obs][6] (shared) or NULL
+ *   workspace    uavb_rrt_workspace_bytes(B, max_iterations) bytes of device memory
+ *   path_out     [B][max_path][3] start -> goal,   path_len_out [B]
+ *   simple_path_out / simple_len_out: greedy shortcut of the path (rrt.py:97-118); both NULL to skip
+ *   cost_out [B] length of the path (inf when none), status_out [B]: 0 ok, 1 no path found (the reference raises),
+ *   2 path longer than max_path;  stats_out [B][2] = iterations used, nodes in the best tree; may be NULL */
+long long uavb_rrt_workspace_bytes(int B, int max_iterations);
+int uavb_rrt_star_f64(const double* space_limits, const double* start, const double* goal, int B, double max_distance,
+                      int max_iterations, const double* obstacles, int n_obs, unsigned long long seed, long long index_base,
+                      void* workspace, double* path_out, int max_path, int* path_len_out, double* simple_path_out,
+                      int* simple_len_out, double* cost_out, int* status_out, int* stats_out, void* stream);
+
+/* RRTStar._segment_intersects_cuboid / _is_valid_connection (rrt.py:232-274) for n segments p[i] -> q[i]:
+ * hit_out[i] = 1 when the segment intersects ANY of the n_obs boxes (exact slab test), else 0. */
+int uavb_segments_hit_aabbs_f64(const double* p, const double* q, int n, const double* boxes, int n_obs, int* hit_out,
+                                void* stream);
 
 /* Measured FMA throughput of the device in TFLOP/s (2 flop per FMA), for the roofline denominators
  * that MEASURED_PEAKS.json does not carry.  Synchronous. */

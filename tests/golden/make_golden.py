@@ -276,7 +276,54 @@ def closed_loops():
     print("variants:", {k: float(v) for k, v in var.items() if k.endswith("final_dist") or k.endswith("first_collision_tick")})
 
 
+def rrt():
+    """Reference RRTStar (uav_ac/planning/rrt.py) fed with the Philox stream of oracle/rrt_np.py (the stream the CUDA kernel draws
+    from) through a patched np.random.uniform: best paths, their greedy simplification, slab-test truth table."""
+    import contextlib
+    import io
+    from uav_ac.planning.rrt import RRTStar
+    from oracle import rrt_np
+
+    def run_ref(limits, start, goal, step, iters, obs, seed, mission):
+        state = {"it": -1, "k": 0, "u": None}
+
+        def fake_uniform(lo, hi):       # the reference draws uniform(0, 1) and, unless it samples the goal, three uniform(lo, hi)
+            if lo == 0 and hi == 1 and state["k"] == 0:
+                state["it"] += 1
+                state["u"] = rrt_np.philox_u01(seed, mission, state["it"])
+                state["k"] = 1 if state["u"][0] >= 0.15 else 0
+                return state["u"][0]
+            k = state["k"]
+            state["k"] = (k + 1) % 4
+            return lo + (hi - lo) * state["u"][k]
+
+        r = RRTStar(limits, start, goal, step, iters, obs)
+        with unittest.mock.patch("numpy.random.uniform", fake_uniform), contextlib.redirect_stdout(io.StringIO()):
+            r.run()
+        return r
+
+    limits = np.array([[0, 0, -6.0], [24, 14, 0]])
+    out = {"limits": limits, "obstacles": OBSTACLES, "step": np.array(1.5), "iters": np.array(1500), "seed": np.array(20261017)}
+    starts = np.array([[1, 7, -1.3], [2, 2, -1.0], [22, 12, -4.0], [1, 13, -5.0], [12, 1, -0.5], [3, 7, -3.1]])
+    goals = np.array([[23, 7, -2.0], [22, 12, -3.0], [2, 3, -1.5], [23, 1, -1.0], [12, 13, -5.5], [5, 7, -3.1]])
+    out["starts"], out["goals"] = starts, goals
+    for m in range(len(starts)):
+        r = run_ref(limits, starts[m], goals[m], 1.5, 1500, OBSTACLES, 20261017, m)
+        out[f"path{m}"] = r.best_path
+        out[f"simple{m}"] = r.simplify_path(r.best_path)
+        out[f"cost{m}"] = np.array(RRTStar.path_cost(r.best_path))
+    r = run_ref(limits, starts[0], goals[0], 1.5, 1500, None, 20261017, 0)          # no obstacles
+    out["path_free"] = r.best_path
+    rng = np.random.default_rng(3)
+    p, q = rng.uniform([0, 0, -6], [24, 14, 0], (400, 3)), rng.uniform([0, 0, -6], [24, 14, 0], (400, 3))
+    q[:40] = p[:40] + rng.normal(size=(40, 3)) * [1.0, 0, 0]                        # axis-parallel segments (|d| < 1e-12 branches)
+    hits = np.array([[RRTStar._segment_intersects_cuboid(p[i], q[i], box) for box in OBSTACLES] for i in range(len(p))])
+    out.update(seg_p=p, seg_q=q, seg_hits=hits)
+    np.savez_compressed(os.path.join(HERE, "rrt.npz"), **out)
+    print("rrt.npz:", {k: v.shape for k, v in out.items() if k.startswith("path")}, "segment hits", int(hits.any(axis=1).sum()), "of", len(p))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["planning", "stages", "closed_loops"]
+    which = sys.argv[1:] or ["planning", "stages", "closed_loops", "rrt"]
     for w in which:
         globals()[w]()

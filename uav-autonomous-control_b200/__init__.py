@@ -7,7 +7,7 @@ C ABI of ``include/uavb.h``.  Import as ``uav_ac_b200``; the module layout mirro
 
     uav_ac_b200.planning.minimum_snap.MinimumSnap      uav_ac_b200.control.controller.CascadedController
     uav_ac_b200.quadrotor.quad.Quad                    uav_ac_b200.main.TrajectoryController
-    uav_ac_b200.simulation.batched_sim.BatchedSimulation
+    uav_ac_b200.simulation.batched_sim.BatchedSimulation   uav_ac_b200.planning.rrt.RRTStar
 
 There is no CPU fallback: the kernels are the only implementation, and calls raise when libuavb.so
 or a CUDA device is missing.

@@ -31,7 +31,7 @@ SYMBOLS = (
     "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_yaw_profile_f64",
     "uavb_minsnap_table_hits_f64",
     "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
-    "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host",
+    "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host", "uavb_rrt_workspace_bytes", "uavb_rrt_star_f64", "uavb_segments_hit_aabbs_f64",
 )
 
 
@@ -117,11 +117,16 @@ def lib() -> ctypes.CDLL:
     L.uavb_mc_missions_f64.argtypes = [c_ulonglong, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.uavb_measure_fma_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
     L.uavb_minsnap_solve_f64_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]
+    L.uavb_rrt_workspace_bytes.argtypes = [c_int, c_int]
+    L.uavb_rrt_star_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_int, c_ulonglong, c_longlong, c_void_p,
+                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.uavb_segments_hit_aabbs_f64.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
     L.uavb_fly_mission_host.argtypes = [POINTER(MissionHost), c_void_p, c_void_p, POINTER(c_int)]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("uavb_last_error", "uavb_vehicle_defaults"):
+        if name not in ("uavb_last_error", "uavb_vehicle_defaults", "uavb_rrt_workspace_bytes"):
             fn.restype = c_int
+    L.uavb_rrt_workspace_bytes.restype = c_longlong
     _lib = L
     return L
 
