@@ -337,3 +337,33 @@ def test_montecarlo_batch_matches_c_oracle_on_every_rollout(cuda, golden):
     assert np.abs(met[:, 0] - m_ref[:, 0]).max() < POS_TOL and np.abs(met[:, 3] - m_ref[:, 3]).max() < 2e-5
     assert np.abs(met[:, 2] - m_ref[:, 2]).max() < 2e-5 and np.abs(met[:, 4] - m_ref[:, 4]).max() < POS_TOL
     assert (met[:, 7] == m_ref[:, 7]).all() and (met[:, 5] == 0).all()
+
+
+def test_time_sliced_schedule_is_bit_identical_to_a_single_slice(cuda, monkeypatch):
+    """The persistent work queue ((slice, group) items, state parked in the carry block between slices) must not change
+    a single bit: 5 000 per-rollout missions with wind and obstacle sets flown as one slice, as 7 slices and as 60 slices."""
+    import torch
+    from uav_ac_b200 import kernels
+    B = 5000
+    wp, vel = kernels.mc_missions(3, B, 4)
+    ground = wp[:, 0].clone()
+    ground[:, 2] = -0.021
+    plan = kernels.plan_missions([(torch.stack((ground, wp[:, 0]), dim=1).contiguous(), vel), (wp, vel)], 0.01)
+    wind = kernels.mc_uniform(4, B, [-0.08] * 3, [0.08] * 3)
+    rng = np.random.default_rng(1)
+    ctr, half = rng.uniform([2, 2, -5], [22, 12, -1], (4, 5, 3)), rng.uniform(0.3, 1.2, (4, 5, 3))
+    boxes = torch.tensor(np.stack((ctr[..., 0] - half[..., 0], ctr[..., 0] + half[..., 0], ctr[..., 1] - half[..., 1], ctr[..., 1] + half[..., 1],
+                                   ctr[..., 2] - half[..., 2], ctr[..., 2] + half[..., 2]), axis=-1).astype(np.float32), device=cuda)
+    sets = (torch.arange(B, device=cuda) % 4).to(torch.int32)
+    n = 6000 + 7                                                     # not a multiple of the outer period
+    runs = []
+    for chunks in ("1", "7", "60"):
+        monkeypatch.setenv("UAVB_ROLLOUT_CHUNKS", chunks)
+        r = kernels.rollout(plan, B, n, start=ground.contiguous(), goal=wp[:, -1].contiguous(), mc_wind=wind, obstacles=boxes, obstacle_set=sets,
+                            want_carry=True)
+        torch.cuda.synchronize()
+        runs.append(r)
+    monkeypatch.delenv("UAVB_ROLLOUT_CHUNKS")
+    for r in runs[1:]:
+        assert torch.equal(r.metrics, runs[0].metrics) and torch.equal(r.state, runs[0].state) and torch.equal(r.carry.view(torch.int32)[:50], runs[0].carry.view(torch.int32)[:50])
+    assert float(runs[0].metrics[:, 1].mean()) > 0.02                # collisions happen, so first-hit ticks cross slice boundaries
