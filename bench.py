@@ -277,8 +277,9 @@ def run_b200(args):
 
     def hot_path(wp, vel, mc):
         """K1 (two tables) + table geometry + K2 over the shard; returns the per-rollout metrics."""
-        plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True)
         n_ticks = n_ticks_holder.get("n")
+        plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True,
+                                     table_rows=None if n_ticks is None else n_ticks // FREQUENCY)
         if n_ticks is None:                                  # mission length is data dependent: read it once, outside the timed steps
             n_ticks = n_ticks_holder["n"] = FREQUENCY * int(plan.total_rows.item())
         kernels.rollout(plan, B, n_ticks, start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc[:11], mc_mass=mc[11],
@@ -380,7 +381,7 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(mc_host.numel() * 4 + wp_host.numel() * 8 + 8),
                     "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                     "call": "uavb_fly_mission_host (C ABI, pinned host buffers, synchronous); host wall-clock, max over ranks"},
-            "gpu_launches": 5 * args.steps,        # per step: 2x minsnap_solve, 2x table_meta, 1x rollout_sliced (torch glue kernels not counted)
+            "gpu_launches": 7 * args.steps,        # per step: 2x minsnap_solve, 2x table_meta, 2x set-point table, 1x rollout_sliced (torch glue not counted)
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r01_ncu_rollout_v4.md)",
                          "kernel": "rollout_sliced_kernel<MC,8>", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,

@@ -179,6 +179,10 @@ typedef struct uavb_rollout_args {
   const int*    mission_seg_count;  /* [B] segments of each rollout, NULL = n_seg_shared for all      */
   int           n_seg_shared;
   double        dt_outer;     /* table sampling period, quad.dt * frequency (main.py:97)             */
+  const void*   shared_targets;   /* optional, shared missions only: the per-row set-points precomputed by
+                                     uavb_rollout_targets_f64 ([n_target_rows] records of 56 bytes); NULL = the kernel
+                                     evaluates the polynomials itself.  Both forms give bit-identical rollouts.        */
+  int           n_target_rows;
 
   const double* start;        /* initial position, [3] (start_stride 0) or [B][3] (start_stride 3)    */
   int           start_stride;
@@ -193,6 +197,15 @@ typedef struct uavb_rollout_args {
   float*        metrics_out;  /* [B][UAVB_N_METRICS]; may be NULL                                      */
   float*        log_out;      /* [n_ticks / log_stride][13][B] SoA samples; required iff log_stride > 0 */
 } uavb_rollout_args;
+
+/* Set-points of every table row of ONE mission (the rows MinimumSnap._generate_trajectory would sample, :97-124, plus the
+ * heading rule of _calculate_yaws as a direction): x y z in fp64, velocity / acceleration / heading direction in fp32,
+ * 56 bytes per row.  A shared-mission rollout that receives this table reads one row per outer period instead of
+ * evaluating 9 polynomials per drone.  segment arrays as in uavb_rollout_args (n_seg segments of one mission);
+ * targets_out holds n_rows = sum(seg_rows) records. */
+#define UAVB_TARGET_ROW_BYTES 56
+int uavb_rollout_targets_f64(const double* seg_coeffs, const int* seg_rows, const int* seg_table, const double* seg_yaw0,
+                             int n_seg, double dt_outer, void* targets_out, int n_rows, void* stream);
 
 /* Execution (DESIGN.md "K2"): metrics-only fp32 launches run a persistent grid of 8 CTAs x 64 drones per SM at 128
  * registers; when the batch exceeds that capacity the mission is cut into time slices that CTAs pull from an atomic work

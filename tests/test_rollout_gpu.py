@@ -367,3 +367,27 @@ def test_time_sliced_schedule_is_bit_identical_to_a_single_slice(cuda, monkeypat
     for r in runs[1:]:
         assert torch.equal(r.metrics, runs[0].metrics) and torch.equal(r.state, runs[0].state) and torch.equal(r.carry.view(torch.int32)[:50], runs[0].carry.view(torch.int32)[:50])
     assert float(runs[0].metrics[:, 1].mean()) > 0.02                # collisions happen, so first-hit ticks cross slice boundaries
+
+
+def test_precomputed_set_point_table_is_bit_identical_to_on_the_fly_evaluation(cuda):
+    """Shared missions read one 56-byte row per outer period (uavb_rollout_targets_f64) instead of evaluating the polynomials per
+    drone; both forms must give the same bits, also past the end of the table (hold-last-row) and with an over-long table."""
+    import torch
+    from uav_ac_b200 import kernels
+    from uav_ac_b200.simulation.scene import LAB_COURSE_WAYPOINTS as W
+    for v in (2.0, 3.0):
+        plan = lab_course_plan(cuda, v)
+        n = 10 * int(plan.total_rows.item()) + 3000
+        B = 300
+        rng = np.random.default_rng(int(v))
+        mc = mc_arrays(cuda, B, rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3)))
+        a = _fly(cuda, plan, B, n, use_targets=True, **mc)
+        b = _fly(cuda, plan, B, n, use_targets=False, **mc)
+        assert plan.targets.shape == (int(plan.total_rows.item()), 56)
+        assert torch.equal(a.metrics, b.metrics) and torch.equal(a.state, b.state)
+        wp = torch.tensor(W, dtype=torch.float64, device=cuda)
+        vel = torch.tensor([v], dtype=torch.float64, device=cuda)
+        longer = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], 0.01, shared=True,
+                                       table_rows=int(plan.total_rows.item()) + 77)
+        c = _fly(cuda, longer, B, n, **mc)
+        assert torch.equal(c.metrics, b.metrics) and torch.equal(c.state, b.state)

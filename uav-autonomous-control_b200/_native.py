@@ -20,6 +20,7 @@ N_METRICS = 8
 CARRY_WORDS = 52
 STATE_DIM = 13
 MAX_SPLINES = 64
+TARGET_ROW_BYTES = 56
 GAIN_NAMES = ("kp_xy", "kd_xy", "kp_z", "kd_z", "ki_z", "kp_roll", "kp_pitch", "kp_yaw", "kp_p", "kp_q", "kp_r")
 M_FINAL_DIST, M_COLLISION, M_RMSE, M_MEAN_ERR, M_MAX_ERR, M_STATUS, M_FIRST_HIT, M_PERIODS = range(8)
 (STAGE_OUTER, STAGE_INNER, STAGE_PHYSICS, STAGE_ALTITUDE, STAGE_LATERAL, STAGE_ROLL_PITCH, STAGE_YAW, STAGE_BODY_RATE, STAGE_ALLOCATE,
@@ -30,7 +31,7 @@ SYMBOLS = (
     "uavb_version", "uavb_last_error", "uavb_device_count", "uavb_device_info", "uavb_minsnap_solve_f64",
     "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_yaw_profile_f64",
     "uavb_minsnap_table_hits_f64",
-    "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
+    "uavb_rollout_targets_f64", "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
     "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host", "uavb_rrt_workspace_bytes", "uavb_rrt_star_f64", "uavb_segments_hit_aabbs_f64",
 )
 
@@ -59,6 +60,7 @@ class RolloutArgs(Structure):
         ("mc_mass", c_void_p), ("mc_inertia", c_void_p), ("mc_gains", c_void_p), ("mc_wind", c_void_p),
         ("seg_coeffs", c_void_p), ("seg_rows", c_void_p), ("seg_table", c_void_p), ("seg_yaw0", c_void_p),
         ("mission_seg_begin", c_void_p), ("mission_seg_count", c_void_p), ("n_seg_shared", c_int), ("dt_outer", c_double),
+        ("shared_targets", c_void_p), ("n_target_rows", c_int),
         ("start", c_void_p), ("start_stride", c_int), ("goal", c_void_p), ("goal_stride", c_int),
         ("aabbs", c_void_p), ("aabb_set", c_void_p),
         ("carry", c_void_p), ("state_out", c_void_p), ("metrics_out", c_void_p), ("log_out", c_void_p),
@@ -108,6 +110,7 @@ def lib() -> ctypes.CDLL:
     L.uavb_minsnap_sample_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]
     L.uavb_minsnap_yaw_profile_f64.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]
     L.uavb_minsnap_table_hits_f64.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    L.uavb_rollout_targets_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_int, c_void_p]
     L.uavb_rollout_f32.argtypes = [POINTER(RolloutArgs), c_void_p]
     L.uavb_rollout_f64.argtypes = [POINTER(RolloutArgs), c_void_p]
     L.uavb_vehicle_defaults.argtypes = [POINTER(Vehicle)]

@@ -141,11 +141,19 @@ template <class R> struct Drone {
   R zbx, zby, zbz;     // thrust direction MuJoCo last computed (stale body z axis)
 };
 
-// Set-point of one table row (minimum_snap.py:122-123 columns 0..9), fp64 from the Horner evaluation.
-// The yaw column (:9) travels as a heading direction (yc, ys) = k (cos yaw, sin yaw), k > 0 arbitrary.
-struct Target {
-  double x, y, z, vx, vy, vz, ax, ay, az;
-  double yc, ys;
+// Set-point of one table row (minimum_snap.py:122-123 columns 0..9): fp64 position (errors are formed in fp64), the rest
+// already rounded to the arithmetic type.  The yaw column (:9) travels as a heading direction (yc, ys) = k (cos yaw,
+// sin yaw), k > 0 arbitrary.
+template <class R> struct Target {
+  double x, y, z;
+  R vx, vy, vz, ax, ay, az;
+  R yc, ys;
+};
+
+// The same set-point as it is stored in a precomputed table (shared missions): 56 bytes per row.
+struct TargetRow {
+  double x, y, z;
+  float vx, vy, vz, ax, ay, az, yc, ys;
 };
 
 template <class R> UAVB_HD void set_thrust_cmd(Drone<R>& d, const VehU<R>& u, R c) {
@@ -247,18 +255,18 @@ template <class R> UAVB_HD R yaw_rate_cmd(const VehP<R>& v, R q0, R q1, R q2, R 
 
 // TrajectoryController._update_outer_loop (main.py:47-61) on the fresh state.
 // Requires a folded position (d.dx = d.dy = d.dz = 0).
-template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, const Target& t) {
+template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, const Target<R>& t) {
   const RotE<R> r = rot_entries<R>(d.q0, d.q1, d.q2, d.q3);
   const R inv_R22 = Math<R>::rcp_fast(r.R22);
   // position errors are formed in fp64 and rounded once
-  const R c = altitude_cmd<R>(d.integral, u, v, (R)(t.z - d.pz), d.vz, (R)t.vz, (R)t.az, inv_R22);
+  const R c = altitude_cmd<R>(d.integral, u, v, (R)(t.z - d.pz), d.vz, t.vz, t.az, inv_R22);
   set_thrust_cmd<R>(d, u, c);
   R bx, by;
-  lateral_cmd<R>(u, v, (R)(t.x - d.px), (R)(t.y - d.py), d.vx, d.vy, (R)t.vx, (R)t.vy, (R)t.ax, (R)t.ay, c, &bx, &by);
+  lateral_cmd<R>(u, v, (R)(t.x - d.px), (R)(t.y - d.py), d.vx, d.vy, t.vx, t.vy, t.ax, t.ay, c, &bx, &by);
   R p_c, q_c;
   roll_pitch_cmd<R>(v, bx, by, r, inv_R22, &p_c, &q_c);
   d.pc = p_c; d.qc = q_c;
-  d.rc = yaw_rate_cmd<R>(v, d.q0, d.q1, d.q2, d.q3, (R)t.yc, (R)t.ys, q_c);
+  d.rc = yaw_rate_cmd<R>(v, d.q0, d.q1, d.q2, d.q3, t.yc, t.ys, q_c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -411,8 +419,7 @@ template <class R, bool NORM = true> UAVB_HD void inner_tick(Drone<R>& d, const 
 // Position, velocity and acceleration come from one pass of the nested Horner recurrence
 //   d2 <- d2 t + d1 ; d1 <- d1 t + p ; p <- p t + c_k      (k = 6 .. 0;  p' = d1, p'' = 2 d2)
 // i.e. 3 FMAs per coefficient and no multiplications by the derivative factors k, k(k-1).
-template <class LOAD> UAVB_HD void eval_row(LOAD ld, double t, Target* out) {
-  double p[3], v[3], a[3];
+template <class LOAD> UAVB_HD void eval_row(LOAD ld, double t, double* p, double* v, double* a) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -428,9 +435,6 @@ template <class LOAD> UAVB_HD void eval_row(LOAD ld, double t, Target* out) {
     }
     p[ax] = pp; v[ax] = d1; a[ax] = d2 + d2;
   }
-  out->x = p[0]; out->y = p[1]; out->z = p[2];
-  out->vx = v[0]; out->vy = v[1]; out->vz = v[2];
-  out->ax = a[0]; out->ay = a[1]; out->az = a[2];
 }
 
 }  // namespace uavb

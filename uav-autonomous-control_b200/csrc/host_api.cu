@@ -113,6 +113,12 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
       a.seg_yaw0 = pool.upload(seg_yaw0.data(), n_seg);
       a.n_seg_shared = n_seg;
       a.dt_outer = dt_outer;
+      void* d_targets = total_rows > 0 ? static_cast<void*>(pool.alloc<char>((size_t)total_rows * UAVB_TARGET_ROW_BYTES)) : nullptr;
+      if (d_targets && pool.err == cudaSuccess) {
+        result = uavb_rollout_targets_f64(d_coeffs, d_rows, a.seg_table, a.seg_yaw0, n_seg, dt_outer, d_targets, (int)total_rows, st);
+        a.shared_targets = d_targets;
+        a.n_target_rows = (int)total_rows;
+      }
       a.start = m->start ? pool.upload(m->start, 3) : d_wp;
       a.goal = m->goal ? pool.upload(m->goal, 3) : d_wp + 3 * (size_t)(m->n_waypoints - 1);
       a.aabbs = m->n_obs > 0 ? pool.upload(m->aabbs, (size_t)m->n_obs * 6) : nullptr;

@@ -23,6 +23,10 @@ struct MissionView {
   const double* yaw0;     // [n_seg] look-ahead yaw of the table starting here (minimum_snap.py:134-135)
   int seg_begin, seg_count;
   double dt_outer;
+  // shared missions: the set-points of every table row precomputed once per launch (same arithmetic as cursor_target, so
+  // both forms give bit-identical rollouts); the cursor is then just the global row index.  nullptr = evaluate on the fly.
+  const TargetRow* trows;
+  int n_trows;
 };
 
 constexpr double kSpeed2Min = 0x1.0c6f7a0b5ed8dp-20;
@@ -73,7 +77,7 @@ UAVB_HD void cursor_advance(int* seg, int* row, const MissionView& m) {
 }
 
 // Fetch the set-point of the cursor row: polynomial values plus the yaw rule of _calculate_yaws.
-template <class R> UAVB_HD void cursor_target(Cursor<R>& c, const MissionView& m, Target* t) {
+template <class R> UAVB_HD void cursor_target(Cursor<R>& c, const MissionView& m, Target<R>* t) {
   const int sg = m.seg_begin + c.seg;
   const double* cf = m.coeffs + (size_t)sg * 24;
 #if defined(__CUDA_ARCH__)
@@ -81,7 +85,8 @@ template <class R> UAVB_HD void cursor_target(Cursor<R>& c, const MissionView& m
 #else
   auto ld = [cf](int i) { return cf[i]; };
 #endif
-  eval_row(ld, (double)c.row * m.dt_outer, t);
+  double p[3], v[3], a[3];
+  eval_row(ld, (double)c.row * m.dt_outer, p, v, a);
   if (c.row == 0 && m.table[sg]) {                       // a new table starts: rows before its first valid row take yaw0
     double s0, c0;
     const double y0 = m.yaw0[sg];
@@ -90,8 +95,26 @@ template <class R> UAVB_HD void cursor_target(Cursor<R>& c, const MissionView& m
   }
   // valid iff np.linalg.norm(v_xy) >= 1e-3 (:128-129): norm = sqrt(fl(fl(vx^2) + fl(vy^2))), and sqrt is monotonic, so the
   // test is s >= kSpeed2Min with kSpeed2Min the smallest double whose square root rounds to >= 1e-3.
-  if (speed2_unfused(t->vx, t->vy) >= kSpeed2Min) { c.hx = (R)t->vx; c.hy = (R)t->vy; }
-  t->yc = (double)c.hx; t->ys = (double)c.hy;
+  if (speed2_unfused(v[0], v[1]) >= kSpeed2Min) { c.hx = (R)v[0]; c.hy = (R)v[1]; }
+  t->x = p[0]; t->y = p[1]; t->z = p[2];
+  t->vx = (R)v[0]; t->vy = (R)v[1]; t->vz = (R)v[2];
+  t->ax = (R)a[0]; t->ay = (R)a[1]; t->az = (R)a[2];
+  t->yc = c.hx; t->ys = c.hy;
+}
+
+// The same from a precomputed row (shared missions).
+template <class R> UAVB_HD void table_target(const TargetRow* rows, int row, Target<R>* t) {
+  const TargetRow* r = rows + row;
+#if defined(__CUDA_ARCH__)
+  t->x = __ldg(&r->x); t->y = __ldg(&r->y); t->z = __ldg(&r->z);
+  t->vx = (R)__ldg(&r->vx); t->vy = (R)__ldg(&r->vy); t->vz = (R)__ldg(&r->vz);
+  t->ax = (R)__ldg(&r->ax); t->ay = (R)__ldg(&r->ay); t->az = (R)__ldg(&r->az);
+  t->yc = (R)__ldg(&r->yc); t->ys = (R)__ldg(&r->ys);
+#else
+  t->x = r->x; t->y = r->y; t->z = r->z;
+  t->vx = (R)r->vx; t->vy = (R)r->vy; t->vz = (R)r->vz; t->ax = (R)r->ax; t->ay = (R)r->ay; t->az = (R)r->az;
+  t->yc = (R)r->yc; t->ys = (R)r->ys;
+#endif
 }
 
 // n_ticks ticks of the closed loop for one drone.  `tick0` is the global index of the first tick
@@ -111,11 +134,16 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
   int k = 0;
   while (k < n_ticks) {
     if (c.phase == 0) {
-      Target t;
-      cursor_target<R>(c, m, &t);
+      Target<R> t;
+      if (m.trows) {
+        table_target<R>(m.trows, c.row, &t);
+        if (c.row + 1 < m.n_trows) ++c.row;                  // index clamp of main.py:61
+      } else {
+        cursor_target<R>(c, m, &t);
+        cursor_advance(&c.seg, &c.row, m);
+      }
       outer_update<R>(d, u, v, t);
       c.tx = t.x; c.ty = t.y; c.tz = t.z;
-      cursor_advance(&c.seg, &c.row, m);
     }
     const int n = (freq - c.phase < n_ticks - k) ? (freq - c.phase) : (n_ticks - k);
     bool watch = false;

@@ -152,6 +152,8 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
   m.seg_begin = a.mission_seg_begin ? a.mission_seg_begin[i] : 0;
   m.seg_count = a.mission_seg_count ? a.mission_seg_count[i] : a.n_seg_shared;
   m.dt_outer = a.dt_outer;
+  m.trows = a.mission_seg_begin ? nullptr : static_cast<const TargetRow*>(a.shared_targets);
+  m.n_trows = a.n_target_rows;
 
   Drone<R> d;
   Cursor<R> c;
@@ -298,6 +300,59 @@ __global__ void __maxnreg__(rollout_regs(K)) rollout_sliced_kernel(const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Set-point table of a shared mission.  Pass 1 (one thread per row): polynomial values and the row's own heading
+// (velocity direction where the horizontal speed reaches the threshold, NaN elsewhere).  Pass 2: every row takes the
+// heading of the last valid row at or before it inside its MinimumSnap table, or the table's look-ahead yaw when there is
+// none -- exactly the values cursor_target carries from row to row.
+__global__ void __launch_bounds__(128) target_rows_kernel(const double* __restrict__ coeffs, const int* __restrict__ rows,
+                                                          const int* __restrict__ table, int n_seg, double dt_outer,
+                                                          TargetRow* __restrict__ out, float2* __restrict__ raw, int* __restrict__ tstart,
+                                                          int n_rows) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_rows) return;
+  int seg = 0, first = 0, tab_first = 0;                    // segment of row g, its first row, first row of its table
+  int last_seg = 0, last_first = 0, last_tab = 0;            // last segment that owns rows (for rows past the end of the mission)
+  for (; seg < n_seg; ++seg) {
+    if (table[seg]) tab_first = first;
+    if (rows[seg] > 0) { last_seg = seg; last_first = first; last_tab = tab_first; }
+    if (g < first + rows[seg]) break;
+    first += rows[seg];
+  }
+  int local = g - first;
+  if (seg == n_seg) { seg = last_seg; first = last_first; tab_first = last_tab; local = rows[seg] - 1; }   // hold the last row (main.py:61)
+  const double* cf = coeffs + (size_t)seg * 24;
+  double p[3], v[3], a[3];
+  eval_row([cf](int i) { return __ldg(cf + i); }, (double)local * dt_outer, p, v, a);
+  TargetRow r;
+  r.x = p[0]; r.y = p[1]; r.z = p[2];
+  r.vx = (float)v[0]; r.vy = (float)v[1]; r.vz = (float)v[2];
+  r.ax = (float)a[0]; r.ay = (float)a[1]; r.az = (float)a[2];
+  r.yc = 0.f; r.ys = 0.f;
+  out[g] = r;
+  const bool valid = speed2_unfused(v[0], v[1]) >= kSpeed2Min;
+  raw[g] = valid ? make_float2((float)v[0], (float)v[1]) : make_float2(nanf(""), nanf(""));
+  tstart[g] = (tab_first << 8) | seg;                       // n_seg <= 2 * UAVB_MAX_SPLINES < 256
+}
+
+__global__ void __launch_bounds__(128) target_heading_kernel(const float2* __restrict__ raw, const int* __restrict__ tstart,
+                                                             const double* __restrict__ yaw0, const int* __restrict__ rows, int n_seg,
+                                                             TargetRow* __restrict__ out, int n_rows) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_rows) return;
+  const int tab_first = tstart[g] >> 8;
+  int r = g;
+  float2 h = raw[r];
+  while (h.x != h.x && r > tab_first) h = raw[--r];
+  if (h.x != h.x) {                                         // no valid row yet in this table: its look-ahead yaw
+    int seg = 0, first = 0;
+    while (seg < n_seg && first != tab_first) first += rows[seg++];
+    const double y0 = yaw0[seg];
+    h = make_float2((float)cos(y0), (float)sin(y0));
+  }
+  out[g].yc = h.x; out[g].ys = h.y;
+}
+
 static int check_args(const uavb_rollout_args* a, bool f64) {
   UAVB_REQUIRE(a != nullptr, "rollout: args is NULL");
   UAVB_REQUIRE(a->B >= 0 && a->n_ticks >= 0, "rollout: B and n_ticks must be >= 0");
@@ -316,6 +371,8 @@ static int check_args(const uavb_rollout_args* a, bool f64) {
   UAVB_REQUIRE(a->n_obs >= 0 && a->n_obs <= 1024, "rollout: n_obs out of range");
   UAVB_REQUIRE(a->n_obs == 0 || (a->aabbs != nullptr && a->n_obs_sets >= 1), "rollout: n_obs > 0 needs aabbs and n_obs_sets >= 1");
   UAVB_REQUIRE(a->dt_outer > 0.0 && a->veh.dt > 0.0 && a->veh.mass > 0.0, "rollout: dt_outer, veh.dt and veh.mass must be positive");
+  UAVB_REQUIRE(a->shared_targets == nullptr || (a->mission_seg_begin == nullptr && a->n_target_rows >= 1),
+               "rollout: shared_targets needs a shared mission and n_target_rows >= 1");
   return UAVB_OK;
 }
 
@@ -430,6 +487,31 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
 }
 
 }  // namespace uavb
+
+extern "C" int uavb_rollout_targets_f64(const double* seg_coeffs, const int* seg_rows, const int* seg_table, const double* seg_yaw0, int n_seg,
+                                        double dt_outer, void* targets_out, int n_rows, void* stream) {
+  using namespace uavb;
+  static_assert(sizeof(TargetRow) == UAVB_TARGET_ROW_BYTES, "TargetRow layout");
+  UAVB_REQUIRE(seg_coeffs && seg_rows && seg_table && seg_yaw0 && targets_out, "rollout_targets: NULL pointer");
+  UAVB_REQUIRE(n_seg >= 1 && n_seg <= 255 && n_rows >= 0 && dt_outer > 0.0, "rollout_targets: 1 <= n_seg <= 255, n_rows >= 0, dt_outer > 0 required");
+  int rc = require_device();
+  if (rc) return rc;
+  if (n_rows == 0) return UAVB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StreamScratch tmp(st);
+  if (tmp.alloc((size_t)n_rows * (sizeof(float2) + sizeof(int))) != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(UAVB_ENOMEM, "rollout_targets: scratch allocation failed");
+  }
+  float2* raw = static_cast<float2*>(tmp.p);
+  int* tstart = reinterpret_cast<int*>(raw + n_rows);
+  TargetRow* out = static_cast<TargetRow*>(targets_out);
+  target_rows_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(seg_coeffs, seg_rows, seg_table, n_seg, dt_outer, out, raw, tstart, n_rows);
+  UAVB_CUDA_OK(cudaGetLastError());
+  target_heading_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(raw, tstart, seg_yaw0, seg_rows, n_seg, out, n_rows);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
 
 extern "C" int uavb_rollout_f32(const uavb_rollout_args* args, void* stream) { return uavb::launch_rollout<float>(args, stream); }
 extern "C" int uavb_rollout_f64(const uavb_rollout_args* args, void* stream) { return uavb::launch_rollout<double>(args, stream); }

@@ -28,7 +28,7 @@ __device__ __forceinline__ void load_state(Drone<float>& d, const float* X, long
   d.zbx = d.zby = 0.f; d.zbz = 1.f;
 }
 
-__device__ __forceinline__ void load_target(Target& t, const float* T, long long B, long long i) {
+__device__ __forceinline__ void load_target(Target<float>& t, const float* T, long long B, long long i) {
   t.x = T[0 * B + i]; t.y = T[1 * B + i]; t.z = T[2 * B + i];
   t.vx = T[3 * B + i]; t.vy = T[4 * B + i]; t.vz = T[5 * B + i];
   t.ax = T[6 * B + i]; t.ay = T[7 * B + i]; t.az = T[8 * B + i];
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) stage_kernel(const __grid_constant__ Stag
   if (a.X) load_state(d, a.X, B, i);
   switch (a.stage) {
     case UAVB_STAGE_OUTER: {
-      Target t;
+      Target<float> t;
       load_target(t, a.target, B, i);
       d.integral = a.integral[i];
       outer_update<float>(d, u, v, t);

@@ -118,6 +118,7 @@ class MissionPlan:
     seg_count: Optional[torch.Tensor] = None   # [B] i32
     total_rows: Optional[torch.Tensor] = None  # [n_missions] i32 table rows of each mission
     times: Optional[torch.Tensor] = None       # [n_seg] f64 (MinimumSnap.times)
+    targets: Optional[torch.Tensor] = None     # shared missions: [n_rows, 56] u8 per-row set-points (uavb_rollout_targets_f64)
 
     @property
     def shared(self) -> bool:
@@ -125,14 +126,16 @@ class MissionPlan:
 
 
 def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float, shared: bool = False,
-                  factor: float = START_END_TIME_FACTOR) -> MissionPlan:
+                  factor: float = START_END_TIME_FACTOR, table_rows: Optional[int] = None) -> MissionPlan:
     """Solve and pack missions made of consecutive MinimumSnap tables.
 
     ``tables`` lists (waypoints [B, S_k+1, 3], velocity [B]) per table, e.g. the vertical take-off
     (S=1) followed by the course of ``_generate_mission_trajectory`` (uav_ac/main.py:73-84).  Mission b
     flies table 0 then table 1 ...; each table keeps its own yaw hold like the reference, where the
     two MinimumSnap instances are independent.  ``shared=True`` requires B == 1 and lets every
-    rollout fly the same mission (BASELINE configs[2]).
+    rollout fly the same mission (BASELINE configs[2]); its per-row set-point table is built as well.
+    ``table_rows`` (shared only): number of rows to tabulate when the caller already knows the table
+    length -- it avoids the device->host read of the row count (rows past the end repeat the last row).
     """
     B = tables[0][0].shape[0]
     dev = tables[0][0].device
@@ -162,10 +165,25 @@ def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float
         if B != 1:
             raise ValueError("shared=True needs a single mission")
         plan.n_seg_shared = n_per
+        plan.targets = rollout_targets(plan, table_rows)
     else:
         plan.seg_begin = torch.arange(B, dtype=torch.int32, device=dev) * n_per
         plan.seg_count = torch.full((B,), n_per, dtype=torch.int32, device=dev)
     return plan
+
+
+def rollout_targets(plan: MissionPlan, n_rows: Optional[int] = None) -> torch.Tensor:
+    """Per-row set-points of a shared mission ([n_rows, 56] bytes; struct TargetRow): what every drone of a shared-mission
+    rollout reads once per outer period instead of evaluating the polynomials itself (bit-identical results).
+    ``n_rows`` defaults to sum(seg_rows), which costs one device->host read."""
+    n_seg = plan.seg_rows.numel()
+    if n_rows is None:
+        n_rows = int(plan.seg_rows.sum().item())
+    out = torch.empty((n_rows, nat.TARGET_ROW_BYTES), dtype=torch.uint8, device=plan.seg_coeffs.device)
+    nat.check(nat.lib().uavb_rollout_targets_f64(
+        nat.ptr(plan.seg_coeffs, torch.float64, "seg_coeffs"), nat.ptr(plan.seg_rows, torch.int32, "seg_rows"), nat.ptr(plan.seg_table, torch.int32, "seg_table"),
+        nat.ptr(plan.seg_yaw0, torch.float64, "seg_yaw0"), n_seg, float(plan.dt), nat.ptr(out), n_rows, nat.stream_ptr(out.device)), "uavb_rollout_targets_f64")
+    return out
 
 
 # ------------------------------------------------------------------------------------------ K2
@@ -183,7 +201,7 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
             mc_inertia: Optional[torch.Tensor] = None, mc_gains: Optional[torch.Tensor] = None, mc_wind: Optional[torch.Tensor] = None,
             obstacles: Optional[torch.Tensor] = None, obstacle_set: Optional[torch.Tensor] = None, thrust_frame_lag: int = 1,
             log_stride: int = 0, carry: Optional[torch.Tensor] = None, resume: bool = False, want_state: bool = True,
-            want_metrics: bool = True, want_carry: bool = False, dtype: torch.dtype = torch.float32, index_base: int = 0,
+            want_metrics: bool = True, want_carry: bool = False, dtype: torch.dtype = torch.float32, index_base: int = 0, use_targets: bool = True,
             out: Optional[RolloutResult] = None) -> RolloutResult:
     """n_ticks ticks of `trajectory_controller.step(); simulation.step()` for B drones
     (tests/integration/test_mujoco_trajectory_tracking.py:27-31) in one persistent kernel launch.
@@ -214,6 +232,9 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     a.seg_yaw0 = nat.ptr(plan.seg_yaw0, torch.float64, "seg_yaw0")
     if plan.shared:
         a.n_seg_shared = int(plan.n_seg_shared)
+        if plan.targets is not None and use_targets:
+            a.shared_targets = nat.ptr(plan.targets, torch.uint8, "targets")
+            a.n_target_rows = int(plan.targets.shape[0])
     else:
         if plan.seg_begin.numel() != B:
             raise ValueError("plan holds per-rollout missions for a different batch size")
