@@ -53,7 +53,7 @@ extern "C" {
 /* per-rollout status bits (metrics column 5 and status_out of uavb_rollout_f32) */
 #define UAVB_ROLLOUT_OK        0
 #define UAVB_ROLLOUT_NONFINITE 1    /* state became NaN/Inf (the reference has no guard: controller.py:50,150,167) */
-#define UAVB_ROLLOUT_DIVERGED  2    /* |position| left the 1e4 m sanity ball */
+#define UAVB_ROLLOUT_DIVERGED  2    /* tracking error exceeded 1e4 m */
 
 /* metrics_out columns */
 #define UAVB_M_FINAL_DIST 0         /* |p - goal| after the last tick            (main.py:115)            */

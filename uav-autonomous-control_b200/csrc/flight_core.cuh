@@ -79,6 +79,13 @@ template <> struct Math<float> {
     *s = sinf(x); *c = cosf(x);
 #endif
   }
+  static UAVB_HD void sincos_fast(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+    *s = __sinf(x); *c = __cosf(x);
+#else
+    *s = sinf(x); *c = cosf(x);
+#endif
+  }
   static UAVB_HD float floor(float x) { return floorf(x); }
   static UAVB_HD float abs(float x) { return fabsf(x); }
   static UAVB_HD float fmin(float a, float b) { return fminf(a, b); }
@@ -94,6 +101,7 @@ template <> struct Math<double> {
   static UAVB_HD double fma(double a, double b, double c) { return ::fma(a, b, c); }
   static UAVB_HD double atan2(double y, double x) { return ::atan2(y, x); }
   static UAVB_HD void sincos(double x, double* s, double* c) { *s = ::sin(x); *c = ::cos(x); }
+  static UAVB_HD void sincos_fast(double x, double* s, double* c) { *s = ::sin(x); *c = ::cos(x); }
   static UAVB_HD double floor(double x) { return ::floor(x); }
   static UAVB_HD double abs(double x) { return ::fabs(x); }
   static UAVB_HD double fmin(double a, double b) { return ::fmin(a, b); }
@@ -378,10 +386,12 @@ UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx,
       cm1 = x2 * M::fma(x2, M::fma(x2, M::fma(x2, R(1.0 / 40320), R(-1.0 / 720)), R(1.0 / 24)), R(-0.5));
     }
   } else {
-    const R wn = M::sqrt(wn2);
+    // |w| > 63 rad/s: a tumbling vehicle.  Single-MUFU forms (fp32: rsqrt + sin/cos approximations, abs. error ~1e-6) keep
+    // this cold branch free of subroutine calls, so the hot loop around it keeps its constants in (uniform) registers.
+    const R iw = M::rsqrt(wn2);
     R sn, cs;
-    M::sincos(h * wn, &sn, &cs);
-    sf = sn / wn;
+    M::sincos_fast(h * (wn2 * iw), &sn, &cs);
+    sf = sn * iw;
     cm1 = cs - R(1);
   }
   const R bx = sf * d.wx, by = sf * d.wy, bz = sf * d.wz;

@@ -178,9 +178,8 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
       const R e = M::sqrt_fast(e2);
       a.sum_e += e; a.sum_e2 += e2; a.max_e = M::fmax(a.max_e, e);
       ++a.periods;
-      const R fx = (R)d.px, fy = (R)d.py, fz = (R)d.pz;
       if (!M::finite(e2)) a.status |= 1;
-      else if (fx * fx + fy * fy + fz * fz > R(1e8)) a.status |= 2;
+      else if (e2 > R(1e8)) a.status |= 2;                   // more than 1e4 m from its set-point
     }
   }
 }

@@ -34,17 +34,27 @@ template <class R> struct RolloutDev {
   VehP<R> vp;     // per-rollout constants when no Monte-Carlo override is given (constant bank)
 };
 
-// Shared obstacle set staged in shared memory (broadcast reads) or a per-rollout set in global
-// memory; inclusive bounds exactly as is_collision_cuboid (minimum_snap.py:352-357).
-struct Boxes {
+// Obstacle set: SHARED = one set for the launch, staged in the CTA's dynamic shared memory (LDS.64 broadcast reads);
+// otherwise a per-rollout set in global memory.  A box is three (min, max) pairs; inclusive bounds exactly as
+// is_collision_cuboid (minimum_snap.py:352-357).
+template <bool SHARED> struct BoxesT {
   static constexpr bool kAny = true;
   const float* b;
   int n;
+  __device__ __forceinline__ const float2* box(int i) const {
+    if constexpr (SHARED) {
+      extern __shared__ float2 s_box_pairs[];              // the same dynamic shared memory stage_shared_boxes fills
+      return s_box_pairs + 3 * i;
+    } else {
+      return reinterpret_cast<const float2*>(b) + 3 * i;
+    }
+  }
   template <class R> __device__ __forceinline__ bool hit(R x, R y, R z) const {
     bool h = false;
     for (int i = 0; i < n; ++i) {
-      const float* q = b + 6 * i;
-      h |= (q[0] <= x) & (x <= q[1]) & (q[2] <= y) & (y <= q[3]) & (q[4] <= z) & (z <= q[5]);
+      const float2* q = box(i);
+      const float2 bx = q[0], by = q[1], bz = q[2];
+      h |= (bx.x <= x) & (x <= bx.y) & (by.x <= y) & (y <= by.y) & (bz.x <= z) & (z <= bz.y);
     }
     return h;
   }
@@ -52,8 +62,9 @@ struct Boxes {
   template <class R> __device__ __forceinline__ bool within(R x, R y, R z, R reach) const {
     bool w = false;
     for (int i = 0; i < n; ++i) {
-      const float* q = b + 6 * i;
-      const R gx = fmax((R)q[0] - x, x - (R)q[1]), gy = fmax((R)q[2] - y, y - (R)q[3]), gz = fmax((R)q[4] - z, z - (R)q[5]);
+      const float2* q = box(i);
+      const float2 bx = q[0], by = q[1], bz = q[2];
+      const R gx = fmax((R)bx.x - x, x - (R)bx.y), gy = fmax((R)by.x - y, y - (R)by.y), gz = fmax((R)bz.x - z, z - (R)bz.y);
       w |= !(fmax(gx, fmax(gy, gz)) > reach);          // NaN positions keep watching
     }
     return w;
@@ -186,10 +197,11 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
     }
   };
   if (a.n_obs > 0) {
-    Boxes boxes;
-    boxes.n = a.n_obs;
-    boxes.b = shared_boxes ? s_boxes : a.aabbs + (size_t)a.aabb_set[i] * a.n_obs * 6;
-    fly(boxes);
+    if (shared_boxes) {
+      fly(BoxesT<true>{nullptr, a.n_obs});
+    } else {
+      fly(BoxesT<false>{a.aabbs + (size_t)a.aabb_set[i] * a.n_obs * 6, a.n_obs});
+    }
   } else {
     fly(NoObstacles{});
   }

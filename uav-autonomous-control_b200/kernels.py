@@ -116,13 +116,22 @@ class MissionPlan:
     n_seg_shared: int = 0              # > 0: every rollout flies segments [0, n_seg_shared)
     seg_begin: Optional[torch.Tensor] = None   # [B] i32 per-rollout missions
     seg_count: Optional[torch.Tensor] = None   # [B] i32
-    total_rows: Optional[torch.Tensor] = None  # [n_missions] i32 table rows of each mission
+    rows_per_mission: Optional[torch.Tensor] = None   # [n_missions] i32 table rows of each mission (computed on first use when None)
     times: Optional[torch.Tensor] = None       # [n_seg] f64 (MinimumSnap.times)
     targets: Optional[torch.Tensor] = None     # shared missions: [n_rows, 56] u8 per-row set-points (uavb_rollout_targets_f64)
+    status: Optional[torch.Tensor] = None      # shared missions: [n_tables] i32 UAVB_SOLVE_* of each table
 
     @property
     def shared(self) -> bool:
         return self.seg_begin is None
+
+    @property
+    def total_rows(self) -> torch.Tensor:
+        """[n_missions] i32 table rows of each mission."""
+        if self.rows_per_mission is None:
+            n = 1 if self.shared else self.seg_begin.numel()
+            self.rows_per_mission = self.seg_rows.reshape(n, -1).sum(dim=1).to(torch.int32)
+        return self.rows_per_mission
 
 
 def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float, shared: bool = False,
@@ -139,6 +148,10 @@ def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float
     """
     B = tables[0][0].shape[0]
     dev = tables[0][0].device
+    if shared:
+        if B != 1:
+            raise ValueError("shared=True needs a single mission")
+        return _plan_shared(tables, dt, factor, table_rows)
     per_table = []
     for wp, vel in tables:
         if wp.shape[0] != B:
@@ -160,15 +173,44 @@ def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float
     total = sum(t[4] for t in per_table)
     n_per = seg_rows.shape[1]
     plan = MissionPlan(seg_coeffs.reshape(-1, 8, 3), seg_rows.reshape(-1), seg_table.reshape(-1), seg_yaw0.reshape(-1), float(dt),
-                       total_rows=total.to(torch.int32), times=times.reshape(-1))
-    if shared:
-        if B != 1:
-            raise ValueError("shared=True needs a single mission")
-        plan.n_seg_shared = n_per
-        plan.targets = rollout_targets(plan, table_rows)
-    else:
-        plan.seg_begin = torch.arange(B, dtype=torch.int32, device=dev) * n_per
-        plan.seg_count = torch.full((B,), n_per, dtype=torch.int32, device=dev)
+                       rows_per_mission=total.to(torch.int32), times=times.reshape(-1))
+    plan.seg_begin = torch.arange(B, dtype=torch.int32, device=dev) * n_per
+    plan.seg_count = torch.full((B,), n_per, dtype=torch.int32, device=dev)
+    return plan
+
+
+_SHARED_CONSTS: dict = {}
+
+
+def _plan_shared(tables, dt: float, factor: float, table_rows: Optional[int]) -> MissionPlan:
+    """One mission flown by every rollout: K1 per table straight into the packed segment arrays, one table-geometry launch,
+    the set-point table -- T + 5 kernel launches for T tables, no host synchronisation when ``table_rows`` is given."""
+    dev = tables[0][0].device
+    splines = tuple(int(wp.shape[1]) - 1 for wp, _ in tables)
+    n_seg, T = sum(splines), len(splines)
+    key = (dev, splines)
+    if key not in _SHARED_CONSTS:                       # launch-invariant index arrays, built once per mission shape
+        starts = [sum(splines[:k]) for k in range(T)]
+        flag = torch.zeros(n_seg, dtype=torch.int32)
+        flag[starts] = 1
+        _SHARED_CONSTS[key] = (torch.tensor(starts + [n_seg], dtype=torch.int32, device=dev), flag.to(dev), torch.tensor(starts, dtype=torch.int64, device=dev))
+    offsets, seg_table, starts = _SHARED_CONSTS[key]
+    coeffs = torch.empty((n_seg, 8, 3), dtype=torch.float64, device=dev)
+    times = torch.empty((n_seg,), dtype=torch.float64, device=dev)
+    status = torch.empty((T,), dtype=torch.int32, device=dev)
+    L, st, off = nat.lib(), nat.stream_ptr(dev), 0
+    for k, (wp, vel) in enumerate(tables):
+        if wp.shape[0] != 1 or vel.shape != (1,):
+            raise ValueError("shared=True needs a single mission per table")
+        nat.check(L.uavb_minsnap_solve_f64(nat.ptr(wp, torch.float64, "waypoints"), nat.ptr(vel, torch.float64, "velocity"), 1, splines[k], float(factor),
+                                           ctypes.c_void_p(coeffs.data_ptr() + off * 192), ctypes.c_void_p(times.data_ptr() + off * 8),
+                                           ctypes.c_void_p(status.data_ptr() + k * 4), st), "uavb_minsnap_solve_f64")
+        off += splines[k]
+    rows, yaw0, total = table_meta(coeffs, times, offsets, dt)
+    seg_yaw0 = torch.zeros((n_seg,), dtype=torch.float64, device=dev).index_copy_(0, starts, yaw0)
+    plan = MissionPlan(coeffs, rows, seg_table, seg_yaw0, float(dt), times=times, n_seg_shared=n_seg)
+    plan.status = status
+    plan.targets = rollout_targets(plan, table_rows)
     return plan
 
 
@@ -178,7 +220,7 @@ def rollout_targets(plan: MissionPlan, n_rows: Optional[int] = None) -> torch.Te
     ``n_rows`` defaults to sum(seg_rows), which costs one device->host read."""
     n_seg = plan.seg_rows.numel()
     if n_rows is None:
-        n_rows = int(plan.seg_rows.sum().item())
+        n_rows = int(plan.total_rows.sum().item())
     out = torch.empty((n_rows, nat.TARGET_ROW_BYTES), dtype=torch.uint8, device=plan.seg_coeffs.device)
     nat.check(nat.lib().uavb_rollout_targets_f64(
         nat.ptr(plan.seg_coeffs, torch.float64, "seg_coeffs"), nat.ptr(plan.seg_rows, torch.int32, "seg_rows"), nat.ptr(plan.seg_table, torch.int32, "seg_table"),
