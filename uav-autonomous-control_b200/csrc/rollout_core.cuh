@@ -27,6 +27,11 @@ struct MissionView {
   // both forms give bit-identical rollouts); the cursor is then just the global row index.  nullptr = evaluate on the fly.
   const TargetRow* trows;
   int n_trows;
+  // on-the-fly evaluation: per-thread staging area for the 24 coefficients of the current spline (element k at
+  // cache[k * cache_stride]; shared memory in the rollout kernels), refilled only when the spline changes -- a spline
+  // lasts ~100-250 outer periods.  nullptr = read the coefficients from global memory every period.
+  double* cache;
+  int cache_stride;
 };
 
 constexpr double kSpeed2Min = 0x1.0c6f7a0b5ed8dp-20;
@@ -42,6 +47,7 @@ UAVB_HD double speed2_unfused(double vx, double vy) {
 
 template <class R> struct Cursor {
   int seg, row;           // table row the NEXT outer update will use (main.py:48 trajectory_index)
+  int cached_seg;         // packed segment whose coefficients sit in MissionView::cache (-1 = none; not part of the carry)
   int phase;              // inner_step % frequency (main.py:25,39), kept incrementally
   R hx, hy;               // heading direction of the last valid row (minimum_snap.py:126-136 hold-last-valid),
                           // any positive multiple of (cos yaw, sin yaw)
@@ -80,13 +86,27 @@ UAVB_HD void cursor_advance(int* seg, int* row, const MissionView& m) {
 template <class R> UAVB_HD void cursor_target(Cursor<R>& c, const MissionView& m, Target<R>* t) {
   const int sg = m.seg_begin + c.seg;
   const double* cf = m.coeffs + (size_t)sg * 24;
-#if defined(__CUDA_ARCH__)
-  auto ld = [cf](int i) { return __ldg(cf + i); };
-#else
-  auto ld = [cf](int i) { return cf[i]; };
-#endif
   double p[3], v[3], a[3];
-  eval_row(ld, (double)c.row * m.dt_outer, p, v, a);
+  if (m.cache) {
+    if (c.cached_seg != sg) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+      for (int k = 0; k < 24; ++k) m.cache[k * m.cache_stride] = __ldg(cf + k);
+#else
+      for (int k = 0; k < 24; ++k) m.cache[k * m.cache_stride] = cf[k];
+#endif
+      c.cached_seg = sg;
+    }
+    const double* cc = m.cache;
+    const int cs = m.cache_stride;
+    eval_row([cc, cs](int i) { return cc[i * cs]; }, (double)c.row * m.dt_outer, p, v, a);
+  } else {
+#if defined(__CUDA_ARCH__)
+    eval_row([cf](int i) { return __ldg(cf + i); }, (double)c.row * m.dt_outer, p, v, a);
+#else
+    eval_row([cf](int i) { return cf[i]; }, (double)c.row * m.dt_outer, p, v, a);
+#endif
+  }
   if (c.row == 0 && m.table[sg]) {                       // a new table starts: rows before its first valid row take yaw0
     double s0, c0;
     const double y0 = m.yaw0[sg];
@@ -198,7 +218,7 @@ template <class R> UAVB_HD void drone_init(Drone<R>& d, const VehU<R>& u, double
 }
 
 template <class R> UAVB_HD void cursor_init(Cursor<R>& c) {
-  c.seg = 0; c.row = 0; c.phase = 0; c.hx = R(1); c.hy = R(0); c.tx = c.ty = c.tz = 0.0;
+  c.seg = 0; c.row = 0; c.cached_seg = -1; c.phase = 0; c.hx = R(1); c.hy = R(0); c.tx = c.ty = c.tz = 0.0;
 }
 
 template <class R> UAVB_HD void accum_init(Accum<R>& a) {

@@ -32,6 +32,7 @@ template <class R> struct RolloutDev {
   uavb_rollout_args a;
   VehU<R> u;      // launch-uniform constants (constant bank)
   VehP<R> vp;     // per-rollout constants when no Monte-Carlo override is given (constant bank)
+  int coeff_cache_offset;   // offset (in doubles) of the [24][64] coefficient staging area in dynamic shared memory, -1 = none
 };
 
 // Obstacle set: SHARED = one set for the launch, staged in the CTA's dynamic shared memory (LDS.64 broadcast reads);
@@ -121,7 +122,7 @@ struct Carry {
     d.om0 = w(16); d.om1 = w(17); d.om2 = w(18); d.om3 = w(19);
     d.integral = w(20); set_thrust_cmd<float>(d, u, w(21)); d.pc = w(22); d.qc = w(23); d.rc = w(24);
     d.zbx = w(25); d.zby = w(26); d.zbz = w(27); c.hx = w(28);
-    c.seg = f2i(w(29)); c.row = f2i(w(30)); c.phase = f2i(w(31));
+    c.seg = f2i(w(29)); c.row = f2i(w(30)); c.phase = f2i(w(31)); c.cached_seg = -1;
     c.tx = get64(32); c.ty = get64(34); c.tz = get64(36);
     a.sum_e = w(38); a.sum_e2 = w(39); a.max_e = w(40);
     a.periods = f2i(w(41)); a.collided = f2i(w(42)); a.first_hit = f2i(w(43)); a.status = f2i(w(44));
@@ -165,6 +166,12 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
   m.dt_outer = a.dt_outer;
   m.trows = a.mission_seg_begin ? nullptr : static_cast<const TargetRow*>(a.shared_targets);
   m.n_trows = a.n_target_rows;
+  m.cache = nullptr; m.cache_stride = 0;
+  if (p.coeff_cache_offset >= 0) {             // on-the-fly evaluation: this thread's column of the CTA's coefficient staging area
+    extern __shared__ double s_dyn_f64[];
+    m.cache = s_dyn_f64 + p.coeff_cache_offset + threadIdx.x;
+    m.cache_stride = kRolloutThreads;
+  }
 
   Drone<R> d;
   Cursor<R> c;
@@ -437,7 +444,14 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   mc_from_vehicle(mc, a->veh);
   make_vehp<R>(p.vp, a->veh, mc);
   const int grid = div_up(a->B, kRolloutThreads);
-  const size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
+  size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
+  p.coeff_cache_offset = -1;
+  const bool from_table = a->shared_targets != nullptr && a->mission_seg_begin == nullptr;
+  if (!from_table && sizeof(R) == 4 && a->log_stride == 0) {     // metrics-only fp32 kernels stage the current spline in shared memory
+    smem = (smem + 7) / 8 * 8;
+    p.coeff_cache_offset = (int)(smem / 8);
+    smem += sizeof(double) * 24 * kRolloutThreads;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool mc_any = a->mc_mass || a->mc_inertia || a->mc_gains || a->mc_wind;
   const bool log = a->log_stride > 0;
