@@ -92,3 +92,30 @@ def test_lab_course_xml_reproduces_the_transcribed_constants():
     np.testing.assert_array_equal(s.motor_time_constants, [v.tau_rise, v.tau_fall])
     np.testing.assert_array_equal(s.flight_limits, [v.max_ascent, v.max_descent, v.max_speed_xy, v.max_horiz_accel, v.max_tilt])
     np.testing.assert_array_equal(s.rotor_spins, [1, -1, 1, -1])
+
+
+def test_mujoco_to_ned_state_converts_enu_and_flu_frames():
+    """tests/unit/simulation/test_mujoco_sim.py:61-74 of the reference, plus a batch."""
+    s = scene.mujoco_to_ned_state([1.0, -2.0, 3.0], [np.sqrt(0.5), 0.0, 0.0, np.sqrt(0.5)], [4.0, -5.0, 6.0, 0.1, -0.2, 0.3])
+    np.testing.assert_allclose(s, [1, 2, -3, np.sqrt(0.5), 0, 0, -np.sqrt(0.5), 4, 5, -6, 0.1, 0.2, -0.3], rtol=1e-15)
+    b = scene.mujoco_to_ned_state(np.zeros((5, 3)), np.tile([2.0, 0, 0, 0], (5, 1)), np.zeros((5, 6)))
+    assert b.shape == (5, 13) and np.all(b[:, 3] == 1.0)
+    with pytest.raises(ValueError):
+        scene.mujoco_to_ned_state([0, 0, 0], [0, 0, 0, 0], np.zeros(6))
+    with pytest.raises(ValueError):
+        scene.mujoco_to_ned_state([0, 0, np.nan], [1, 0, 0, 0], np.zeros(6))
+
+
+def test_laboratory_course_is_the_compact_multi_challenge_route():
+    """tests/unit/test_utils.py:10-62 of the reference on the transcribed scene and config."""
+    from uav_ac_b200 import utils
+    cfg, cfg_flight = utils.get_config()
+    assert cfg.getint("frequency") > 0 and cfg_flight.getfloat("velocity") > 0 and cfg_flight.getfloat("min_dist_target") == 0.5
+    w, obs, lim = scene.LAB_COURSE_WAYPOINTS, scene.LAB_COURSE_OBSTACLES, scene.PLANNING_BOUNDS
+    size = lim[1] - lim[0]
+    assert size[0] == pytest.approx(24.0) and size[1] == pytest.approx(14.0) and len(w) == 9
+    assert np.linalg.norm(np.diff(w, axis=0), axis=1).sum() > 25.0
+    lower_alt, upper_alt = -obs[:, 5], -obs[:, 4]                       # NED z is down: altitude = -z
+    assert np.any(lower_alt > 2.0) and np.any(np.isclose(lower_alt, 0.0)) and np.any(upper_alt < 3.0)
+    assert np.all((w >= lim[0]) & (w <= lim[1]))
+    assert np.array_equal(utils.parse_array({"k": "[1, 2, 3]"}, "k"), [1, 2, 3])

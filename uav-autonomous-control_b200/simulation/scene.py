@@ -144,3 +144,16 @@ def load_scene(xml_path) -> Scene:
                  thrust_limits=numeric("rotor_thrust_limits", 2), motor_time_constants=numeric("motor_time_constants", 2),
                  flight_limits=numeric("flight_limits", 5), planning_bounds=np.array([b[:3], b[3:]]), start_position=start, goal_position=goal,
                  mission_waypoints=np.vstack((start, mandatory, goal)), obstacles=obstacles)
+
+
+def mujoco_to_ned_state(position, quaternion, velocity) -> np.ndarray:
+    """MuJoCo ENU/FLU free-joint state(s) -> the NED/FRD state vector(s) X of the batched path (mujoco_sim.py:20-45),
+    for users who replay or seed rollouts from a MuJoCo simulation.  Accepts (3,), (4,), (6,) or batches (B, .)."""
+    p, q, v = (np.asarray(a, dtype=float) for a in (position, quaternion, velocity))
+    if p.shape[-1] != 3 or q.shape[-1] != 4 or v.shape[-1] != 6 or not all(np.all(np.isfinite(a)) for a in (p, q, v)):
+        raise ValueError("MuJoCo position / quaternion / velocity must contain 3 / 4 / 6 finite values")
+    n = np.linalg.norm(q, axis=-1, keepdims=True)
+    if np.any(n == 0):
+        raise ValueError("MuJoCo quaternion cannot be zero")
+    flip = np.array([1.0, -1.0, -1.0])
+    return np.concatenate((p * flip, q / n * np.array([1.0, 1.0, -1.0, -1.0]), v[..., :3] * flip, v[..., 3:] * flip), axis=-1)
