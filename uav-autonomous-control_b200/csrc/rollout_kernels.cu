@@ -135,7 +135,7 @@ struct Carry {
 // pose; writes the carry block (to_carry) and / or the final outputs (finish).
 // MC: some per-rollout override (mass / inertia / gains / wind) is present; otherwise every vehicle constant is a
 // constant-bank operand.
-template <class R, bool LOG, bool MC>
+template <class R, bool LOG, bool MC, bool TABLE>
 __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float* s_boxes, long long i, int n_ticks, bool from_carry,
                                             bool to_carry, bool finish) {
   const uavb_rollout_args& a = p.a;
@@ -197,10 +197,10 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
       GlobalLog<R> lg;
       lg.out = reinterpret_cast<R*>(a.log_out) + i;
       lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride;
-      rollout_run<R>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+      rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
     } else {
       NoLog lg;
-      rollout_run<R>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+      rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
     }
   };
   if (a.n_obs > 0) {
@@ -263,7 +263,10 @@ __global__ void __maxnreg__(rollout_regs(K)) rollout_kernel(const __grid_constan
   stage_shared_boxes(p.a, s_boxes);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.a.B) return;
-  drone_slice<R, LOG, MC>(p, s_boxes, i, p.a.n_ticks, p.a.resume != 0, p.a.carry != nullptr, true);
+  if (p.a.shared_targets != nullptr && p.a.mission_seg_begin == nullptr)
+    drone_slice<R, LOG, MC, true>(p, s_boxes, i, p.a.n_ticks, p.a.resume != 0, p.a.carry != nullptr, true);
+  else
+    drone_slice<R, LOG, MC, false>(p, s_boxes, i, p.a.n_ticks, p.a.resume != 0, p.a.carry != nullptr, true);
 }
 
 // Time-sliced persistent launch (every metrics-only fp32 rollout).  When the batch needs between one and a few waves of
@@ -288,7 +291,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-template <bool MC, int K>
+template <bool MC, bool TABLE, int K>
 __global__ void __maxnreg__(rollout_regs(K)) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
   extern __shared__ float s_boxes[];
   __shared__ int s_item;
@@ -311,7 +314,7 @@ __global__ void __maxnreg__(rollout_regs(K)) rollout_sliced_kernel(const __grid_
     if (i < p.a.B) {
       const bool last = c == sch.n_chunks - 1;
       const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
-      drone_slice<float, false, MC>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last);
+      drone_slice<float, false, MC, TABLE>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last);
     }
     __threadfence();
     __syncthreads();
@@ -423,11 +426,10 @@ struct StreamScratch {
   }
 };
 
-template <bool MC> static void launch_sliced(int k, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch) {
+template <bool MC, bool TABLE> static void launch_sliced(int k, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch) {
   switch (k) {
-    case 8: rollout_sliced_kernel<MC, 8><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
-    case 10: rollout_sliced_kernel<MC, 10><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
-    default: rollout_sliced_kernel<MC, 12><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
+    case 8: rollout_sliced_kernel<MC, TABLE, 8><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
+    default: rollout_sliced_kernel<MC, TABLE, 12><<<grid, kRolloutThreads, smem, st>>>(p, sch); break;
   }
 }
 
@@ -476,7 +478,7 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
       const int f = atoi(force);
       if (f >= kRolloutCtasMin && f <= kRolloutCtasMax) k = f;
     }
-    if (k != 8 && k != 10) k = 12;
+    if (k != 8) k = 12;                                                  // compiled residencies: 8 (production) and 12 (experiments)
     const int slots = sms * k;
     // ~32 items per resident CTA keep the tail near 3 % of the launch; slices are whole outer periods of >= 100 ticks
     constexpr int kMinChunkTicks = 100;
@@ -505,8 +507,14 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     sch.done = sch.counter + 1;
     sch.n_groups = grid; sch.n_chunks = n_chunks; sch.chunk_ticks = chunk;
     const int pgrid = slots < grid ? slots : grid;
-    if (mc_any) launch_sliced<true>(k, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
-    else launch_sliced<false>(k, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
+    const RolloutDev<float>& pf = *reinterpret_cast<RolloutDev<float>*>(&p);
+    if (from_table) {
+      if (mc_any) launch_sliced<true, true>(k, pgrid, smem, st, pf, sch);
+      else launch_sliced<false, true>(k, pgrid, smem, st, pf, sch);
+    } else {
+      if (mc_any) launch_sliced<true, false>(k, pgrid, smem, st, pf, sch);
+      else launch_sliced<false, false>(k, pgrid, smem, st, pf, sch);
+    }
   }
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
