@@ -45,6 +45,10 @@ UAVB_HD double speed2_unfused(double vx, double vy) {
 #endif
 }
 
+template <bool V> struct BoolC {
+  static constexpr bool value = V;
+};
+
 template <class R> struct Cursor {
   int seg, row;           // table row the NEXT outer update will use (main.py:48 trajectory_index)
   int cached_seg;         // packed segment whose coefficients sit in MissionView::cache (-1 = none; not part of the carry)
@@ -175,19 +179,23 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
       const R reach = R(1.01) * (speed + v.acc_max * T) * T + R(1e-4);
       watch = obst.within((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz), reach);
     }
-    if (watch) {
+    // the stretch is specialised on the two warp-uniform switches (watch, lag): the 1 kHz body then carries no selects for them
+    auto stretch = [&](auto watch_c, auto lag_c) {
+      constexpr bool kWatch = decltype(watch_c)::value, kLag = decltype(lag_c)::value;
       for (int j = 0; j < n; ++j) {
-        inner_tick<R, LOG::kNormEveryTick>(d, u, v, lag);
-        if (!a.collided && obst.hit((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz))) {
-          a.collided = 1; a.first_hit = tick0 + k + j;
+        inner_tick<R, LOG::kNormEveryTick>(d, u, v, kLag);
+        if constexpr (kWatch) {
+          if (!a.collided && obst.hit((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz))) {
+            a.collided = 1; a.first_hit = tick0 + k + j;
+          }
         }
         logger.tick(d);
       }
+    };
+    if (watch) {
+      if (lag) stretch(BoolC<true>{}, BoolC<true>{}); else stretch(BoolC<true>{}, BoolC<false>{});
     } else {
-      for (int j = 0; j < n; ++j) {
-        inner_tick<R, LOG::kNormEveryTick>(d, u, v, lag);
-        logger.tick(d);
-      }
+      if (lag) stretch(BoolC<false>{}, BoolC<true>{}); else stretch(BoolC<false>{}, BoolC<false>{});
     }
     k += n;
     c.phase += n;
