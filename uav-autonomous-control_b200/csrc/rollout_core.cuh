@@ -182,6 +182,9 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
     // the stretch is specialised on the two warp-uniform switches (watch, lag): the 1 kHz body then carries no selects for them
     auto stretch = [&](auto watch_c, auto lag_c) {
       constexpr bool kWatch = decltype(watch_c)::value, kLag = decltype(lag_c)::value;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
       for (int j = 0; j < n; ++j) {
         inner_tick<R, LOG::kNormEveryTick>(d, u, v, kLag);
         if constexpr (kWatch) {
