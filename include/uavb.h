@@ -80,7 +80,7 @@ int         uavb_device_info(int dev, int* sm_count, int* cc_major, int* cc_mino
  * reference's KKT system [[Q,A^T],[A,0]] (rows listed at :171-255, Q at :155-169) is computed from
  * its reduced form: the free unknowns are velocity/acceleration/jerk at the S-1 interior waypoints,
  * the stationarity conditions form an SPD block-tridiagonal system with 3x3 blocks that is solved
- * in registers, and the 8 coefficients of every spline follow in closed form (DESIGN.md "K1").
+ * in registers (block Thomas elimination, LDL^T blocks), and the 8 coefficients of every spline follow in closed form (DESIGN.md "K1").
  *
  *   waypoints  [B][S+1][3]  row-major, NED metres
  *   velocity   [B]          cruise speed of each mission (minimum_snap.py:13 `velocity`)
