@@ -66,18 +66,17 @@ class TrajectoryController:
         self.trajectory_index = min(self.trajectory_index + 1, n - 1)
 
 
-def _trajectory_after_takeoff(trajectory: np.ndarray, takeoff_waypoint: np.ndarray) -> np.ndarray:
-    """Trajectory from the sample nearest the take-off waypoint (main.py:64-70)."""
-    trajectory = np.asarray(trajectory)
-    distances = np.linalg.norm(trajectory[:, :3] - takeoff_waypoint, axis=1)
-    return trajectory[np.argmin(distances):]
+def _trajectory_after_takeoff(trajectory, takeoff_waypoint) -> np.ndarray:
+    """Rows of the table from the one closest to the take-off waypoint onwards (main.py:64-70; used for display only)."""
+    table = np.asarray(trajectory)
+    first = int(np.argmin(((table[:, :3] - np.asarray(takeoff_waypoint)) ** 2).sum(axis=1)))
+    return table[first:]
 
 
-def _generate_mission_trajectory(waypoints: np.ndarray, obstacles: np.ndarray, velocity: float, dt: float) -> np.ndarray:
-    """Isolated vertical take-off followed by the laboratory course (main.py:73-84)."""
-    takeoff_trajectory = MinimumSnap(waypoints[:2], obstacles, velocity, dt).get_trajectory()
-    course_trajectory = MinimumSnap(waypoints[1:], obstacles, velocity, dt).get_trajectory()
-    return np.vstack((takeoff_trajectory, course_trajectory))
+def _generate_mission_trajectory(waypoints, obstacles, velocity: float, dt: float) -> np.ndarray:
+    """Two independent plans stacked (main.py:73-84): the vertical take-off (start -> first waypoint), then the course."""
+    legs = (waypoints[:2], waypoints[1:])
+    return np.vstack([MinimumSnap(leg, obstacles, velocity, dt).get_trajectory() for leg in legs])
 
 
 def main(batch: int = 100_000) -> None:
