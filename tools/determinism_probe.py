@@ -1,4 +1,4 @@
-"""Development probe: are rollout results independent of the residency variant, of time slicing and of sharding?"""
+"""Development probe: are rollout results independent of time slicing and of sharding?"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -21,22 +21,21 @@ sets = (torch.arange(B, device=dev) % 64).to(torch.int32)
 plan, start, goal, wind = c4_inputs(B)
 n = 10 * int(plan.total_rows.max().item())
 def fly(plan, B, start, goal, wind, sets, **env):
-    for k in ("UAVB_ROLLOUT_K", "UAVB_ROLLOUT_SLICED"):
+    for k in ("UAVB_ROLLOUT_CHUNKS",):
         os.environ.pop(k, None)
     for k, v in env.items():
         os.environ[k] = str(v)
     r = kernels.rollout(plan, B, n, start=start, goal=goal, mc_wind=wind, obstacles=boxes, obstacle_set=sets)
     torch.cuda.synchronize()
     return r
-ref = fly(plan, B, start, goal, wind, sets, UAVB_ROLLOUT_K=8, UAVB_ROLLOUT_SLICED=0)
-for env in (dict(UAVB_ROLLOUT_K=10, UAVB_ROLLOUT_SLICED=0), dict(UAVB_ROLLOUT_K=12, UAVB_ROLLOUT_SLICED=0), dict(UAVB_ROLLOUT_K=8, UAVB_ROLLOUT_SLICED=1),
-            dict(UAVB_ROLLOUT_K=12, UAVB_ROLLOUT_SLICED=1), dict()):
+ref = fly(plan, B, start, goal, wind, sets, UAVB_ROLLOUT_CHUNKS=1)
+for env in (dict(UAVB_ROLLOUT_CHUNKS=3), dict(UAVB_ROLLOUT_CHUNKS=40), dict()):
     r = fly(plan, B, start, goal, wind, sets, **env)
     print(env, "metrics equal", bool(torch.equal(r.metrics, ref.metrics)), "state equal", bool(torch.equal(r.state, ref.state)),
           "max |dmetrics|", float((r.metrics - ref.metrics).abs().max()))
 lo, m = 120_000, 512
 plan2, s2, g2, w2 = c4_inputs(m, lo)
-sub = fly(plan2, m, s2, g2, w2, sets[lo:lo + m].contiguous(), UAVB_ROLLOUT_K=8, UAVB_ROLLOUT_SLICED=0)
+sub = fly(plan2, m, s2, g2, w2, sets[lo:lo + m].contiguous())
 d = (sub.metrics - ref.metrics[lo:lo + m]).abs()
 print("reshard: metrics equal", bool(torch.equal(sub.metrics, ref.metrics[lo:lo + m])), "per-column max diff", d.max(dim=0).values.tolist())
 print("  plan coeffs equal", bool(torch.equal(plan2.seg_coeffs, plan.seg_coeffs.reshape(B, -1, 8, 3)[lo:lo + m].reshape(-1, 8, 3))),

@@ -1,4 +1,5 @@
-"""Development probe: one-shot vs time-sliced rollout at several batch sizes and slice counts."""
+"""Development probe: the time-sliced rollout at several batch sizes and slice counts (UAVB_ROLLOUT_CHUNKS; 1 = a single slice,
+i.e. the behaviour of a one-shot launch)."""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,7 +14,7 @@ plan = kernels.plan_missions([(wpl[None, :2].contiguous(), v3), (wpl[None, 1:].c
 n_ticks = 10 * int(plan.total_rows.item())
 obs = torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=dev)
 def run(B, **env):
-    for k in ("UAVB_ROLLOUT_K", "UAVB_ROLLOUT_SLICED", "UAVB_ROLLOUT_CHUNKS"):
+    for k in ("UAVB_ROLLOUT_CHUNKS",):
         os.environ.pop(k, None)
     for k, v in env.items():
         os.environ[k] = str(v)
@@ -28,9 +29,10 @@ def run(B, **env):
     t = statistics.mean(ts)
     print(f"B={B} {env}: {t:.3f} ms -> {B * n_ticks / t / 1e6:.1f} G ticks/s", flush=True)
 for B in (37888, 75776, 100000, 151552):
-    run(B, UAVB_ROLLOUT_SLICED=0)
+    run(B, UAVB_ROLLOUT_CHUNKS=1)
 for ch in (2, 5, 10, 25, 50, 100):
-    run(100000, UAVB_ROLLOUT_SLICED=1, UAVB_ROLLOUT_CHUNKS=ch)
-run(500000, UAVB_ROLLOUT_SLICED=0)
-run(500000, UAVB_ROLLOUT_SLICED=1, UAVB_ROLLOUT_CHUNKS=1)
-run(500000, UAVB_ROLLOUT_SLICED=1, UAVB_ROLLOUT_CHUNKS=8)
+    run(100000, UAVB_ROLLOUT_CHUNKS=ch)
+run(100000)
+run(500000, UAVB_ROLLOUT_CHUNKS=1)
+run(500000, UAVB_ROLLOUT_CHUNKS=8)
+run(500000)
