@@ -145,37 +145,136 @@ __global__ void __launch_bounds__(128) table_meta_kernel(const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 sampled table.  Pass 1: one warp per mission, lanes stride the rows of each segment and write
-// position / velocity / acceleration / spline id; the yaw column receives atan2(vy, vx) or NaN for
-// rows below the speed threshold.  Pass 2: one thread per mission walks its rows in order and
-// applies np.unwrap + hold-last-valid + first-valid look-ahead (minimum_snap.py:126-136).
-__global__ void __launch_bounds__(128) sample_rows_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
-                                                          const int* __restrict__ seg_rows, const int* __restrict__ row_offsets, int B,
-                                                          double dt, double* __restrict__ table) {
-  const int lane = threadIdx.x & 31;
+// K3 sampled table, one pass, one warp per mission.  The lanes take 32 consecutive rows (across spline boundaries),
+// evaluate position / velocity / acceleration, and resolve the yaw column with warp scans that carry their state from
+// chunk to chunk: np.unwrap over the valid rows is raw + cumsum(correction) (a prefix sum), hold-last-valid is a
+// fill-forward from the nearest valid lane, and rows before the first valid row take the first valid yaw, found by a
+// short velocity-only pre-scan (minimum_snap.py:126-136).  Each 32 x 11 tile is staged in shared memory and leaves the
+// warp as one contiguous 2 816-byte block of fully coalesced 8-byte stores.
+constexpr int kSampleWarps = 4;
+
+struct RowEval {
+  double p[3], v[3], a[3];
+};
+
+__device__ __forceinline__ void eval_table_row(const double* __restrict__ c, double t, RowEval& r, bool vel_only) {
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const double c7 = c[21 + ax], c6 = c[18 + ax], c5 = c[15 + ax], c4 = c[12 + ax];
+    const double c3 = c[9 + ax], c2 = c[6 + ax], c1 = c[3 + ax], c0 = c[ax];
+    r.v[ax] = (((((7.0 * c7 * t + 6.0 * c6) * t + 5.0 * c5) * t + 4.0 * c4) * t + 3.0 * c3) * t + 2.0 * c2) * t + c1;
+    if (!vel_only) {
+      r.p[ax] = ((((((c7 * t + c6) * t + c5) * t + c4) * t + c3) * t + c2) * t + c1) * t + c0;
+      r.a[ax] = ((((42.0 * c7 * t + 30.0 * c6) * t + 20.0 * c5) * t + 12.0 * c4) * t + 6.0 * c3) * t + 2.0 * c2;
+    }
+  }
+}
+
+__device__ __forceinline__ bool yaw_valid(double vx, double vy) { return sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy))) >= 1e-3; }
+
+__global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
+                                                                         const int* __restrict__ seg_rows, const int* __restrict__ row_offsets,
+                                                                         int B, double dt, double* __restrict__ table) {
+  __shared__ double s_tile[kSampleWarps][32 * 11];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
+  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+  const double two_pi = 6.283185307179586476925286766559, pi = 3.141592653589793238462643383279;
   const int s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
-  long long row = row_offsets[b];
-  for (int s = s0; s < s1; ++s) {
-    const int n = seg_rows[s];
-    const double* c = coeffs + (size_t)s * 24;
-    for (int j = lane; j < n; j += 32) {
-      const double t = (double)j * dt;
-      double* o = table + (size_t)(row + j) * 11;
-#pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        const double c7 = c[21 + ax], c6 = c[18 + ax], c5 = c[15 + ax], c4 = c[12 + ax];
-        const double c3 = c[9 + ax], c2 = c[6 + ax], c1 = c[3 + ax], c0 = c[ax];
-        o[ax] = ((((((c7 * t + c6) * t + c5) * t + c4) * t + c3) * t + c2) * t + c1) * t + c0;
-        o[3 + ax] = (((((7.0 * c7 * t + 6.0 * c6) * t + 5.0 * c5) * t + 4.0 * c4) * t + 3.0 * c3) * t + 2.0 * c2) * t + c1;
-        o[6 + ax] = ((((42.0 * c7 * t + 30.0 * c6) * t + 20.0 * c5) * t + 12.0 * c4) * t + 6.0 * c3) * t + 2.0 * c2;
+  const long long row0 = row_offsets[b];
+  const int N = (int)(row_offsets[b + 1] - row0);
+  double* tile = s_tile[wib];
+
+  // segment cursor shared by the warp: segment `cs` starts at mission row `cf`
+  auto locate = [&](int g, int& s, int& f) {           // advance (s, f) until row g lies in segment s
+    while (s < s1 - 1 && g >= f + seg_rows[s]) { f += seg_rows[s]; ++s; }
+  };
+
+  // ---- pre-scan: the first valid yaw (look-ahead value of the leading rows); zeros when no row is valid
+  double first_yaw = 0.0;
+  bool any_valid = false;
+  {
+    int cs = s0, cf = 0;
+    for (int base = 0; base < N && !any_valid; base += 32) {
+      int s = cs, f = cf;
+      const int g = base + lane;
+      bool valid = false;
+      double raw = 0.0;
+      if (g < N) {
+        locate(g, s, f);
+        RowEval r;
+        eval_table_row(coeffs + (size_t)s * 24, (double)(g - f) * dt, r, true);
+        valid = yaw_valid(r.v[0], r.v[1]);
+        if (valid) raw = atan2(r.v[1], r.v[0]);
       }
-      const double vx = o[3], vy = o[4];
-      o[9] = (sqrt(vx * vx + vy * vy) >= 1e-3) ? atan2(vy, vx) : nan("");
-      o[10] = (double)(s - s0);
+      const unsigned bal = __ballot_sync(full, valid);
+      if (bal) { first_yaw = __shfl_sync(full, raw, __ffs(bal) - 1); any_valid = true; }
+      locate(base + 31 < N ? base + 31 : N - 1, cs, cf);   // warp-uniform cursor for the next chunk
     }
-    row += n;
+  }
+
+  // ---- main pass
+  int cs = s0, cf = 0;
+  bool have_prev = false;
+  double prev_raw = 0.0, cum = 0.0, hold = first_yaw;
+  for (int base = 0; base < N; base += 32) {
+    int s = cs, f = cf;
+    const int g = base + lane;
+    const bool active = g < N;
+    bool valid = false;
+    double raw = 0.0;
+    RowEval r;
+    if (active) {
+      locate(g, s, f);
+      eval_table_row(coeffs + (size_t)s * 24, (double)(g - f) * dt, r, false);
+      valid = yaw_valid(r.v[0], r.v[1]);
+      if (valid) raw = atan2(r.v[1], r.v[0]);
+    }
+    const unsigned bal = __ballot_sync(full, valid);
+    // np.unwrap on the valid rows: dd against the previous valid row (in this chunk or carried), correction where |dd| >= pi
+    const unsigned before = bal & lt;
+    const int pv = before ? 31 - __clz(before) : -1;
+    const double pr_lane = __shfl_sync(full, raw, pv >= 0 ? pv : 0);
+    double corr = 0.0;
+    if (valid && (pv >= 0 || have_prev)) {
+      const double dd = raw - (pv >= 0 ? pr_lane : prev_raw);
+      double ddmod = dd + pi;
+      ddmod = ddmod - two_pi * floor(ddmod / two_pi) - pi;
+      if (ddmod == -pi && dd > 0.0) ddmod = pi;
+      if (fabs(dd) >= pi) corr = ddmod - dd;
+    }
+    double incl = corr;                                  // inclusive prefix sum of the corrections over the lanes
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const double up = __shfl_up_sync(full, incl, off);
+      if (lane >= off) incl += up;
+    }
+    const double y_valid = raw + (cum + incl);
+    // hold-last-valid: nearest valid lane at or before this one, else the value carried from earlier chunks
+    const unsigned upto = bal & (lt | (1u << lane));
+    const int lv = upto ? 31 - __clz(upto) : -1;
+    const double y_lane = __shfl_sync(full, y_valid, lv >= 0 ? lv : 0);
+    const double yaw = any_valid ? (lv >= 0 ? y_lane : hold) : 0.0;
+    if (bal) {
+      const int last = 31 - __clz(bal);
+      prev_raw = __shfl_sync(full, raw, last);
+      hold = __shfl_sync(full, y_valid, last);
+      have_prev = true;
+    }
+    cum += __shfl_sync(full, incl, 31);
+    // ---- stage the tile and write it out contiguously
+    if (active) {
+      double* o = tile + lane * 11;
+      o[0] = r.p[0]; o[1] = r.p[1]; o[2] = r.p[2]; o[3] = r.v[0]; o[4] = r.v[1]; o[5] = r.v[2];
+      o[6] = r.a[0]; o[7] = r.a[1]; o[8] = r.a[2]; o[9] = yaw; o[10] = (double)(s - s0);
+    }
+    __syncwarp();
+    const int n_here = (N - base < 32 ? N - base : 32) * 11;
+    double* out = table + (size_t)(row0 + base) * 11;
+    for (int e = lane; e < n_here; e += 32) out[e] = tile[e];
+    __syncwarp();
+    locate(base + 31 < N ? base + 31 : N - 1, cs, cf);
   }
 }
 
@@ -328,9 +427,8 @@ extern "C" int uavb_minsnap_sample_f64(const double* coeffs, const double* times
   if (rc) return rc;
   if (B == 0) return UAVB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  sample_rows_kernel<<<div_up((long long)B * 32, 128), 128, 0, st>>>(coeffs, seg_offsets, seg_rows, row_offsets, B, dt, table_out);
-  UAVB_CUDA_OK(cudaGetLastError());
-  sample_yaw_kernel<<<div_up(B, 128), 128, 0, st>>>(row_offsets, B, table_out + 9, 11);
+  sample_table_kernel<<<div_up((long long)B * 32, 32 * kSampleWarps), 32 * kSampleWarps, 0, st>>>(coeffs, seg_offsets, seg_rows, row_offsets, B, dt,
+                                                                                                  table_out);
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }
