@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UAVB_VERSION 100            /* 0.1.0 */
+#define UAVB_VERSION 110            /* 0.1.10: carry block of 52 words, stage ABI v2, host mission call, set-point table, RRT* */
 
 #define UAVB_OK          0
 #define UAVB_EINVAL     -1          /* bad argument (null pointer, size out of range) */

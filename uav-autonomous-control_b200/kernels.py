@@ -288,11 +288,9 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     if goal is not None:
         a.goal = nat.ptr(goal, torch.float64, "goal")
         a.goal_stride = 0 if goal.dim() == 1 else 3
-    keep = [start, goal]
     if obstacles is not None and obstacles.numel() > 0:
         obs = obstacles if obstacles.dim() == 3 else obstacles.unsqueeze(0)
         obs = obs.to(torch.float32).contiguous()
-        keep.append(obs)
         a.n_obs_sets, a.n_obs = int(obs.shape[0]), int(obs.shape[1])
         a.aabbs = nat.ptr(obs, torch.float32, "obstacles")
         if obstacle_set is not None:
