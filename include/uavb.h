@@ -207,12 +207,13 @@ typedef struct uavb_rollout_args {
 int uavb_rollout_targets_f64(const double* seg_coeffs, const int* seg_rows, const int* seg_table, const double* seg_yaw0,
                              int n_seg, double dt_outer, void* targets_out, int n_rows, void* stream);
 
-/* Execution (DESIGN.md "K2"): metrics-only fp32 launches run a persistent grid of 8 CTAs x 64 drones per SM at 128
- * registers; when the batch exceeds that capacity the mission is cut into time slices that CTAs pull from an atomic work
- * queue, a drone resting in the carry block between slices (scratch comes from a library-private stream-ordered pool when
- * `carry` is NULL).  One compiled body serves every batch size, so per-rollout results do not depend on B, on index_base
- * or on how a job is sharded over launches and GPUs.  Launches with a state log (log_stride > 0) run one-shot and
- * renormalise the quaternion every tick; metrics-only launches renormalise once per outer period (state_out is unit).
+/* Execution (DESIGN.md "K2"): fp32 launches run a persistent grid of 8 CTAs x 64 drones per SM at 128 registers; when the
+ * batch exceeds that capacity the mission is cut into time slices that CTAs pull from an atomic work queue, a drone
+ * resting in the carry block between slices (scratch comes from a library-private stream-ordered pool when `carry` is
+ * NULL); a state log is written slice by slice into its place.  One compiled body per mode serves every batch size, so
+ * per-rollout results do not depend on B, on index_base or on how a job is sharded over launches and GPUs.  Launches with
+ * a state log (log_stride > 0) renormalise the quaternion every tick, metrics-only launches once per outer period
+ * (state_out is unit either way).  uavb_rollout_f64 runs one-shot.
  *
  * Replaces, for B drones and n_ticks ticks, the loop
  *     trajectory_controller.step(); simulation.step()

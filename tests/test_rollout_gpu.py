@@ -391,3 +391,24 @@ def test_precomputed_set_point_table_is_bit_identical_to_on_the_fly_evaluation(c
                                        table_rows=int(plan.total_rows.item()) + 77)
         c = _fly(cuda, longer, B, n, **mc)
         assert torch.equal(c.metrics, b.metrics) and torch.equal(c.state, b.state)
+
+
+def test_state_log_is_identical_across_slice_counts(cuda, monkeypatch):
+    """A state log written slice by slice lands in the same places with the same bits, for strides that do and do not divide
+    the slice length, and its last sample is the final state."""
+    import torch
+    plan = lab_course_plan(cuda, 3.0)
+    B, n = 700, 2350
+    rng = np.random.default_rng(9)
+    mc = mc_arrays(cuda, B, rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3)))
+    for stride in (1, 7, 50):
+        logs = []
+        for chunks in ("1", "9"):
+            monkeypatch.setenv("UAVB_ROLLOUT_CHUNKS", chunks)
+            r = _fly(cuda, plan, B, n, log_stride=stride, **mc)
+            logs.append(r)
+        monkeypatch.delenv("UAVB_ROLLOUT_CHUNKS")
+        assert logs[0].log.shape == (n // stride, 13, B)
+        assert torch.equal(logs[0].log, logs[1].log) and torch.equal(logs[0].state, logs[1].state) and torch.equal(logs[0].metrics, logs[1].metrics)
+        if n % stride == 0:
+            assert torch.equal(logs[0].log[-1], logs[0].state)

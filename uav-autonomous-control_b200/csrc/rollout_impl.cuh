@@ -1,5 +1,5 @@
 // rollout_impl.cuh -- device side of K2, shared by the translation units that instantiate its kernels
-// (rollout_sliced.cu: metrics-only fp32; rollout_log.cu: fp32 with a state log; rollout_f64.cu: fp64 validation build).
+// (rollout_sliced.cu: metrics-only fp32; rollout_log.cu: fp32 with a state log; rollout_f64.cu: one-shot fp64 validation build).
 //
 // Each thread keeps its drone's 13-state, displacement accumulator, rotor speeds, controller integrator,
 // commands, table cursor and metric accumulators in registers for a whole slice of the mission (hundreds to
@@ -135,9 +135,10 @@ struct Carry {
 // pose; writes the carry block (to_carry) and / or the final outputs (finish).
 // MC: some per-rollout override (mass / inertia / gains / wind) is present; otherwise every vehicle constant is a
 // constant-bank operand.
+// `launch_tick0`: ticks of THIS launch that precede the slice (places the slice's samples in the state log).
 template <class R, bool LOG, bool MC, bool TABLE>
 __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float* s_boxes, long long i, int n_ticks, bool from_carry,
-                                            bool to_carry, bool finish) {
+                                            bool to_carry, bool finish, int launch_tick0 = 0) {
   const uavb_rollout_args& a = p.a;
   const long long B = a.B;
   const bool shared_boxes = a.n_obs > 0 && a.aabb_set == nullptr;
@@ -195,8 +196,8 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
   auto fly = [&](const auto& obst) {
     if constexpr (LOG) {
       GlobalLog<R> lg;
-      lg.out = reinterpret_cast<R*>(a.log_out) + i;
-      lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride;
+      lg.out = reinterpret_cast<R*>(a.log_out) + (size_t)(launch_tick0 / a.log_stride) * 13 * B + i;
+      lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride - launch_tick0 % a.log_stride;
       rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
     } else {
       NoLog lg;
@@ -256,7 +257,7 @@ __device__ __forceinline__ void stage_shared_boxes(const uavb_rollout_args& a, f
   }
 }
 
-// One-shot launch: thread i flies drone i for the whole launch (state-log launches and the fp64 validation build).
+// One-shot launch: thread i flies drone i for the whole launch (the fp64 validation build).
 template <class R, bool LOG, bool MC>
 __global__ void __maxnreg__(kRolloutRegs) rollout_kernel(const __grid_constant__ RolloutDev<R> p) {
   extern __shared__ float s_boxes[];
@@ -272,7 +273,7 @@ __global__ void __maxnreg__(kRolloutRegs) rollout_kernel(const __grid_constant__
   drone_slice<R, LOG, MC, false>(p, s_boxes, i, p.a.n_ticks, p.a.resume != 0, p.a.carry != nullptr, true);   // fp64: always on the fly
 }
 
-// Time-sliced persistent launch (every metrics-only fp32 rollout).  When the batch needs between one and a few waves of
+// Time-sliced persistent launch (every fp32 rollout, with or without a state log).  When the batch needs between one and a few waves of
 // CTAs, a one-shot launch ends with a long tail: every CTA lives for the whole mission, so the last partial wave costs a full
 // mission time at a fraction of the machine.  Here the grid is exactly the resident capacity, the mission is cut into
 // `n_chunks` slices of `chunk_ticks` ticks, and CTAs pull (chunk, group) items from an atomic counter in chunk-major
@@ -294,7 +295,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-template <bool MC, bool TABLE>
+template <bool MC, bool TABLE, bool LOG>
 __global__ void __maxnreg__(kRolloutRegs) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
   extern __shared__ float s_boxes[];
   __shared__ int s_item;
@@ -317,7 +318,7 @@ __global__ void __maxnreg__(kRolloutRegs) rollout_sliced_kernel(const __grid_con
     if (i < p.a.B) {
       const bool last = c == sch.n_chunks - 1;
       const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
-      drone_slice<float, false, MC, TABLE>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last);
+      drone_slice<float, LOG, MC, TABLE>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
     }
     __threadfence();
     __syncthreads();
@@ -328,7 +329,7 @@ __global__ void __maxnreg__(kRolloutRegs) rollout_sliced_kernel(const __grid_con
 
 // Host-side launchers, one per translation unit (kernel templates are instantiated where they are launched).
 void launch_rollout_sliced(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
-void launch_rollout_log_f32(bool mc, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p);
+void launch_rollout_sliced_log(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
 void launch_rollout_f64(bool log, bool mc, int grid, size_t smem, cudaStream_t st, const RolloutDev<double>& p);
 
 }  // namespace uavb

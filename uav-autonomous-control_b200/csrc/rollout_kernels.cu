@@ -127,7 +127,7 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
   p.coeff_cache_offset = -1;
   const bool from_table = a->shared_targets != nullptr && a->mission_seg_begin == nullptr;
-  if (!from_table && sizeof(R) == 4 && a->log_stride == 0) {     // metrics-only fp32 kernels stage the current spline in shared memory
+  if (!from_table && sizeof(R) == 4) {                            // fp32 kernels stage the current spline in shared memory
     smem = (smem + 7) / 8 * 8;
     p.coeff_cache_offset = (int)(smem / 8);
     smem += sizeof(double) * 24 * kRolloutThreads;
@@ -137,14 +137,12 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   const bool log = a->log_stride > 0;
   if constexpr (sizeof(R) == 8) {                      // validation build
     launch_rollout_f64(log, mc_any, grid, smem, st, p);
-  } else if (log) {
-    launch_rollout_log_f32(mc_any, grid, smem, st, p);
   } else {
     int sms = 0;
     rc = sm_count_cached(&sms);
     if (rc) return rc;
-    // Metrics-only fp32 launches ALWAYS run the time-sliced persistent kernel (8 CTAs x 64 drones per SM, 128 registers, no
-    // spills), with a single slice when slicing has nothing to gain.  One compiled body for every batch size keeps
+    // fp32 launches ALWAYS run the time-sliced persistent kernel (8 CTAs x 64 drones per SM, 128 registers), with a single
+    // slice when slicing has nothing to gain; a state log is written slice by slice into its place.  One compiled body for every batch size keeps
     // per-rollout results independent of how a job is sharded (ptxas fuses mul+add differently under different register
     // caps, so differently compiled variants are NOT bit-identical to each other).
     const int slots = sms * kRolloutCtasPerSm;
@@ -175,7 +173,8 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     sch.done = sch.counter + 1;
     sch.n_groups = grid; sch.n_chunks = n_chunks; sch.chunk_ticks = chunk;
     const int pgrid = slots < grid ? slots : grid;
-    launch_rollout_sliced(mc_any, from_table, pgrid, smem, st, p, sch);
+    if (log) launch_rollout_sliced_log(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
+    else launch_rollout_sliced(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
   }
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;

@@ -5,11 +5,11 @@ namespace uavb {
 
 void launch_rollout_sliced(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch) {
   if (table) {
-    if (mc) rollout_sliced_kernel<true, true><<<grid, kRolloutThreads, smem, st>>>(p, sch);
-    else rollout_sliced_kernel<false, true><<<grid, kRolloutThreads, smem, st>>>(p, sch);
+    if (mc) rollout_sliced_kernel<true, true, false><<<grid, kRolloutThreads, smem, st>>>(p, sch);
+    else rollout_sliced_kernel<false, true, false><<<grid, kRolloutThreads, smem, st>>>(p, sch);
   } else {
-    if (mc) rollout_sliced_kernel<true, false><<<grid, kRolloutThreads, smem, st>>>(p, sch);
-    else rollout_sliced_kernel<false, false><<<grid, kRolloutThreads, smem, st>>>(p, sch);
+    if (mc) rollout_sliced_kernel<true, false, false><<<grid, kRolloutThreads, smem, st>>>(p, sch);
+    else rollout_sliced_kernel<false, false, false><<<grid, kRolloutThreads, smem, st>>>(p, sch);
   }
 }
 
