@@ -381,7 +381,7 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(mc_host.numel() * 4 + wp_host.numel() * 8 + 8),
                     "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                     "call": "uavb_fly_mission_host (C ABI, pinned host buffers, synchronous); host wall-clock, max over ranks"},
-            "gpu_launches": 7 * args.steps,        # per step: 2x minsnap_solve, 1x table_meta, 2x set-point table, 1x rollout_sliced, (+1 torch index_copy; other torch glue not counted)
+            "gpu_launches": 6 * args.steps,        # own kernels per step: 2x minsnap_solve, table_meta, target_rows + target_heading, rollout_sliced (torch glue not counted)
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r01_ncu_rollout_v7.md)",
                          "kernel": "rollout_sliced_kernel<MC,8>", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,
