@@ -3,7 +3,7 @@
 // so the fp32 error budget can be explored in the GPU-less build container before GPU
 // time is spent.  Host float arithmetic is not bit-identical to the device (FMA contraction, rsqrt,
 // __fdividef differ), so this only bounds the error statistically; the parity tests run on the GPU.
-//   g++ -O2 -ffp-contract=fast -march=native -I uav-autonomous-control_b200/csrc tools/host_probe.cpp -o /tmp/host_probe
+//   g++ -O2 -ffp-contract=fast -march=native -I uav-autonomous-control_b200/csrc tests/devtools/host_probe.cpp -o /tmp/host_probe
 //   /tmp/host_probe mission.bin out.bin [f32|f64]
 #include <cstdio>
 #include <cstdlib>

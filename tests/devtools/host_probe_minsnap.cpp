@@ -1,6 +1,6 @@
 // DEVELOPMENT PROBE (not product, never loaded by the package): host build of csrc/minsnap_core.cuh so
 // the K1 arithmetic can be compared with tests/golden/planning.npz in the GPU-less build container.
-//   g++ -O2 -shared -fPIC -I uav-autonomous-control_b200/csrc tools/host_probe_minsnap.cpp -o /tmp/libprobe_minsnap.so
+//   g++ -O2 -shared -fPIC -I uav-autonomous-control_b200/csrc tests/devtools/host_probe_minsnap.cpp -o /tmp/libprobe_minsnap.so
 #include "minsnap_core.cuh"
 using namespace uavb;
 template <int MAXS> static int run(const double* w, double vel, int S, double factor, double* c, double* t) {

@@ -5,7 +5,7 @@ NOT RUNNABLE IN THE BUILD CONTAINER OR ON THE GPU BOX (MuJoCo 3.x is absent ther
 has never been executed by the authors of this repository; it exists because parity of oracle/freebody.py with MuJoCo is
 UNPINNED (DESIGN.md "Oracle") and only a machine with MuJoCo can pin it.
 
-    python tools/mujoco_crosscheck.py --reference /path/to/UAV-Autonomous-control [--velocity 2.0]
+    python tests/devtools/mujoco_crosscheck.py --reference /path/to/UAV-Autonomous-control [--velocity 2.0]
 
 It runs the reference's own headless loop (tests/integration/test_mujoco_trajectory_tracking.py:11-36: MujocoSimulation +
 TrajectoryController + CascadedController + Quad), records quad.X after every outer period, flies the same table with the
@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -1,7 +1,7 @@
-"""Drive tools/host_probe (development numerics probe) against tests/golden closed-loop logs."""
+"""Drive tests/devtools/host_probe (development numerics probe) against tests/golden closed-loop logs."""
 import struct, subprocess, sys
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repo root
 from oracle import minsnap_np as M
 
 def mission_blob(wp, v, dt=0.01, method="solve"):
