@@ -303,10 +303,13 @@ template <class R> UAVB_HD void allocate_forces(const VehU<R>& u, R coll, const 
     // no rotor limit binds: every ratio of quad.py:116-119 is >= 1, the scale is 1 and the final clip is the identity
     f[0] = coll + m0; f[1] = coll + m1; f[2] = coll + m2; f[3] = coll + m3;
   } else {
-    const R l0 = (m0 > R(0)) ? M::div(room_hi, m0) : ((m0 < R(0)) ? M::div(room_lo, m0) : R(1));
-    const R l1 = (m1 > R(0)) ? M::div(room_hi, m1) : ((m1 < R(0)) ? M::div(room_lo, m1) : R(1));
-    const R l2 = (m2 > R(0)) ? M::div(room_hi, m2) : ((m2 < R(0)) ? M::div(room_lo, m2) : R(1));
-    const R l3 = (m3 > R(0)) ? M::div(room_hi, m3) : ((m3 < R(0)) ? M::div(room_lo, m3) : R(1));
+    // ratio of quad.py:116-119 per rotor, as straight-line selects: a few lanes of a warp saturating must not cost the
+    // whole warp four branch diamonds.  (m < 0 || m > 0) is the ordered "not zero": a NaN moment keeps ratio 1 as before.
+    auto ratio = [&](R m) {
+      const R l = M::div((m > R(0)) ? room_hi : room_lo, m);
+      return (m < R(0) || m > R(0)) ? l : R(1);
+    };
+    const R l0 = ratio(m0), l1 = ratio(m1), l2 = ratio(m2), l3 = ratio(m3);
     const R s = clampr<R>(M::fmin(M::fmin(l0, l1), M::fmin(l2, l3)), R(0), R(1));
     f[0] = clampr<R>(M::fma(s, m0, coll), u.fmin, u.fmax);
     f[1] = clampr<R>(M::fma(s, m1, coll), u.fmin, u.fmax);

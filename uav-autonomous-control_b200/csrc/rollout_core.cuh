@@ -179,6 +179,12 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
       const R reach = R(1.01) * (speed + v.acc_max * T) * T + R(1e-4);
       watch = obst.within((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz), reach);
     }
+#if defined(__CUDA_ARCH__)
+    // one decision per warp: with per-rollout missions / obstacle sets the lanes disagree, and a divergent warp would run the
+    // whole 1 kHz stretch twice (once per side).  Watching is always correct (the per-tick test is the exact one), so any lane
+    // that needs it switches it on for its warp.
+    if (OBST::kAny) watch = __any_sync(__activemask(), watch);
+#endif
     // the stretch is specialised on the two warp-uniform switches (watch, lag): the 1 kHz body then carries no selects for them
     auto stretch = [&](auto watch_c, auto lag_c) {
       constexpr bool kWatch = decltype(watch_c)::value, kLag = decltype(lag_c)::value;
