@@ -118,6 +118,7 @@ template <class R> struct VehU {
   R kf, inv_kf, arm_kf, kappa_kf;                  // arm*kf, kappa*kf: torque per unit of summed w^2
   R inv_arm4, inv_kappa4;                          // 1/(4 arm), 1/(4 kappa): mixer division by 4 folded in (quad.py:112)
   R fmin, fmax, fmin4, fmax4, a_rise, a_fall;      // a_* = 1 - exp(-dt/tau) (quad.py:102)
+  R w2min, w2max, quarter_inv_kf;                  // rotor units (see "rotor units" below): fmin/kf, fmax/kf, 1/(4 kf)
   R max_ascent, max_descent, max_speed_xy, max_acc_xy, max_tilt, integral_limit;
 };
 
@@ -128,6 +129,10 @@ template <class R> struct VehP {
   R dIx, dIy, dIz;                                 // Iz-Iy, Ix-Iz, Iy-Ix (gyroscopic term, diagonal inertia)
   R Ikp_p, Ikp_q, Ikp_r;                           // I * kp of the body-rate loop (controller.py:128)
   R dt_invIx, dt_invIy, dt_invIz;                  // dt / I
+  // the same three groups in rotor units (the persistent rollout's 1 kHz body; the SI ones serve the stage kernels)
+  R Gx, Gy, Gz;                                    // dIx/(4 arm kf), dIy/(4 arm kf), -dIz/(4 kappa kf)
+  R Jp, Jq, Jr;                                    // Ikp_p/(4 arm kf), Ikp_q/(4 arm kf), -Ikp_r/(4 kappa kf)
+  R Wx, Wy, Wz;                                    // dt arm kf/Ix, dt arm kf/Iy, dt kappa kf/Iz
   R dvx, dvy, dvz;                                 // dt * (wind/m + g e_z): velocity gained per tick without thrust
   // 100 Hz outer loop
   R mass, kp_xy, kd_xy, kp_z, kd_z, ki_z, kp_roll, kp_pitch, kp_yaw;
@@ -144,7 +149,7 @@ template <class R> struct Drone {
   R om0, om1, om2, om3;  // rotor speeds (quad.py:85)
   R integral;          // altitude integrator (controller.py:20)
   R thrust_cmd;        // main.py:26
-  R coll;              // clip(thrust_cmd, 4 fmin, 4 fmax) / 4 (quad.py:107,113), refreshed with thrust_cmd
+  R coll;              // clip(thrust_cmd, 4 fmin, 4 fmax) / (4 kf) (quad.py:107,113) in rotor units, refreshed with thrust_cmd
   R pc, qc, rc;        // pqr_cmd (main.py:27)
   R zbx, zby, zbz;     // thrust direction MuJoCo last computed (stale body z axis)
 };
@@ -166,7 +171,7 @@ struct TargetRow {
 
 template <class R> UAVB_HD void set_thrust_cmd(Drone<R>& d, const VehU<R>& u, R c) {
   d.thrust_cmd = c;
-  d.coll = R(0.25) * clampr<R>(c, u.fmin4, u.fmax4);
+  d.coll = u.quarter_inv_kf * clampr<R>(c, u.fmin4, u.fmax4);
 }
 
 // Fold the displacement into the fp64 position (done at outer-period boundaries).
@@ -290,59 +295,56 @@ template <class R> UAVB_HD void body_rate_moment(const Drone<R>& d, const VehP<R
   Mo[2] = M::fma(v.Ikp_r, d.rc - d.wz, g[2]);
 }
 
-// Quad._allocate_rotor_forces (quad.py:105-122): mixer rows (+,+,+) (-,+,-) (-,-,+) (+,-,-) on [p_bar q_bar r_bar] / 4;
-// `coll` = clip(thrust_cmd, 4 fmin, 4 fmax) / 4.
-template <class R> UAVB_HD void allocate_forces(const VehU<R>& u, R coll, const R* Mo, R* f) {
+// Mixer rows (+,+,+) (-,+,-) (-,-,+) (+,-,-) on the scaled moments (p_bar, q_bar, r_bar)/4 plus the rotor limits of
+// quad.py:114-121.  Unit-agnostic: `coll`, `lo`, `hi` and the result share one unit (N in the stage form, rotor units in the
+// persistent rollout).
+template <class R> UAVB_HD void mix_and_limit(R pb, R qb, R rb, R coll, R lo, R hi, R* f) {
   typedef Math<R> M;
-  const R pb = Mo[0] * u.inv_arm4, qb = Mo[1] * u.inv_arm4, rb = -Mo[2] * u.inv_kappa4;
   const R s1 = pb + qb, s2 = pb - qb;
   const R m0 = s1 + rb, m1 = -(s2 + rb), m2 = rb - s1, m3 = s2 - rb;
-  const R room_hi = u.fmax - coll, room_lo = u.fmin - coll;
+  const R room_hi = hi - coll, room_lo = lo - coll;
   const R m_hi = M::fmax(M::fmax(m0, m1), M::fmax(m2, m3)), m_lo = M::fmin(M::fmin(m0, m1), M::fmin(m2, m3));
   if (m_hi <= room_hi && m_lo >= room_lo) {
     // no rotor limit binds: every ratio of quad.py:116-119 is >= 1, the scale is 1 and the final clip is the identity
     f[0] = coll + m0; f[1] = coll + m1; f[2] = coll + m2; f[3] = coll + m3;
   } else {
     // ratio of quad.py:116-119 per rotor, as straight-line selects: a few lanes of a warp saturating must not cost the
-    // whole warp four branch diamonds.  (m < 0 || m > 0) is the ordered "not zero": a NaN moment keeps ratio 1 as before.
+    // whole warp four branch diamonds.  (m < 0 || m > 0) is the ordered "not zero": a NaN moment keeps ratio 1.
     auto ratio = [&](R m) {
       const R l = M::div((m > R(0)) ? room_hi : room_lo, m);
       return (m < R(0) || m > R(0)) ? l : R(1);
     };
     const R l0 = ratio(m0), l1 = ratio(m1), l2 = ratio(m2), l3 = ratio(m3);
     const R s = clampr<R>(M::fmin(M::fmin(l0, l1), M::fmin(l2, l3)), R(0), R(1));
-    f[0] = clampr<R>(M::fma(s, m0, coll), u.fmin, u.fmax);
-    f[1] = clampr<R>(M::fma(s, m1, coll), u.fmin, u.fmax);
-    f[2] = clampr<R>(M::fma(s, m2, coll), u.fmin, u.fmax);
-    f[3] = clampr<R>(M::fma(s, m3, coll), u.fmin, u.fmax);
+    f[0] = clampr<R>(M::fma(s, m0, coll), lo, hi);
+    f[1] = clampr<R>(M::fma(s, m1, coll), lo, hi);
+    f[2] = clampr<R>(M::fma(s, m2, coll), lo, hi);
+    f[3] = clampr<R>(M::fma(s, m3, coll), lo, hi);
   }
 }
 
-// Quad.set_propeller_speed after the allocation (quad.py:95-103): w_cmd = sqrt(f / kf), asymmetric first-order lag.
-template <class R> UAVB_HD void motor_lag(Drone<R>& d, const VehU<R>& u, const R* f, R* cmd_out) {
+// Quad._allocate_rotor_forces (quad.py:105-122) in newtons; `coll` = clip(thrust_cmd, 4 fmin, 4 fmax) / 4.
+template <class R> UAVB_HD void allocate_forces(const VehU<R>& u, R coll, const R* Mo, R* f) {
+  mix_and_limit<R>(Mo[0] * u.inv_arm4, Mo[1] * u.inv_arm4, -Mo[2] * u.inv_kappa4, coll, u.fmin, u.fmax, f);
+}
+
+// Asymmetric first-order lag of the rotor speeds toward their commands (quad.py:98-103).
+template <class R> UAVB_HD void lag_toward(Drone<R>& d, const VehU<R>& u, R c0, R c1, R c2, R c3) {
   typedef Math<R> M;
-  const R c0 = M::sqrt_fast(f[0] * u.inv_kf), c1 = M::sqrt_fast(f[1] * u.inv_kf), c2 = M::sqrt_fast(f[2] * u.inv_kf), c3 = M::sqrt_fast(f[3] * u.inv_kf);
   d.om0 = M::fma((c0 > d.om0) ? u.a_rise : u.a_fall, c0 - d.om0, d.om0);
   d.om1 = M::fma((c1 > d.om1) ? u.a_rise : u.a_fall, c1 - d.om1, d.om1);
   d.om2 = M::fma((c2 > d.om2) ? u.a_rise : u.a_fall, c2 - d.om2, d.om2);
   d.om3 = M::fma((c3 > d.om3) ? u.a_rise : u.a_fall, c3 - d.om3, d.om3);
+}
+
+// Quad.set_propeller_speed after the allocation (quad.py:95-103): w_cmd = sqrt(f / kf), then the lag.
+template <class R> UAVB_HD void motor_lag(Drone<R>& d, const VehU<R>& u, const R* f, R* cmd_out) {
+  typedef Math<R> M;
+  const R c0 = M::sqrt_fast(f[0] * u.inv_kf), c1 = M::sqrt_fast(f[1] * u.inv_kf), c2 = M::sqrt_fast(f[2] * u.inv_kf), c3 = M::sqrt_fast(f[3] * u.inv_kf);
+  lag_toward<R>(d, u, c0, c1, c2, c3);
   if (cmd_out) { cmd_out[0] = c0; cmd_out[1] = c1; cmd_out[2] = c2; cmd_out[3] = c3; }
 }
 
-// Body-rate controller + allocation + motor lag; returns the gyroscopic term of the CURRENT state.
-template <class R>
-UAVB_HD void inner_control(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R* gx, R* gy, R* gz, R* moment_out, R* forces_out) {
-  R g[3], Mo[3], f[4];
-  body_rate_moment<R>(d, v, g, Mo);
-  *gx = g[0]; *gy = g[1]; *gz = g[2];
-  allocate_forces<R>(u, d.coll, Mo, f);
-  motor_lag<R>(d, u, f, nullptr);
-  if (moment_out) { moment_out[0] = Mo[0]; moment_out[1] = Mo[1]; moment_out[2] = Mo[2]; }
-  if (forces_out) { forces_out[0] = f[0]; forces_out[1] = f[1]; forces_out[2] = f[2]; forces_out[3] = f[3]; }
-}
-
-// Inner loop, part 2: rotor wrench with the given thrust axis + free-body semi-implicit Euler step
-// (mujoco_sim.py:232-255 + MuJoCo Euler; oracle/freebody.py states the same equations in fp64).
 // 1.5 - 0.5 |q|^2 = 1/|q| + O((|q|^2 - 1)^2): renormalisation of a quaternion whose norm is 1 up to accumulated rounding.
 template <class R> UAVB_HD void renormalise_q(Drone<R>& d) {
   typedef Math<R> M;
@@ -351,25 +353,29 @@ template <class R> UAVB_HD void renormalise_q(Drone<R>& d) {
   d.q0 *= rn; d.q1 *= rn; d.q2 *= rn; d.q3 *= rn;
 }
 
+// Sums of squared rotor speeds behind the wrench (mujoco_sim.py:235-247, rotor layout lab_course.xml:116-119):
+//   tot = s0+s1+s2+s3,  tx = (s0+s3)-(s1+s2),  ty = (s0+s1)-(s2+s3),  tzn = -((s1+s3)-(s0+s2)),  s_i = w_i^2
+// from one butterfly (8 additions).
+template <class R> UAVB_HD void rotor_sums(const Drone<R>& d, R* tot, R* tx, R* ty, R* tzn) {
+  const R s0 = d.om0 * d.om0, s1 = d.om1 * d.om1, s2 = d.om2 * d.om2, s3 = d.om3 * d.om3;
+  const R a = s0 + s1, b = s2 + s3, c = s0 - s1, e = s2 - s3;
+  *tot = a + b; *ty = a - b; *tx = c - e; *tzn = c + e;
+}
+
 // NORM: renormalise the quaternion in this step (mujoco_sim.py:36-42 does so every tick).  The persistent rollout passes
 // false and renormalises once per outer period instead: q * dq of a unit q and the unit dq below stays unit up to
 // ~6e-8 per tick, the drift over 10 ticks (< 1e-6 in |q|^2) scales the thrust axis and R by the same factor, far inside
 // the fp32 noise of the step, and the outer loop always sees a freshly normalised q.
+// Semi-implicit Euler with the velocity gain `dvt` along the thrust axis (zx, zy, zz) and the new body rates (nwx, nwy, nwz).
 template <class R, bool NORM = true>
-UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx, R zy, R zz, R gx, R gy, R gz) {
+UAVB_HD void integrate(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx, R zy, R zz, R dvt, R nwx, R nwy, R nwz) {
   typedef Math<R> M;
-  // f_i = kf w_i^2; collective and body torques from the sums of squares (mujoco_sim.py:235-247)
-  const R s0 = d.om0 * d.om0, s1 = d.om1 * d.om1, s2 = d.om2 * d.om2, s3 = d.om3 * d.om3;
-  const R s03 = s0 + s3, s12 = s1 + s2, s01 = s0 + s1, s23 = s2 + s3, s13 = s1 + s3, s02 = s0 + s2;
-  const R dvt = -(s01 + s23) * v.kf_dt_over_m;                 // dt * specific thrust along -z body
   // velocities first (semi-implicit Euler)
   // (the per-tick increment is formed first and added once: near hover thrust and gravity cancel inside it)
   d.vx += M::fma(zx, dvt, v.dvx);
   d.vy += M::fma(zy, dvt, v.dvy);
   d.vz += M::fma(zz, dvt, v.dvz);
-  d.wx = M::fma(v.dt_invIx, M::fma(u.arm_kf, s03 - s12, -gx), d.wx);
-  d.wy = M::fma(v.dt_invIy, M::fma(u.arm_kf, s01 - s23, -gy), d.wy);
-  d.wz = M::fma(v.dt_invIz, M::fma(u.kappa_kf, s13 - s02, -gz), d.wz);
+  d.wx = nwx; d.wy = nwy; d.wz = nwz;
   // positions with the new velocity
   d.dx = M::fma(u.dt, d.vx, d.dx);
   d.dy = M::fma(u.dt, d.vy, d.dy);
@@ -414,16 +420,47 @@ UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx,
   }
 }
 
-// One full inner tick in the reference order (SURVEY 8(a) "exact tick order"): body-rate loop,
-// allocation, motor lag, wrench with the stale (lag=1) or fresh (lag=0) thrust axis, integration.
+// Inner loop, part 2 in SI units (stage kernels): rotor wrench with the given thrust axis + free-body step
+// (mujoco_sim.py:232-255 + MuJoCo Euler; oracle/freebody.py states the same equations in fp64).
+template <class R, bool NORM = true>
+UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx, R zy, R zz, R gx, R gy, R gz) {
+  typedef Math<R> M;
+  R tot, tx, ty, tzn;
+  rotor_sums<R>(d, &tot, &tx, &ty, &tzn);
+  const R dvt = -tot * v.kf_dt_over_m;                         // dt * specific thrust along -z body
+  integrate<R, NORM>(d, u, v, zx, zy, zz, dvt,
+                     M::fma(v.dt_invIx, M::fma(u.arm_kf, tx, -gx), d.wx),
+                     M::fma(v.dt_invIy, M::fma(u.arm_kf, ty, -gy), d.wy),
+                     M::fma(v.dt_invIz, M::fma(-u.kappa_kf, tzn, -gz), d.wz));
+}
+
+// One full inner tick in the reference order (SURVEY 8(a) "exact tick order"): body-rate loop (controller.py:115-130),
+// allocation (quad.py:105-122), motor lag (quad.py:95-103), wrench with the stale (lag=1) or fresh (lag=0) thrust axis
+// (mujoco_sim.py:232-255), integration.
+//
+// Rotor units.  Everything between the body-rate error and the rotor speeds is linear, so the tick works with moments
+// divided by (4 arm kf) -- (4 kappa kf) and a flipped sign for yaw -- and forces divided by kf, i.e. directly with squared
+// rotor speeds: the mixer inputs need no scaling, the speed commands are sqrt() of the limited mixer outputs, and the
+// gyroscopic term re-enters the rate update as -4 g' next to the rotor sums.  Same equations as body_rate_moment ->
+// allocate_forces -> motor_lag -> physics_step with the constant factors folded into VehP (Gx.., Jp.., Wx..) once per
+// rollout; 7 multiplications fewer per tick.
 template <class R, bool NORM = true> UAVB_HD void inner_tick(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, int thrust_frame_lag) {
-  R gx, gy, gz;
-  inner_control<R>(d, u, v, &gx, &gy, &gz, nullptr, nullptr);
+  typedef Math<R> M;
+  const R gx = v.Gx * (d.wy * d.wz), gy = v.Gy * (d.wz * d.wx), gz = v.Gz * (d.wx * d.wy);
+  R w2[4];
+  mix_and_limit<R>(M::fma(v.Jp, d.pc - d.wx, gx), M::fma(v.Jq, d.qc - d.wy, gy), M::fma(v.Jr, d.rc - d.wz, gz),
+                   d.coll, u.w2min, u.w2max, w2);
+  lag_toward<R>(d, u, M::sqrt_fast(w2[0]), M::sqrt_fast(w2[1]), M::sqrt_fast(w2[2]), M::sqrt_fast(w2[3]));
   R zx, zy, zz;
   body_z<R>(d, &zx, &zy, &zz);                               // axis of X_k: what mj_step's forward pass will compute
   const R ux = thrust_frame_lag ? d.zbx : zx, uy = thrust_frame_lag ? d.zby : zy, uz = thrust_frame_lag ? d.zbz : zz;
   d.zbx = zx; d.zby = zy; d.zbz = zz;
-  physics_step<R, NORM>(d, u, v, ux, uy, uz, gx, gy, gz);
+  R tot, tx, ty, tzn;
+  rotor_sums<R>(d, &tot, &tx, &ty, &tzn);
+  integrate<R, NORM>(d, u, v, ux, uy, uz, -tot * v.kf_dt_over_m,
+                     M::fma(v.Wx, M::fma(R(-4), gx, tx), d.wx),
+                     M::fma(v.Wy, M::fma(R(-4), gy, ty), d.wy),
+                     M::fma(-v.Wz, M::fma(R(-4), gz, tzn), d.wz));
 }
 
 // ---------------------------------------------------------------------------------------------

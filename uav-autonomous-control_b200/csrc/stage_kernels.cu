@@ -129,12 +129,11 @@ __global__ void __launch_bounds__(128) stage_kernel(const __grid_constant__ Stag
       break;
     }
     case UAVB_STAGE_INNER: {
-      set_thrust_cmd<float>(d, u, a.thrust[i]);
       d.pc = a.pqr_cmd[0 * B + i]; d.qc = a.pqr_cmd[1 * B + i]; d.rc = a.pqr_cmd[2 * B + i];
       d.om0 = a.omega[0 * B + i]; d.om1 = a.omega[1 * B + i]; d.om2 = a.omega[2 * B + i]; d.om3 = a.omega[3 * B + i];
       float g[3], mom[3], f[4], cmd[4];
       body_rate_moment<float>(d, v, g, mom);
-      allocate_forces<float>(u, d.coll, mom, f);
+      allocate_forces<float>(u, 0.25f * clampr<float>(a.thrust[i], u.fmin4, u.fmax4), mom, f);
       motor_lag<float>(d, u, f, cmd);
       if (a.moment) { a.moment[0 * B + i] = mom[0]; a.moment[1 * B + i] = mom[1]; a.moment[2 * B + i] = mom[2]; }
       if (a.forces) { a.forces[0 * B + i] = f[0]; a.forces[1 * B + i] = f[1]; a.forces[2 * B + i] = f[2]; a.forces[3 * B + i] = f[3]; }

@@ -46,6 +46,7 @@ template <class R> inline void make_vehu(VehU<R>& v, const uavb_vehicle& u, doub
   v.kf = (R)u.kf; v.inv_kf = (R)(1.0 / u.kf); v.arm_kf = (R)(u.arm * u.kf); v.kappa_kf = (R)(u.kappa * u.kf);
   v.inv_arm4 = (R)(0.25 / u.arm); v.inv_kappa4 = (R)(0.25 / u.kappa);
   v.fmin = (R)u.min_thrust; v.fmax = (R)u.max_thrust; v.fmin4 = (R)(4.0 * u.min_thrust); v.fmax4 = (R)(4.0 * u.max_thrust);
+  v.w2min = (R)(u.min_thrust / u.kf); v.w2max = (R)(u.max_thrust / u.kf); v.quarter_inv_kf = (R)(0.25 / u.kf);
   v.a_rise = (R)(1.0 - exp(-u.dt / u.tau_rise)); v.a_fall = (R)(1.0 - exp(-u.dt / u.tau_fall));
   v.max_ascent = (R)u.max_ascent; v.max_descent = (R)u.max_descent; v.max_speed_xy = (R)u.max_speed_xy;
   v.max_acc_xy = (R)u.max_horiz_accel; v.max_tilt = (R)u.max_tilt; v.integral_limit = (R)u.integral_limit;
@@ -58,6 +59,10 @@ template <class R> UAVB_HD void make_vehp(VehP<R>& v, const uavb_vehicle& u, con
   v.dIx = (R)(Iz - Iy); v.dIy = (R)(Ix - Iz); v.dIz = (R)(Iy - Ix);
   v.Ikp_p = (R)(Ix * o.gains[8]); v.Ikp_q = (R)(Iy * o.gains[9]); v.Ikp_r = (R)(Iz * o.gains[10]);
   v.dt_invIx = (R)(u.dt / Ix); v.dt_invIy = (R)(u.dt / Iy); v.dt_invIz = (R)(u.dt / Iz);
+  const double ia = 1.0 / (4.0 * u.arm * u.kf), ik = 1.0 / (4.0 * u.kappa * u.kf);   // rotor units, see inner_tick
+  v.Gx = (R)((Iz - Iy) * ia); v.Gy = (R)((Ix - Iz) * ia); v.Gz = (R)(-(Iy - Ix) * ik);
+  v.Jp = (R)(Ix * o.gains[8] * ia); v.Jq = (R)(Iy * o.gains[9] * ia); v.Jr = (R)(-Iz * o.gains[10] * ik);
+  v.Wx = (R)(u.dt * u.arm * u.kf / Ix); v.Wy = (R)(u.dt * u.arm * u.kf / Iy); v.Wz = (R)(u.dt * u.kappa * u.kf / Iz);
   v.dvx = (R)(u.dt * o.wind[0] / m); v.dvy = (R)(u.dt * o.wind[1] / m); v.dvz = (R)(u.dt * (o.wind[2] / m + u.g));
   v.mass = (R)m;
   v.kp_xy = (R)o.gains[0]; v.kd_xy = (R)o.gains[1]; v.kp_z = (R)o.gains[2]; v.kd_z = (R)o.gains[3]; v.ki_z = (R)o.gains[4];
