@@ -133,6 +133,7 @@ template <class R> struct VehP {
   R Gx, Gy, Gz;                                    // dIx/(4 arm kf), dIy/(4 arm kf), -dIz/(4 kappa kf)
   R Jp, Jq, Jr;                                    // Ikp_p/(4 arm kf), Ikp_q/(4 arm kf), -Ikp_r/(4 kappa kf)
   R Wx, Wy, Wz;                                    // dt arm kf/Ix, dt arm kf/Iy, dt kappa kf/Iz
+  R Kx, Ky, Kz;                                    // -dt dIx/Ix, -dt dIy/Iy, -dt dIz/Iz: rate gained per unit of wy wz, wz wx, wx wy
   R dvx, dvy, dvz;                                 // dt * (wind/m + g e_z): velocity gained per tick without thrust
   // 100 Hz outer loop
   R mass, kp_xy, kd_xy, kp_z, kd_z, ki_z, kp_roll, kp_pitch, kp_yaw;
@@ -151,6 +152,7 @@ template <class R> struct Drone {
   R thrust_cmd;        // main.py:26
   R coll;              // clip(thrust_cmd, 4 fmin, 4 fmax) / (4 kf) (quad.py:107,113) in rotor units, refreshed with thrust_cmd
   R pc, qc, rc;        // pqr_cmd (main.py:27)
+  R cp, cq, cr;        // the same in rotor units (Jp pc, Jq qc, Jr rc): what the persistent rollout carries between ticks
   R zbx, zby, zbz;     // thrust direction MuJoCo last computed (stale body z axis)
 };
 
@@ -280,6 +282,7 @@ template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, cons
   roll_pitch_cmd<R>(v, bx, by, r, inv_R22, &p_c, &q_c);
   d.pc = p_c; d.qc = q_c;
   d.rc = yaw_rate_cmd<R>(v, d.q0, d.q1, d.q2, d.q3, t.yc, t.ys, q_c);
+  d.cp = v.Jp * d.pc; d.cq = v.Jq * d.qc; d.cr = v.Jr * d.rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -302,12 +305,14 @@ template <class R> UAVB_HD void mix_and_limit(R pb, R qb, R rb, R coll, R lo, R 
   typedef Math<R> M;
   const R s1 = pb + qb, s2 = pb - qb;
   const R m0 = s1 + rb, m1 = -(s2 + rb), m2 = rb - s1, m3 = s2 - rb;
-  const R room_hi = hi - coll, room_lo = lo - coll;
-  const R m_hi = M::fmax(M::fmax(m0, m1), M::fmax(m2, m3)), m_lo = M::fmin(M::fmin(m0, m1), M::fmin(m2, m3));
-  if (m_hi <= room_hi && m_lo >= room_lo) {
-    // no rotor limit binds: every ratio of quad.py:116-119 is >= 1, the scale is 1 and the final clip is the identity
-    f[0] = coll + m0; f[1] = coll + m1; f[2] = coll + m2; f[3] = coll + m3;
+  // unclipped outputs first: when all four lie inside the limits no ratio of quad.py:116-119 is below 1, the scale is 1
+  // and the final clip is the identity
+  const R f0 = coll + m0, f1 = coll + m1, f2 = coll + m2, f3 = coll + m3;
+  const R f_hi = M::fmax(M::fmax(f0, f1), M::fmax(f2, f3)), f_lo = M::fmin(M::fmin(f0, f1), M::fmin(f2, f3));
+  if (f_hi <= hi && f_lo >= lo) {
+    f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3;
   } else {
+    const R room_hi = hi - coll, room_lo = lo - coll;
     // ratio of quad.py:116-119 per rotor, as straight-line selects: a few lanes of a warp saturating must not cost the
     // whole warp four branch diamonds.  (m < 0 || m > 0) is the ordered "not zero": a NaN moment keeps ratio 1.
     auto ratio = [&](R m) {
@@ -441,15 +446,17 @@ UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx,
 // Rotor units.  Everything between the body-rate error and the rotor speeds is linear, so the tick works with moments
 // divided by (4 arm kf) -- (4 kappa kf) and a flipped sign for yaw -- and forces divided by kf, i.e. directly with squared
 // rotor speeds: the mixer inputs need no scaling, the speed commands are sqrt() of the limited mixer outputs, and the
-// gyroscopic term re-enters the rate update as -4 g' next to the rotor sums.  Same equations as body_rate_moment ->
+// gyroscopic products re-enter the rate update with their own constants K.  Same equations as body_rate_moment ->
 // allocate_forces -> motor_lag -> physics_step with the constant factors folded into VehP (Gx.., Jp.., Wx..) once per
-// rollout; 7 multiplications fewer per tick.
+// rollout.
 template <class R, bool NORM = true> UAVB_HD void inner_tick(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, int thrust_frame_lag) {
   typedef Math<R> M;
-  const R gx = v.Gx * (d.wy * d.wz), gy = v.Gy * (d.wz * d.wx), gz = v.Gz * (d.wx * d.wy);
+  // gyroscopic products; M' = J (cmd - w) + G (w x w) is formed as (J cmd + G prod) - J w with J cmd carried from the
+  // outer loop, and the products re-enter the rate update through K
+  const R yz = d.wy * d.wz, zx_ = d.wz * d.wx, xy = d.wx * d.wy;
   R w2[4];
-  mix_and_limit<R>(M::fma(v.Jp, d.pc - d.wx, gx), M::fma(v.Jq, d.qc - d.wy, gy), M::fma(v.Jr, d.rc - d.wz, gz),
-                   d.coll, u.w2min, u.w2max, w2);
+  mix_and_limit<R>(M::fma(-v.Jp, d.wx, M::fma(v.Gx, yz, d.cp)), M::fma(-v.Jq, d.wy, M::fma(v.Gy, zx_, d.cq)),
+                   M::fma(-v.Jr, d.wz, M::fma(v.Gz, xy, d.cr)), d.coll, u.w2min, u.w2max, w2);
   lag_toward<R>(d, u, M::sqrt_fast(w2[0]), M::sqrt_fast(w2[1]), M::sqrt_fast(w2[2]), M::sqrt_fast(w2[3]));
   R zx, zy, zz;
   body_z<R>(d, &zx, &zy, &zz);                               // axis of X_k: what mj_step's forward pass will compute
@@ -458,9 +465,9 @@ template <class R, bool NORM = true> UAVB_HD void inner_tick(Drone<R>& d, const 
   R tot, tx, ty, tzn;
   rotor_sums<R>(d, &tot, &tx, &ty, &tzn);
   integrate<R, NORM>(d, u, v, ux, uy, uz, -tot * v.kf_dt_over_m,
-                     M::fma(v.Wx, M::fma(R(-4), gx, tx), d.wx),
-                     M::fma(v.Wy, M::fma(R(-4), gy, ty), d.wy),
-                     M::fma(-v.Wz, M::fma(R(-4), gz, tzn), d.wz));
+                     M::fma(v.Wx, tx, M::fma(v.Kx, yz, d.wx)),
+                     M::fma(v.Wy, ty, M::fma(v.Ky, zx_, d.wy)),
+                     M::fma(-v.Wz, tzn, M::fma(v.Kz, xy, d.wz)));
 }
 
 // ---------------------------------------------------------------------------------------------

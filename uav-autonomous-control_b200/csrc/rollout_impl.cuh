@@ -106,7 +106,7 @@ struct Carry {
     w(6) = d.q0; w(7) = d.q1; w(8) = d.q2; w(9) = d.q3;
     w(10) = d.vx; w(11) = d.vy; w(12) = d.vz; w(13) = d.wx; w(14) = d.wy; w(15) = d.wz;
     w(16) = d.om0; w(17) = d.om1; w(18) = d.om2; w(19) = d.om3;
-    w(20) = d.integral; w(21) = d.thrust_cmd; w(22) = d.pc; w(23) = d.qc; w(24) = d.rc;
+    w(20) = d.integral; w(21) = d.thrust_cmd; w(22) = d.cp; w(23) = d.cq; w(24) = d.cr;   // body-rate commands in rotor units
     w(25) = d.zbx; w(26) = d.zby; w(27) = d.zbz; w(28) = c.hx;
     w(29) = i2f(c.seg); w(30) = i2f(c.row); w(31) = i2f(c.phase);
     put64(32, c.tx); put64(34, c.ty); put64(36, c.tz);
@@ -120,7 +120,7 @@ struct Carry {
     d.q0 = w(6); d.q1 = w(7); d.q2 = w(8); d.q3 = w(9);
     d.vx = w(10); d.vy = w(11); d.vz = w(12); d.wx = w(13); d.wy = w(14); d.wz = w(15);
     d.om0 = w(16); d.om1 = w(17); d.om2 = w(18); d.om3 = w(19);
-    d.integral = w(20); set_thrust_cmd<float>(d, u, w(21)); d.pc = w(22); d.qc = w(23); d.rc = w(24);
+    d.integral = w(20); set_thrust_cmd<float>(d, u, w(21)); d.cp = w(22); d.cq = w(23); d.cr = w(24);
     d.zbx = w(25); d.zby = w(26); d.zbz = w(27); c.hx = w(28);
     c.seg = f2i(w(29)); c.row = f2i(w(30)); c.phase = f2i(w(31)); c.cached_seg = -1;
     c.tx = get64(32); c.ty = get64(34); c.tz = get64(36);

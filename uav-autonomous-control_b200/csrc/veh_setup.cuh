@@ -63,6 +63,7 @@ template <class R> UAVB_HD void make_vehp(VehP<R>& v, const uavb_vehicle& u, con
   v.Gx = (R)((Iz - Iy) * ia); v.Gy = (R)((Ix - Iz) * ia); v.Gz = (R)(-(Iy - Ix) * ik);
   v.Jp = (R)(Ix * o.gains[8] * ia); v.Jq = (R)(Iy * o.gains[9] * ia); v.Jr = (R)(-Iz * o.gains[10] * ik);
   v.Wx = (R)(u.dt * u.arm * u.kf / Ix); v.Wy = (R)(u.dt * u.arm * u.kf / Iy); v.Wz = (R)(u.dt * u.kappa * u.kf / Iz);
+  v.Kx = (R)(-u.dt * (Iz - Iy) / Ix); v.Ky = (R)(-u.dt * (Ix - Iz) / Iy); v.Kz = (R)(-u.dt * (Iy - Ix) / Iz);
   v.dvx = (R)(u.dt * o.wind[0] / m); v.dvy = (R)(u.dt * o.wind[1] / m); v.dvz = (R)(u.dt * (o.wind[2] / m + u.g));
   v.mass = (R)m;
   v.kp_xy = (R)o.gains[0]; v.kd_xy = (R)o.gains[1]; v.kp_z = (R)o.gains[2]; v.kd_z = (R)o.gains[3]; v.ki_z = (R)o.gains[4];
