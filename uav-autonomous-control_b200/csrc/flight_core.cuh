@@ -71,7 +71,28 @@ template <> struct Math<float> {
   }
   static UAVB_HD float div(float a, float b) { return a * rcp_fast(b); }
   static UAVB_HD float fma(float a, float b, float c) { return fmaf(a, b, c); }
-  static UAVB_HD float atan2(float y, float x) { return atan2f(y, x); }
+  // atan2 without a division: a = min(|x|,|y|) / max(|x|,|y|) through the reciprocal above, atan(a) = a P(a^2) with an
+  // equi-ripple degree-7 P on [0, 1] (max error 3.7e-8 rad before rounding; 3.3e-7 rad in fp32 over all quadrants, the same
+  // as atan2f, whose error is also set by the rounding of results near pi), then the octant / quadrant reflections.
+  // atan2(0, 0) = 0 like atan2f(+0, +0).
+  static UAVB_HD float atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = (mx > 0.f) ? mn * rcp_fast(mx) : 0.f;
+    const float t = a * a;
+    float p = -0.0040545563519447094f;
+    p = fmaf(p, t, 0.02186292376737154f);
+    p = fmaf(p, t, -0.055912287992173626f);
+    p = fmaf(p, t, 0.09642195584271772f);
+    p = fmaf(p, t, -0.13908629508211973f);
+    p = fmaf(p, t, 0.19946565845760894f);
+    p = fmaf(p, t, -0.33329860832632324f);
+    p = fmaf(p, t, 0.9999993356075512f);
+    float r = a * p;
+    r = (ay > ax) ? 1.57079632679489662f - r : r;
+    r = (x < 0.f) ? 3.14159265358979324f - r : r;
+    return copysignf(r, y);
+  }
   static UAVB_HD void sincos(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
     sincosf(x, s, c);
@@ -303,15 +324,15 @@ template <class R> UAVB_HD void body_rate_moment(const Drone<R>& d, const VehP<R
 // persistent rollout).
 template <class R> UAVB_HD void mix_and_limit(R pb, R qb, R rb, R coll, R lo, R hi, R* f) {
   typedef Math<R> M;
-  const R s1 = pb + qb, s2 = pb - qb;
-  const R m0 = s1 + rb, m1 = -(s2 + rb), m2 = rb - s1, m3 = s2 - rb;
-  // unclipped outputs first: when all four lie inside the limits no ratio of quad.py:116-119 is below 1, the scale is 1
-  // and the final clip is the identity
-  const R f0 = coll + m0, f1 = coll + m1, f2 = coll + m2, f3 = coll + m3;
+  // unclipped outputs first (coll +- r_bar, then +- the roll/pitch sums: 8 additions): when all four lie inside the limits
+  // no ratio of quad.py:116-119 is below 1, the scale is 1 and the final clip is the identity
+  const R s1 = pb + qb, s2 = pb - qb, t1 = coll + rb, t2 = coll - rb;
+  const R f0 = t1 + s1, f1 = t2 - s2, f2 = t1 - s1, f3 = t2 + s2;
   const R f_hi = M::fmax(M::fmax(f0, f1), M::fmax(f2, f3)), f_lo = M::fmin(M::fmin(f0, f1), M::fmin(f2, f3));
   if (f_hi <= hi && f_lo >= lo) {
     f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3;
   } else {
+    const R m0 = s1 + rb, m1 = -(s2 + rb), m2 = rb - s1, m3 = s2 - rb;
     const R room_hi = hi - coll, room_lo = lo - coll;
     // ratio of quad.py:116-119 per rotor, as straight-line selects: a few lanes of a warp saturating must not cost the
     // whole warp four branch diamonds.  (m < 0 || m > 0) is the ordered "not zero": a NaN moment keeps ratio 1.

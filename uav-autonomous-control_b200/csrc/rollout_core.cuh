@@ -74,7 +74,7 @@ struct NoLog {
 
 struct NoObstacles {
   static constexpr bool kAny = false;
-  template <class R> UAVB_HD bool within(R, R, R, R) const { return false; }
+  template <class R> UAVB_HD R gap(R, R, R) const { return R(3.0e38); }
   template <class R> UAVB_HD bool hit(R, R, R) const { return false; }
 };
 
@@ -145,12 +145,13 @@ template <class R> UAVB_HD void table_target(const TargetRow* rows, int row, Tar
 // (first_hit and the log phase are relative to the start of the mission, not of this launch).
 // The tick loop is split at outer-period boundaries so the 1 kHz body stays branch-light.
 //
-// Obstacle culling: at the start of every stretch of n <= freq ticks the drone can move at most
+// Obstacle culling: during a stretch of n <= freq ticks the drone can move at most
 //     reach = (|v| + acc_max n dt) n dt
-// (acc_max bounds gravity + full thrust + wind), so boxes farther than that from the body origin in
-// any axis cannot be entered before the next check and the per-tick inclusive point-in-AABB test
-// (minimum_snap.py:352-357) is skipped for the stretch.  The flag and first-hit tick are those of the
-// per-tick test; only the work changes.
+// (acc_max bounds gravity + full thrust + wind) in any axis.  `clear` is a lower bound of the Chebyshev gap between the
+// body origin and the nearest box: it is measured, then only charged with the reach of every stretch flown, and measured
+// again when the next stretch could use it up.  While clear > reach no box can be entered before the next check and the
+// per-tick inclusive point-in-AABB test (minimum_snap.py:352-357) is skipped for the stretch.  The flag and first-hit tick
+// are those of the per-tick test; only the work changes.
 // TABLE: the mission's set-points come from MissionView::trows (shared missions); otherwise they are evaluated on the fly.
 // A compile-time switch, so the table-driven instantiation carries none of the fp64 evaluation code or its registers.
 template <class R, bool TABLE, class OBST, class LOG>
@@ -158,6 +159,7 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
                          int tick0, int n_ticks, int freq, int lag, const OBST& obst, LOG& logger) {
   typedef Math<R> M;
   int k = 0;
+  R clear = R(0);                                            // not part of the carry: every launch / slice measures first
   while (k < n_ticks) {
     if (c.phase == 0) {
       Target<R> t;
@@ -177,7 +179,9 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
       const R T = (R)n * u.dt;
       const R speed = M::sqrt_fast(d.vx * d.vx + d.vy * d.vy + d.vz * d.vz);
       const R reach = R(1.01) * (speed + v.acc_max * T) * T + R(1e-4);
-      watch = obst.within((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz), reach);
+      if (!(clear > reach)) clear = obst.gap((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz));
+      watch = !(clear > reach);                              // NaN positions keep measuring and watching
+      clear -= reach;
     }
 #if defined(__CUDA_ARCH__)
     // one decision per warp: with per-rollout missions / obstacle sets the lanes disagree, and a divergent warp would run the

@@ -59,16 +59,17 @@ template <bool SHARED> struct BoxesT {
     }
     return h;
   }
-  // true when some box comes within `reach` of the point in every axis (conservative: Chebyshev gap)
-  template <class R> __device__ __forceinline__ bool within(R x, R y, R z, R reach) const {
-    bool w = false;
+  // Chebyshev gap from the point to the nearest box (<= 0 inside or on a face); NaN positions give NaN
+  template <class R> __device__ __forceinline__ R gap(R x, R y, R z) const {
+    R g = R(3.0e38);
     for (int i = 0; i < n; ++i) {
       const float2* q = box(i);
       const float2 bx = q[0], by = q[1], bz = q[2];
       const R gx = fmax((R)bx.x - x, x - (R)bx.y), gy = fmax((R)by.x - y, y - (R)by.y), gz = fmax((R)bz.x - z, z - (R)bz.y);
-      w |= !(fmax(gx, fmax(gy, gz)) > reach);          // NaN positions keep watching
+      const R gi = fmax(gx, fmax(gy, gz));
+      g = (gi < g || gi != gi) ? gi : g;
     }
-    return w;
+    return g;
   }
 };
 
