@@ -289,20 +289,31 @@ template <class R> UAVB_HD R yaw_rate_cmd(const VehP<R>& v, R q0, R q1, R q2, R 
   return (v.kp_yaw * e_yaw * cos_th - q_c * sin_phi) * M::rcp_fast(cos_phi);
 }
 
-// TrajectoryController._update_outer_loop (main.py:47-61) on the fresh state.
-// Requires a folded position (d.dx = d.dy = d.dz = 0).
-template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, const Target<R>& t) {
+// The same for a UNIT quaternion (what the persistent rollout's outer loop always sees): with sa = sin(phi) cos(theta) and
+// R22 = cos(phi) cos(theta), cos(theta)^2 = sa^2 + R22^2, so
+//   (kp e cos(theta) - q_c sin(phi)) / cos(phi) = (kp e (sa^2 + R22^2) - q_c sa) / R22
+// and neither Euler angle nor a square root is needed; inv_R22 is the reciprocal the altitude loop already formed.
+template <class R> UAVB_HD R yaw_rate_cmd_unit(const VehP<R>& v, R q0, R q1, R q2, R q3, R yc, R ys, R q_c, R R22, R inv_R22) {
+  typedef Math<R> M;
+  const R sa = R(2) * (q0 * q1 + q2 * q3);
+  const R sp = R(2) * (q0 * q3 + q1 * q2), cp = R(1) - R(2) * (q2 * q2 + q3 * q3);
+  const R e_yaw = M::atan2(ys * cp - yc * sp, yc * cp + ys * sp);
+  return (v.kp_yaw * e_yaw * (sa * sa + R22 * R22) - q_c * sa) * inv_R22;
+}
+
+// TrajectoryController._update_outer_loop (main.py:47-61) on the fresh state; (ex, ey, ez) = set-point - position, formed
+// in fp64 by the caller and rounded once.
+template <class R> UAVB_HD void outer_update(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, const Target<R>& t, R ex, R ey, R ez) {
   const RotE<R> r = rot_entries<R>(d.q0, d.q1, d.q2, d.q3);
   const R inv_R22 = Math<R>::rcp_fast(r.R22);
-  // position errors are formed in fp64 and rounded once
-  const R c = altitude_cmd<R>(d.integral, u, v, (R)(t.z - d.pz), d.vz, t.vz, t.az, inv_R22);
+  const R c = altitude_cmd<R>(d.integral, u, v, ez, d.vz, t.vz, t.az, inv_R22);
   set_thrust_cmd<R>(d, u, c);
   R bx, by;
-  lateral_cmd<R>(u, v, (R)(t.x - d.px), (R)(t.y - d.py), d.vx, d.vy, t.vx, t.vy, t.ax, t.ay, c, &bx, &by);
+  lateral_cmd<R>(u, v, ex, ey, d.vx, d.vy, t.vx, t.vy, t.ax, t.ay, c, &bx, &by);
   R p_c, q_c;
   roll_pitch_cmd<R>(v, bx, by, r, inv_R22, &p_c, &q_c);
   d.pc = p_c; d.qc = q_c;
-  d.rc = yaw_rate_cmd<R>(v, d.q0, d.q1, d.q2, d.q3, t.yc, t.ys, q_c);
+  d.rc = yaw_rate_cmd_unit<R>(v, d.q0, d.q1, d.q2, d.q3, t.yc, t.ys, q_c, r.R22, inv_R22);
   d.cp = v.Jp * d.pc; d.cq = v.Jq * d.qc; d.cr = v.Jr * d.rc;
 }
 

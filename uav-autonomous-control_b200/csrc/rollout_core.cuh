@@ -55,7 +55,8 @@ template <class R> struct Cursor {
   int phase;              // inner_step % frequency (main.py:25,39), kept incrementally
   R hx, hy;               // heading direction of the last valid row (minimum_snap.py:126-136 hold-last-valid),
                           // any positive multiple of (cos yaw, sin yaw)
-  double tx, ty, tz;      // position set-point of the row used by the current outer period
+  R ex, ey, ez;           // position error (set-point - position, formed in fp64 and rounded once) at the start of the current
+                          // outer period: what the controller saw; the tracking error at its end is this minus the displacement
 };
 
 template <class R> struct Accum {
@@ -170,8 +171,8 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
         cursor_target<R>(c, m, &t);
         cursor_advance(&c.seg, &c.row, m);
       }
-      outer_update<R>(d, u, v, t);
-      c.tx = t.x; c.ty = t.y; c.tz = t.z;
+      c.ex = (R)(t.x - d.px); c.ey = (R)(t.y - d.py); c.ez = (R)(t.z - d.pz);   // the position is folded here (d.dx = 0)
+      outer_update<R>(d, u, v, t, c.ex, c.ey, c.ez);
     }
     const int n = (freq - c.phase < n_ticks - k) ? (freq - c.phase) : (n_ticks - k);
     bool watch = false;
@@ -215,16 +216,18 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
     if (c.phase == freq) {
       c.phase = 0;
       if (!LOG::kNormEveryTick) renormalise_q<R>(d);         // once per outer period (not per launch: chunked runs stay bit-identical)
+      // tracking error |set-point - p| after the period (test_mujoco_trajectory_tracking.py:27-31): p = fold + displacement
+      const R ex = c.ex - d.dx, ey = c.ey - d.dy, ez = c.ez - d.dz;
       fold_position<R>(d);
-      const R ex = (R)(c.tx - d.px), ey = (R)(c.ty - d.py), ez = (R)(c.tz - d.pz);
       const R e2 = ex * ex + ey * ey + ez * ez;
       const R e = M::sqrt_fast(e2);
       a.sum_e += e; a.sum_e2 += e2; a.max_e = M::fmax(a.max_e, e);
       ++a.periods;
-      if (!M::finite(e2)) a.status |= 1;
-      else if (e2 > R(1e8)) a.status |= 2;                   // more than 1e4 m from its set-point
     }
   }
+  // status once per call: a non-finite error makes the sum of squares non-finite for good; max_e ignores NaN but keeps Inf
+  if (!M::finite(a.sum_e2)) a.status |= 1;
+  if (a.max_e > R(1e4)) a.status |= 2;                       // more than 1e4 m from its set-point
 }
 
 template <class R> UAVB_HD void drone_init(Drone<R>& d, const VehU<R>& u, double sx, double sy, double sz) {
@@ -242,7 +245,7 @@ template <class R> UAVB_HD void drone_init(Drone<R>& d, const VehU<R>& u, double
 }
 
 template <class R> UAVB_HD void cursor_init(Cursor<R>& c) {
-  c.seg = 0; c.row = 0; c.cached_seg = -1; c.phase = 0; c.hx = R(1); c.hy = R(0); c.tx = c.ty = c.tz = 0.0;
+  c.seg = 0; c.row = 0; c.cached_seg = -1; c.phase = 0; c.hx = R(1); c.hy = R(0); c.ex = c.ey = c.ez = R(0);
 }
 
 template <class R> UAVB_HD void accum_init(Accum<R>& a) {

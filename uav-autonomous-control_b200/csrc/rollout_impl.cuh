@@ -110,7 +110,8 @@ struct Carry {
     w(20) = d.integral; w(21) = d.thrust_cmd; w(22) = d.cp; w(23) = d.cq; w(24) = d.cr;   // body-rate commands in rotor units
     w(25) = d.zbx; w(26) = d.zby; w(27) = d.zbz; w(28) = c.hx;
     w(29) = i2f(c.seg); w(30) = i2f(c.row); w(31) = i2f(c.phase);
-    put64(32, c.tx); put64(34, c.ty); put64(36, c.tz);
+    w(32) = c.ex; w(33) = c.ey; w(34) = c.ez;
+    w(35) = 0.f; w(36) = 0.f; w(37) = 0.f;                  // spare
     w(38) = a.sum_e; w(39) = a.sum_e2; w(40) = a.max_e;
     w(41) = i2f(a.periods); w(42) = i2f(a.collided); w(43) = i2f(a.first_hit); w(44) = i2f(a.status);
     w(45) = i2f(tick);
@@ -124,7 +125,7 @@ struct Carry {
     d.integral = w(20); set_thrust_cmd<float>(d, u, w(21)); d.cp = w(22); d.cq = w(23); d.cr = w(24);
     d.zbx = w(25); d.zby = w(26); d.zbz = w(27); c.hx = w(28);
     c.seg = f2i(w(29)); c.row = f2i(w(30)); c.phase = f2i(w(31)); c.cached_seg = -1;
-    c.tx = get64(32); c.ty = get64(34); c.tz = get64(36);
+    c.ex = w(32); c.ey = w(33); c.ez = w(34);
     a.sum_e = w(38); a.sum_e2 = w(39); a.max_e = w(40);
     a.periods = f2i(w(41)); a.collided = f2i(w(42)); a.first_hit = f2i(w(43)); a.status = f2i(w(44));
     *tick = f2i(w(45));

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) stage_kernel(const __grid_constant__ Stag
       Target<float> t;
       load_target(t, a.target, B, i);
       d.integral = a.integral[i];
-      outer_update<float>(d, u, v, t);
+      outer_update<float>(d, u, v, t, (float)(t.x - d.px), (float)(t.y - d.py), (float)(t.z - d.pz));
       a.integral[i] = d.integral;
       a.thrust[i] = d.thrust_cmd;
       a.pqr_cmd[0 * B + i] = d.pc; a.pqr_cmd[1 * B + i] = d.qc; a.pqr_cmd[2 * B + i] = d.rc;
