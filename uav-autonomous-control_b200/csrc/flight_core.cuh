@@ -139,6 +139,7 @@ template <class R> struct VehU {
   R kf, inv_kf, arm_kf, kappa_kf;                  // arm*kf, kappa*kf: torque per unit of summed w^2
   R inv_arm4, inv_kappa4;                          // 1/(4 arm), 1/(4 kappa): mixer division by 4 folded in (quad.py:112)
   R fmin, fmax, fmin4, fmax4, a_rise, a_fall;      // a_* = 1 - exp(-dt/tau) (quad.py:102)
+  R a_mean, a_hdiff;                               // (a_rise + a_fall)/2, (a_rise - a_fall)/2
   R w2min, w2max, quarter_inv_kf;                  // rotor units (see "rotor units" below): fmin/kf, fmax/kf, 1/(4 kf)
   R max_ascent, max_descent, max_speed_xy, max_acc_xy, max_tilt, integral_limit;
 };
@@ -365,13 +366,16 @@ template <class R> UAVB_HD void allocate_forces(const VehU<R>& u, R coll, const 
   mix_and_limit<R>(Mo[0] * u.inv_arm4, Mo[1] * u.inv_arm4, -Mo[2] * u.inv_kappa4, coll, u.fmin, u.fmax, f);
 }
 
-// Asymmetric first-order lag of the rotor speeds toward their commands (quad.py:98-103).
+// Asymmetric first-order lag of the rotor speeds toward their commands (quad.py:98-103): w += a (c - w) with a = a_rise
+// when c > w and a_fall otherwise, i.e. a (c - w) = a_mean (c - w) + a_hdiff |c - w| with a_mean = (a_rise + a_fall)/2 and
+// a_hdiff = (a_rise - a_fall)/2 -- two fused multiply-adds and no select.
 template <class R> UAVB_HD void lag_toward(Drone<R>& d, const VehU<R>& u, R c0, R c1, R c2, R c3) {
   typedef Math<R> M;
-  d.om0 = M::fma((c0 > d.om0) ? u.a_rise : u.a_fall, c0 - d.om0, d.om0);
-  d.om1 = M::fma((c1 > d.om1) ? u.a_rise : u.a_fall, c1 - d.om1, d.om1);
-  d.om2 = M::fma((c2 > d.om2) ? u.a_rise : u.a_fall, c2 - d.om2, d.om2);
-  d.om3 = M::fma((c3 > d.om3) ? u.a_rise : u.a_fall, c3 - d.om3, d.om3);
+  const R e0 = c0 - d.om0, e1 = c1 - d.om1, e2 = c2 - d.om2, e3 = c3 - d.om3;
+  d.om0 = M::fma(u.a_hdiff, M::abs(e0), M::fma(u.a_mean, e0, d.om0));
+  d.om1 = M::fma(u.a_hdiff, M::abs(e1), M::fma(u.a_mean, e1, d.om1));
+  d.om2 = M::fma(u.a_hdiff, M::abs(e2), M::fma(u.a_mean, e2, d.om2));
+  d.om3 = M::fma(u.a_hdiff, M::abs(e3), M::fma(u.a_mean, e3, d.om3));
 }
 
 // Quad.set_propeller_speed after the allocation (quad.py:95-103): w_cmd = sqrt(f / kf), then the lag.

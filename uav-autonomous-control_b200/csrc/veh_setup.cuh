@@ -47,7 +47,8 @@ template <class R> inline void make_vehu(VehU<R>& v, const uavb_vehicle& u, doub
   v.inv_arm4 = (R)(0.25 / u.arm); v.inv_kappa4 = (R)(0.25 / u.kappa);
   v.fmin = (R)u.min_thrust; v.fmax = (R)u.max_thrust; v.fmin4 = (R)(4.0 * u.min_thrust); v.fmax4 = (R)(4.0 * u.max_thrust);
   v.w2min = (R)(u.min_thrust / u.kf); v.w2max = (R)(u.max_thrust / u.kf); v.quarter_inv_kf = (R)(0.25 / u.kf);
-  v.a_rise = (R)(1.0 - exp(-u.dt / u.tau_rise)); v.a_fall = (R)(1.0 - exp(-u.dt / u.tau_fall));
+  const double ar = 1.0 - exp(-u.dt / u.tau_rise), af = 1.0 - exp(-u.dt / u.tau_fall);
+  v.a_rise = (R)ar; v.a_fall = (R)af; v.a_mean = (R)(0.5 * (ar + af)); v.a_hdiff = (R)(0.5 * (ar - af));
   v.max_ascent = (R)u.max_ascent; v.max_descent = (R)u.max_descent; v.max_speed_xy = (R)u.max_speed_xy;
   v.max_acc_xy = (R)u.max_horiz_accel; v.max_tilt = (R)u.max_tilt; v.integral_limit = (R)u.integral_limit;
 }
