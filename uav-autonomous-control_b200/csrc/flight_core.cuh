@@ -135,7 +135,7 @@ template <class R> UAVB_HD R clampr(R x, R lo, R hi) { return Math<R>::fmin(Math
 // Constants that are uniform across a launch.  The rollout kernel receives this struct by value in
 // its parameter block, so every field is a constant-bank operand.
 template <class R> struct VehU {
-  R dt, half_dt, dt_outer, g;
+  R dt, half_dt, half_dt_sq, dt_outer, g;
   R kf, inv_kf, arm_kf, kappa_kf;                  // arm*kf, kappa*kf: torque per unit of summed w^2
   R inv_arm4, inv_kappa4;                          // 1/(4 arm), 1/(4 kappa): mixer division by 4 folded in (quad.py:112)
   R fmin, fmax, fmin4, fmax4, a_rise, a_fall;      // a_* = 1 - exp(-dt/tau) (quad.py:102)
@@ -424,7 +424,7 @@ UAVB_HD void integrate(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx, R 
   // q <- q * [cos(a/2), sin(a/2) w/|w|], a = dt |w|   (mju_quatIntegrate), written as q += q*(dq-1)
   const R wn2 = M::fma(d.wx, d.wx, M::fma(d.wy, d.wy, d.wz * d.wz));
   const R h = u.half_dt;
-  const R x2 = (h * h) * wn2;                                // (a/2)^2
+  const R x2 = u.half_dt_sq * wn2;                                // (a/2)^2
   R sf, cm1;
   if (x2 < R(1e-3)) {                                        // |a/2| < 0.0316
     if constexpr (sizeof(R) == 4) {
