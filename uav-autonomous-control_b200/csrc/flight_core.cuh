@@ -147,7 +147,7 @@ template <class R> struct VehU {
 // Constants that differ between rollouts under Monte-Carlo perturbation (uniform otherwise).
 template <class R> struct VehP {
   // 1 kHz body
-  R kf_dt_over_m;                                  // kf dt / m: velocity gained per unit of summed w^2
+  R kf_dt_over_m, kf_dt_over_m2;                   // kf dt / m: velocity gained per unit of summed w^2; twice that
   R dIx, dIy, dIz;                                 // Iz-Iy, Ix-Iz, Iy-Ix (gyroscopic term, diagonal inertia)
   R Ikp_p, Ikp_q, Ikp_r;                           // I * kp of the body-rate loop (controller.py:128)
   R dt_invIx, dt_invIy, dt_invIz;                  // dt / I
@@ -175,7 +175,8 @@ template <class R> struct Drone {
   R coll;              // clip(thrust_cmd, 4 fmin, 4 fmax) / (4 kf) (quad.py:107,113) in rotor units, refreshed with thrust_cmd
   R pc, qc, rc;        // pqr_cmd (main.py:27)
   R cp, cq, cr;        // the same in rotor units (Jp pc, Jq qc, Jr rc): what the persistent rollout carries between ticks
-  R zbx, zby, zbz;     // thrust direction MuJoCo last computed (stale body z axis)
+  R zbx, zby, zbz;     // thrust direction MuJoCo last computed (stale body z axis) as the half axis (a, b, c) of
+                       // half_axis(): z = (2a, 2b, 1 - 2c)
 };
 
 // Set-point of one table row (minimum_snap.py:122-123 columns 0..9): fp64 position (errors are formed in fp64), the rest
@@ -202,6 +203,14 @@ template <class R> UAVB_HD void set_thrust_cmd(Drone<R>& d, const VehU<R>& u, R 
 template <class R> UAVB_HD void fold_position(Drone<R>& d) {
   d.px += (double)d.dx; d.py += (double)d.dy; d.pz += (double)d.dz;
   d.dx = d.dy = d.dz = R(0);
+}
+
+// Half of the third column of R(q) (quad.py:153): z = (2a, 2b, 1 - 2c).
+template <class R> UAVB_HD void half_axis(const Drone<R>& d, R* a, R* b, R* c) {
+  typedef Math<R> M;
+  *a = M::fma(d.q1, d.q3, d.q0 * d.q2);
+  *b = M::fma(d.q2, d.q3, -(d.q0 * d.q1));
+  *c = M::fma(d.q1, d.q1, d.q2 * d.q2);
 }
 
 // Third column of R(q) for a normalised quaternion (quad.py:153): body z axis in the world frame.
@@ -407,15 +416,13 @@ template <class R> UAVB_HD void rotor_sums(const Drone<R>& d, R* tot, R* tx, R* 
 // false and renormalises once per outer period instead: q * dq of a unit q and the unit dq below stays unit up to
 // ~6e-8 per tick, the drift over 10 ticks (< 1e-6 in |q|^2) scales the thrust axis and R by the same factor, far inside
 // the fp32 noise of the step, and the outer loop always sees a freshly normalised q.
-// Semi-implicit Euler with the velocity gain `dvt` along the thrust axis (zx, zy, zz) and the new body rates (nwx, nwy, nwz).
+// Semi-implicit Euler with the velocity increments of the tick (ivx, ivy, ivz) and the new body rates (nwx, nwy, nwz).
+// The increments are formed by the caller and added once: near hover thrust and gravity cancel inside them.
 template <class R, bool NORM = true>
-UAVB_HD void integrate(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx, R zy, R zz, R dvt, R nwx, R nwy, R nwz) {
+UAVB_HD void integrate(Drone<R>& d, const VehU<R>& u, R ivx, R ivy, R ivz, R nwx, R nwy, R nwz) {
   typedef Math<R> M;
   // velocities first (semi-implicit Euler)
-  // (the per-tick increment is formed first and added once: near hover thrust and gravity cancel inside it)
-  d.vx += M::fma(zx, dvt, v.dvx);
-  d.vy += M::fma(zy, dvt, v.dvy);
-  d.vz += M::fma(zz, dvt, v.dvz);
+  d.vx += ivx; d.vy += ivy; d.vz += ivz;
   d.wx = nwx; d.wy = nwy; d.wz = nwz;
   // positions with the new velocity
   d.dx = M::fma(u.dt, d.vx, d.dx);
@@ -469,7 +476,7 @@ UAVB_HD void physics_step(Drone<R>& d, const VehU<R>& u, const VehP<R>& v, R zx,
   R tot, tx, ty, tzn;
   rotor_sums<R>(d, &tot, &tx, &ty, &tzn);
   const R dvt = -tot * v.kf_dt_over_m;                         // dt * specific thrust along -z body
-  integrate<R, NORM>(d, u, v, zx, zy, zz, dvt,
+  integrate<R, NORM>(d, u, M::fma(zx, dvt, v.dvx), M::fma(zy, dvt, v.dvy), M::fma(zz, dvt, v.dvz),
                      M::fma(v.dt_invIx, M::fma(u.arm_kf, tx, -gx), d.wx),
                      M::fma(v.dt_invIy, M::fma(u.arm_kf, ty, -gy), d.wy),
                      M::fma(v.dt_invIz, M::fma(-u.kappa_kf, tzn, -gz), d.wz));
@@ -494,13 +501,16 @@ template <class R, bool NORM = true> UAVB_HD void inner_tick(Drone<R>& d, const 
   mix_and_limit<R>(M::fma(-v.Jp, d.wx, M::fma(v.Gx, yz, d.cp)), M::fma(-v.Jq, d.wy, M::fma(v.Gy, zx_, d.cq)),
                    M::fma(-v.Jr, d.wz, M::fma(v.Gz, xy, d.cr)), d.coll, u.w2min, u.w2max, w2);
   lag_toward<R>(d, u, M::sqrt_fast(w2[0]), M::sqrt_fast(w2[1]), M::sqrt_fast(w2[2]), M::sqrt_fast(w2[3]));
-  R zx, zy, zz;
-  body_z<R>(d, &zx, &zy, &zz);                               // axis of X_k: what mj_step's forward pass will compute
-  const R ux = thrust_frame_lag ? d.zbx : zx, uy = thrust_frame_lag ? d.zby : zy, uz = thrust_frame_lag ? d.zbz : zz;
-  d.zbx = zx; d.zby = zy; d.zbz = zz;
+  // thrust axis of X_k (what mj_step's forward pass will compute) as the half axis (a, b, c): z = (2a, 2b, 1 - 2c), so that
+  // dv = z dvt + dv0 = (a dvt2 + dvx, b dvt2 + dvy, (dvt2/2 + dvz) - c dvt2) with dvt2 = 2 dvt and no doubling of the axis
+  R ha, hb, hc;
+  half_axis<R>(d, &ha, &hb, &hc);
+  const R ua = thrust_frame_lag ? d.zbx : ha, ub = thrust_frame_lag ? d.zby : hb, uc = thrust_frame_lag ? d.zbz : hc;
+  d.zbx = ha; d.zby = hb; d.zbz = hc;
   R tot, tx, ty, tzn;
   rotor_sums<R>(d, &tot, &tx, &ty, &tzn);
-  integrate<R, NORM>(d, u, v, ux, uy, uz, -tot * v.kf_dt_over_m,
+  const R dvt2 = -tot * v.kf_dt_over_m2;                       // 2 dt * specific thrust along -z body
+  integrate<R, NORM>(d, u, M::fma(ua, dvt2, v.dvx), M::fma(ub, dvt2, v.dvy), M::fma(-uc, dvt2, M::fma(R(0.5), dvt2, v.dvz)),
                      M::fma(v.Wx, tx, M::fma(v.Kx, yz, d.wx)),
                      M::fma(v.Wy, ty, M::fma(v.Ky, zx_, d.wy)),
                      M::fma(-v.Wz, tzn, M::fma(v.Kz, xy, d.wz)));

@@ -241,7 +241,7 @@ template <class R> UAVB_HD void drone_init(Drone<R>& d, const VehU<R>& u, double
   set_thrust_cmd<R>(d, u, R(0));                     // main.py:26
   d.pc = d.qc = d.rc = R(0);                         // main.py:27
   d.cp = d.cq = d.cr = R(0);
-  body_z<R>(d, &d.zbx, &d.zby, &d.zbz);              // mj_forward in MujocoSimulation.__init__ (mujoco_sim.py:81)
+  half_axis<R>(d, &d.zbx, &d.zby, &d.zbz);           // mj_forward in MujocoSimulation.__init__ (mujoco_sim.py:81)
 }
 
 template <class R> UAVB_HD void cursor_init(Cursor<R>& c) {

@@ -56,7 +56,7 @@ template <class R> inline void make_vehu(VehU<R>& v, const uavb_vehicle& u, doub
 // Per-rollout constants from the (possibly perturbed) mass, inertia, gains and wind.
 template <class R> UAVB_HD void make_vehp(VehP<R>& v, const uavb_vehicle& u, const McValues& o) {
   const double m = o.mass, Ix = o.inertia[0], Iy = o.inertia[1], Iz = o.inertia[2];
-  v.kf_dt_over_m = (R)(u.kf * u.dt / m);
+  v.kf_dt_over_m = (R)(u.kf * u.dt / m); v.kf_dt_over_m2 = (R)(2.0 * u.kf * u.dt / m);
   v.dIx = (R)(Iz - Iy); v.dIy = (R)(Ix - Iz); v.dIz = (R)(Iy - Ix);
   v.Ikp_p = (R)(Ix * o.gains[8]); v.Ikp_q = (R)(Iy * o.gains[9]); v.Ikp_r = (R)(Iz * o.gains[10]);
   v.dt_invIx = (R)(u.dt / Ix); v.dt_invIy = (R)(u.dt / Iy); v.dt_invIz = (R)(u.dt / Iz);
