@@ -7,13 +7,13 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 wp, vel = kernels.mc_missions(99, B, 4)
 c, t, _ = kernels.minsnap_solve(wp, vel)
 offs = torch.arange(B + 1, dtype=torch.int32, device=wp.device) * 4
-def ev(fn, n=4):
+def ev(fn, n=8):
     ts = []
     for i in range(n):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); out = fn(); b.record(); torch.cuda.synchronize()
         if i: ts.append(a.elapsed_time(b))
-    return statistics.mean(ts), out
+    return statistics.median(ts[2:]), out          # the first two calls allocate the (double-buffered) output
 ms_meta, (rows, yaw0, total) = ev(lambda: kernels.table_meta(c, t.reshape(-1), offs, 0.01))
 roff = torch.zeros(B + 1, dtype=torch.int32, device=wp.device); roff[1:] = torch.cumsum(total, 0)
 n_rows = int(roff[-1])

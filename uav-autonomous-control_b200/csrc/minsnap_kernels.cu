@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "minsnap_core.cuh"
+#include "rollout_core.cuh"
 #include "uavb_common.cuh"
 
 namespace uavb {
@@ -107,15 +108,25 @@ __device__ __forceinline__ int arange_len(double T, double dt) {
   return n > 0.0 ? (n < 2147483647.0 ? (int)n : 2147483647) : 0;
 }
 
+// Horizontal velocity of a table row by the nested Horner recurrence of eval_row (flight_core.cuh): the same operations on the
+// same values, so every kernel that decides "is this row's yaw valid" (table geometry, K3, the set-point table of K2 and K2's
+// on-the-fly evaluation) sees the same bits.  Validity is the exact squared-speed form of rollout_core.cuh.
 __device__ __forceinline__ void eval_vel_xy(const double* __restrict__ c, double t, double* vx, double* vy) {
   double v[2];
 #pragma unroll
   for (int ax = 0; ax < 2; ++ax) {
-    const double c7 = c[21 + ax], c6 = c[18 + ax], c5 = c[15 + ax], c4 = c[12 + ax], c3 = c[9 + ax], c2 = c[6 + ax], c1 = c[3 + ax];
-    v[ax] = (((((7.0 * c7 * t + 6.0 * c6) * t + 5.0 * c5) * t + 4.0 * c4) * t + 3.0 * c3) * t + 2.0 * c2) * t + c1;
+    double pp = __ldg(c + 21 + ax), d1 = 0.0;
+#pragma unroll
+    for (int k = 6; k >= 0; --k) {
+      d1 = fma(d1, t, pp);
+      pp = fma(pp, t, __ldg(c + 3 * k + ax));
+    }
+    v[ax] = d1;
   }
   *vx = v[0]; *vy = v[1];
 }
+
+__device__ __forceinline__ bool yaw_valid(double vx, double vy) { return speed2_unfused(vx, vy) >= kSpeed2Min; }
 
 __global__ void __launch_bounds__(128) table_meta_kernel(const double* __restrict__ coeffs, const double* __restrict__ times,
                                                          const int* __restrict__ seg_offsets, int B, double dt,
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(128) table_meta_kernel(const double* __restric
       for (int j = 0; j < n; ++j) {
         double vx, vy;
         eval_vel_xy(c, (double)j * dt, &vx, &vy);
-        if (sqrt(vx * vx + vy * vy) >= 1e-3) { yaw0 = atan2(vy, vx); found = true; break; }
+        if (yaw_valid(vx, vy)) { yaw0 = atan2(vy, vx); found = true; break; }
       }
     }
   }
@@ -158,19 +169,12 @@ struct RowEval {
 };
 
 __device__ __forceinline__ void eval_table_row(const double* __restrict__ c, double t, RowEval& r, bool vel_only) {
-#pragma unroll
-  for (int ax = 0; ax < 3; ++ax) {
-    const double c7 = c[21 + ax], c6 = c[18 + ax], c5 = c[15 + ax], c4 = c[12 + ax];
-    const double c3 = c[9 + ax], c2 = c[6 + ax], c1 = c[3 + ax], c0 = c[ax];
-    r.v[ax] = (((((7.0 * c7 * t + 6.0 * c6) * t + 5.0 * c5) * t + 4.0 * c4) * t + 3.0 * c3) * t + 2.0 * c2) * t + c1;
-    if (!vel_only) {
-      r.p[ax] = ((((((c7 * t + c6) * t + c5) * t + c4) * t + c3) * t + c2) * t + c1) * t + c0;
-      r.a[ax] = ((((42.0 * c7 * t + 30.0 * c6) * t + 20.0 * c5) * t + 12.0 * c4) * t + 6.0 * c3) * t + 2.0 * c2;
-    }
+  if (vel_only) {
+    eval_vel_xy(c, t, &r.v[0], &r.v[1]);
+  } else {
+    eval_row([c](int i) { return __ldg(c + i); }, t, r.p, r.v, r.a);
   }
 }
-
-__device__ __forceinline__ bool yaw_valid(double vx, double vy) { return sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy))) >= 1e-3; }
 
 __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
                                                                          const int* __restrict__ seg_rows, const int* __restrict__ row_offsets,
@@ -239,16 +243,20 @@ __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const d
     double corr = 0.0;
     if (valid && (pv >= 0 || have_prev)) {
       const double dd = raw - (pv >= 0 ? pr_lane : prev_raw);
-      double ddmod = dd + pi;
-      ddmod = ddmod - two_pi * floor(ddmod / two_pi) - pi;
-      if (ddmod == -pi && dd > 0.0) ddmod = pi;
-      if (fabs(dd) >= pi) corr = ddmod - dd;
+      if (fabs(dd) >= pi) {                                // the only rows np.unwrap corrects; rare, so is the division
+        double ddmod = dd + pi;
+        ddmod = ddmod - two_pi * floor(ddmod / two_pi) - pi;
+        if (ddmod == -pi && dd > 0.0) ddmod = pi;
+        corr = ddmod - dd;
+      }
     }
     double incl = corr;                                  // inclusive prefix sum of the corrections over the lanes
+    if (__any_sync(full, corr != 0.0)) {                   // most chunks have nothing to correct
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const double up = __shfl_up_sync(full, incl, off);
-      if (lane >= off) incl += up;
+      for (int off = 1; off < 32; off <<= 1) {
+        const double up = __shfl_up_sync(full, incl, off);
+        if (lane >= off) incl += up;
+      }
     }
     const double y_valid = raw + (cum + incl);
     // hold-last-valid: nearest valid lane at or before this one, else the value carried from earlier chunks
