@@ -30,7 +30,7 @@ def run(B, **env):
     print(f"B={B} {env}: {t:.3f} ms -> {B * n_ticks / t / 1e6:.1f} G ticks/s", flush=True)
 for B in (37888, 75776, 100000, 151552):
     run(B, UAVB_ROLLOUT_CHUNKS=1)
-for ch in (2, 5, 10, 25, 50, 100):
+for ch in (2, 3, 4, 6, 9, 12, 15, 25, 50):
     run(100000, UAVB_ROLLOUT_CHUNKS=ch)
 run(100000)
 run(500000, UAVB_ROLLOUT_CHUNKS=1)

@@ -77,18 +77,20 @@ template <bool SHARED> struct BoxesT {
 template <class R> struct GlobalLog {
   static constexpr bool kNormEveryTick = true;
   R* out;
-  long long B;
+  unsigned B;              // field stride in elements (check_args bounds 13 B below 2^32 when a log is requested)
   int stride, left;
   __device__ __forceinline__ void tick(const Drone<R>& d) {
     if (--left) return;
     left = stride;
-    // streaming stores: the log is written once and never re-read by the kernel, keep it out of the L2 working set
+    // streaming stores: the log is written once and never re-read by the kernel, keep it out of the L2 working set.
+    // Field offsets are 32-bit multiples of B on one 64-bit base: cheaper address arithmetic than 64-bit products.
     R* o = out;
-    __stcs(o + 0 * B, (R)(d.px + (double)d.dx)); __stcs(o + 1 * B, (R)(d.py + (double)d.dy)); __stcs(o + 2 * B, (R)(d.pz + (double)d.dz));
-    __stcs(o + 3 * B, d.q0); __stcs(o + 4 * B, d.q1); __stcs(o + 5 * B, d.q2); __stcs(o + 6 * B, d.q3);
-    __stcs(o + 7 * B, d.vx); __stcs(o + 8 * B, d.vy); __stcs(o + 9 * B, d.vz);
-    __stcs(o + 10 * B, d.wx); __stcs(o + 11 * B, d.wy); __stcs(o + 12 * B, d.wz);
-    out += 13 * B;
+    const unsigned b = B;
+    __stcs(o, (R)(d.px + (double)d.dx)); __stcs(o + (size_t)b, (R)(d.py + (double)d.dy)); __stcs(o + (size_t)(2u * b), (R)(d.pz + (double)d.dz));
+    __stcs(o + (size_t)(3u * b), d.q0); __stcs(o + (size_t)(4u * b), d.q1); __stcs(o + (size_t)(5u * b), d.q2); __stcs(o + (size_t)(6u * b), d.q3);
+    __stcs(o + (size_t)(7u * b), d.vx); __stcs(o + (size_t)(8u * b), d.vy); __stcs(o + (size_t)(9u * b), d.vz);
+    __stcs(o + (size_t)(10u * b), d.wx); __stcs(o + (size_t)(11u * b), d.wy); __stcs(o + (size_t)(12u * b), d.wz);
+    out = o + (size_t)(13u * b);
   }
 };
 
@@ -199,7 +201,7 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
     if constexpr (LOG) {
       GlobalLog<R> lg;
       lg.out = reinterpret_cast<R*>(a.log_out) + (size_t)(launch_tick0 / a.log_stride) * 13 * B + i;
-      lg.B = B; lg.stride = a.log_stride; lg.left = a.log_stride - launch_tick0 % a.log_stride;
+      lg.B = (unsigned)B; lg.stride = a.log_stride; lg.left = a.log_stride - launch_tick0 % a.log_stride;
       rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
     } else {
       NoLog lg;

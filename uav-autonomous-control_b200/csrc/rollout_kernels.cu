@@ -75,6 +75,7 @@ static int check_args(const uavb_rollout_args* a, bool f64) {
   UAVB_REQUIRE(!(f64 && (a->resume || a->carry)), "rollout_f64: the fp64 validation rollout has no carry/resume");
   UAVB_REQUIRE(a->log_stride >= 0, "rollout: log_stride must be >= 0");
   UAVB_REQUIRE(a->log_stride == 0 || a->log_out != nullptr, "rollout: log_stride > 0 needs log_out");
+  UAVB_REQUIRE(a->log_stride == 0 || a->B <= 300000000LL, "rollout: a state log supports at most 3e8 rollouts per launch");
   UAVB_REQUIRE(a->n_obs >= 0 && a->n_obs <= 1024, "rollout: n_obs out of range");
   UAVB_REQUIRE(a->n_obs == 0 || (a->aabbs != nullptr && a->n_obs_sets >= 1), "rollout: n_obs > 0 needs aabbs and n_obs_sets >= 1");
   UAVB_REQUIRE(a->dt_outer > 0.0 && a->veh.dt > 0.0 && a->veh.mass > 0.0, "rollout: dt_outer, veh.dt and veh.mass must be positive");
