@@ -203,6 +203,37 @@ def test_controller_closed_forms_of_reference_unit_tests(cuda):
     assert CascadedController._pid(2.0, 3.0, 4.0, 1.0, 1.0, 1.0, 0.5) == 9.5 and CascadedController._pd(2.0, 3.0, 1.0, 1.0, 0.5) == 5.5
 
 
+def test_yaw_controller_over_all_quadrants(cuda):
+    """controller.py:156-168 with quad.py:189-213 in NumPy fp64 against the batched method (one atan2 of the rotated heading,
+    division-free) for 8 192 random attitudes (tilt < 60 deg) and yaw set-points over more than the whole circle."""
+    import torch
+    from uav_ac_b200.control.controller import CascadedController
+    rng = np.random.default_rng(5)
+    B = 8192
+    yaw, pitch, roll = rng.uniform(-np.pi, np.pi, B), rng.uniform(-1.0, 1.0, B), rng.uniform(-1.0, 1.0, B)
+    cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+    q = np.stack((cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy), axis=1)
+    q = q.astype(np.float32).astype(np.float64)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    psi_des = rng.uniform(-7.0, 7.0, B)
+    q_c = rng.uniform(-2.0, 2.0, B)
+    quad = _quad(B, cuda)
+    X = np.zeros((B, 13))
+    X[:, 3:7] = q
+    quad.X = torch.tensor(X, dtype=torch.float32, device=cuda)
+    got = CascadedController(9.81, 0.01).yaw_controller(quad, psi_des, quad.kp_yaw, q_c).cpu().numpy()
+    q0, q1, q2, q3 = np.asarray(quad.X.cpu().numpy()[:, 3:7], dtype=np.float64).T          # the fp32 state the kernel saw
+    phi = np.arctan2(2 * (q0 * q1 + q2 * q3), 1 - 2 * (q1 * q1 + q2 * q2))                  # quad.py:189-195
+    theta = np.arcsin(np.clip(2 * (q0 * q2 - q3 * q1), -1, 1))                              # :197-204
+    psi = np.arctan2(2 * (q0 * q3 + q1 * q2), 1 - 2 * (q2 * q2 + q3 * q3))                  # :206-213
+    e = np.mod(psi_des, 2 * np.pi) - psi                                                   # controller.py:164 wrap_to_2pi
+    e = np.mod(e + np.pi, 2 * np.pi) - np.pi                                               # :165 wrap_to_pi
+    want = (float(quad.kp_yaw) * e * np.cos(theta) - q_c * np.sin(phi)) / np.cos(phi)       # :166-167
+    away = np.abs(np.abs(e) - np.pi) > 1e-3                                                # at exactly +-pi either sign is the same error
+    scale = 1.0 / np.abs(np.cos(phi))
+    assert np.all(np.abs(got - want)[away] <= 4e-6 * scale[away] * (1.0 + np.abs(want[away])))
+
+
 def test_per_drone_gains_and_mass_are_honoured(cuda):
     """Monte-Carlo vehicles through the method-level API: gains as (B,) tensors, mass as a (B,) tensor."""
     import torch
