@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UAVB_VERSION 110            /* 0.1.10: carry block of 52 words, stage ABI v2, host mission call, set-point table, RRT* */
+#define UAVB_VERSION 111            /* 0.1.11: carry block of 52 words (contents private to the library version that wrote it; 0.1.11 changed them), stage ABI v2, host mission call, set-point table, RRT* */
 
 #define UAVB_OK          0
 #define UAVB_EINVAL     -1          /* bad argument (null pointer, size out of range) */
