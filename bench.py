@@ -461,7 +461,7 @@ def solve_rate(kernels, dev, flush, peaks):
     peak = peaks.get("hbm_gbs", 6650.0)
     return {"metric": "min-snap solves/s", "value": Bm / t, "unit": "solves/s", "missions": Bm, "splines": 4, "kernel_ms": t * 1e3,
             "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peak, "unit": "GB/s", "frac": byts / t / 1e9 / peak,
-                         "traffic": None, "kernel": "minsnap_solve_kernel<4,kStageSpline,6>", "note": "includes output allocation by torch (cached allocator)"}}
+                         "traffic": None, "kernel": "minsnap_solve_kernel<4,kStagePair,6>", "note": "includes output allocation by torch (cached allocator)"}}
 
 
 def emit(line: dict) -> None:

@@ -20,10 +20,11 @@ constexpr int kSolveThreads = 64;
 //                 a warp's 64-bit stores need the minimal 2 wavefronts) and leave the CTA after every spline, consecutive
 //                 threads writing consecutive doubles of the 192-byte (6-sector) chunk of each mission.  12.8 KB per CTA,
 //                 so residency is limited by registers only.
+//   kStagePair    the same with two splines per flush ([thread][49]): 384-byte chunks, i.e. whole 128-byte lines.
 //   kStageMission the whole mission ([thread][24 S + 1]) is staged and leaves as one contiguous tile (49.7 KB at S = 4).
 //   kDirect       per-thread stores straight from registers (S > 8: work arrays in local memory anyway).
 // Threads past the end of the batch run the solve on the last mission (they must reach the barriers) and store nothing.
-enum { kDirect = 0, kStageMission = 1, kStageSpline = 2 };
+enum { kDirect = 0, kStageMission = 1, kStageSpline = 2, kStagePair = 3 };
 
 template <int MAXS, int MODE, int MINB>
 __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_kernel(
@@ -51,6 +52,23 @@ __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_kernel(
           for (int e = threadIdx.x; e < n_here * 24; e += kSolveThreads) {
             const int m = e / 24, off = e - m * 24;
             gout[(size_t)m * per + seg * 24 + off] = s_out[m * 25 + off];
+          }
+          __syncthreads();
+        });
+  } else if constexpr (MODE == kStagePair) {
+    // two splines at a time: every mission leaves as 384-byte chunks = three whole 128-byte lines (mission stride 192 S bytes)
+    double* mine = s_out + (size_t)threadIdx.x * 49;
+    double* gout = coeffs_out + (size_t)base * per;
+    st = minsnap_solve_one<MAXS>(
+        S, velocity[bb], factor, loadw, [mine](int seg, int j, int ax, double val) { mine[(seg & 1) * 24 + j * 3 + ax] = val; }, storet,
+        [&](int seg) {
+          const bool last = seg == S - 1;
+          if (!(seg & 1) && !last) return;                 // uniform: S is the same for the whole launch
+          const int cnt = (seg & 1) ? 48 : 24, first = (seg & 1) ? seg - 1 : seg;
+          __syncthreads();
+          for (int e = threadIdx.x; e < n_here * cnt; e += kSolveThreads) {
+            const int m = e / cnt, off = e - m * cnt;
+            gout[(size_t)m * per + first * 24 + off] = s_out[m * 49 + off];
           }
           __syncthreads();
         });
@@ -355,7 +373,8 @@ __global__ void __launch_bounds__(128) table_hits_kernel(const double* __restric
 template <int MAXS, int MODE, int MINB>
 static int launch_solve(const double* w, const double* vel, int B, int S, double factor, double* c, double* t, int* st, cudaStream_t stream) {
   const size_t smem = MODE == kStageMission ? sizeof(double) * (size_t)kSolveThreads * (24 * S + 1)
-                                            : (MODE == kStageSpline ? sizeof(double) * (size_t)kSolveThreads * 25 : 0);
+                                            : (MODE == kStageSpline ? sizeof(double) * (size_t)kSolveThreads * 25
+                                               : (MODE == kStagePair ? sizeof(double) * (size_t)kSolveThreads * 49 : 0));
   if (smem > 48 * 1024)
     UAVB_CUDA_OK(cudaFuncSetAttribute(minsnap_solve_kernel<MAXS, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   minsnap_solve_kernel<MAXS, MODE, MINB><<<div_up(B, kSolveThreads), kSolveThreads, smem, stream>>>(w, vel, B, S, factor, c, t, st);
@@ -387,6 +406,7 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
         case 5: return launch_solve<4, kDirect, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
         case 6: return launch_solve<4, kDirect, 8>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
         case 7: return launch_solve<4, kStageSpline, 10>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 8: return launch_solve<4, kStagePair, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
         default: break;
       }
     }
@@ -395,7 +415,8 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
   if (S == 2) return launch_solve<2, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
   // S <= 4 (BASELINE configs[1]): 6 CTAs per SM (168 registers) measured fastest -- 0.216 ms per 10^6 solves against 0.250 ms
   // unconstrained (198 registers, 5 CTAs) and 0.238 ms at 8 CTAs (128 registers, spills); tools/k1_sweep.sh
-  if (S <= 4) return launch_solve<4, kStageSpline, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  // ... and staging two splines at a time (384-byte chunks = whole 128-byte lines, 25 KB per CTA) 0.198 ms against 0.2026 ms
+  if (S <= 4) return launch_solve<4, kStagePair, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
   if (S <= 8) return launch_solve<8, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
   return launch_solve<UAVB_MAX_SPLINES, kDirect, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
 }
