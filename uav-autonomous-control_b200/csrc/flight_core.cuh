@@ -354,15 +354,16 @@ template <class R> UAVB_HD void mix_and_limit(R pb, R qb, R rb, R coll, R lo, R 
     f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3;
   } else {
     const R m0 = s1 + rb, m1 = -(s2 + rb), m2 = rb - s1, m3 = s2 - rb;
-    const R room_hi = hi - coll, room_lo = lo - coll;
-    // ratio of quad.py:116-119 per rotor, as straight-line selects: a few lanes of a warp saturating must not cost the
-    // whole warp four branch diamonds.  (m < 0 || m > 0) is the ordered "not zero": a NaN moment keeps ratio 1.
-    auto ratio = [&](R m) {
-      const R l = M::div((m > R(0)) ? room_hi : room_lo, m);
-      return (m < R(0) || m > R(0)) ? l : R(1);
-    };
-    const R l0 = ratio(m0), l1 = ratio(m1), l2 = ratio(m2), l3 = ratio(m3);
-    const R s = clampr<R>(M::fmin(M::fmin(l0, l1), M::fmin(l2, l3)), R(0), R(1));
+    const R room_hi = hi - coll, room_lo = lo - coll;      // >= 0 and <= 0: coll is a clipped collective share
+    // ratios of quad.py:116-119: room_hi / m for m > 0, room_lo / m for m < 0, 1 for m = 0, and the scale is their minimum
+    // clipped to [0, 1].  With room_hi >= 0 >= room_lo the minimum over the positive moments is the ratio of the LARGEST one
+    // and the minimum over the negative moments that of the most negative one (room * (1/m) is monotonic in m on either
+    // side), so two reciprocals give the same bits as four.  Straight-line selects: a few lanes of a warp saturating must
+    // not cost the warp a chain of branches.  fmax / fmin drop NaN moments, which therefore keep ratio 1.
+    const R m_hi = M::fmax(M::fmax(m0, m1), M::fmax(m2, m3)), m_lo = M::fmin(M::fmin(m0, m1), M::fmin(m2, m3));
+    const R l_hi = (m_hi > R(0)) ? M::div(room_hi, m_hi) : R(1);
+    const R l_lo = (m_lo < R(0)) ? M::div(room_lo, m_lo) : R(1);
+    const R s = clampr<R>(M::fmin(l_hi, l_lo), R(0), R(1));
     f[0] = clampr<R>(M::fma(s, m0, coll), lo, hi);
     f[1] = clampr<R>(M::fma(s, m1, coll), lo, hi);
     f[2] = clampr<R>(M::fma(s, m2, coll), lo, hi);

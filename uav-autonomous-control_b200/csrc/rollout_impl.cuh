@@ -20,12 +20,20 @@
 
 namespace uavb {
 
-constexpr int kRolloutThreads = 64;
-// Residency: 8 CTAs of 64 threads per SM at a register cap of 128.  Registers are allocated per warp in units of 512
-// (16 per thread), so the reachable residencies are 8 / 10 / 12 CTAs at 128 / 96 / 80 registers; measured on B200
-// (DESIGN.md "K2 optimisation log") the spill-free 128-register body with 16 warps per SM sustains the highest tick rate
-// (139 vs 126 G ticks/s for 12 CTAs at 80 registers, 5e5 rollouts), so it is the only variant that is compiled.
-constexpr int kRolloutCtasPerSm = 8;
+// CTA shapes at the register cap of 128 (registers are allocated per warp in units of 512 = 16 per thread, so 16 warps per SM;
+// measured on B200 -- DESIGN.md "K2 optimisation log" -- the spill-free 128-register body with 16 warps per SM sustains the
+// highest tick rate, so it is the only variant that is compiled):
+//   * metrics-only fp32 rollouts: ONE warp per CTA, 16 CTAs per SM.  A work item ends with a CTA barrier, and with
+//     per-rollout missions the warps of a CTA do different amounts of work (obstacle watching, rotor saturation): a second warp
+//     only adds waiting at that barrier (ncu: 4.9 % of the warp samples of BASELINE configs[3] with 2 warps per CTA).
+//   * rollouts with a state log: 64 threads, 8 CTAs per SM -- a CTA writes 256 contiguous bytes per field and sample, which
+//     the DRAM pages like better than 128 (5.0 vs 4.7 TB/s of log writes).
+//   * fp64 validation build: 64 threads.
+constexpr int kRolloutThreads = 32;
+constexpr int kRolloutCtasPerSm = 16;
+constexpr int kRolloutThreadsLog = 64;
+constexpr int kRolloutCtasPerSmLog = 8;
+constexpr int kRolloutThreadsF64 = 64;
 constexpr int kRolloutRegs = 128;
 
 template <class R> struct RolloutDev {
@@ -175,7 +183,7 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
   if (p.coeff_cache_offset >= 0) {             // on-the-fly evaluation: this thread's column of the CTA's coefficient staging area
     extern __shared__ double s_dyn_f64[];
     m.cache = s_dyn_f64 + p.coeff_cache_offset + threadIdx.x;
-    m.cache_stride = kRolloutThreads;
+    m.cache_stride = (int)blockDim.x;
   }
 
   Drone<R> d;

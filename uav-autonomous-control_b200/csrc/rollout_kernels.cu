@@ -124,29 +124,30 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   McValues mc;
   mc_from_vehicle(mc, a->veh);
   make_vehp<R>(p.vp, a->veh, mc);
-  const int grid = div_up(a->B, kRolloutThreads);
+  const bool log = a->log_stride > 0;
+  const int threads = sizeof(R) == 8 ? kRolloutThreadsF64 : (log ? kRolloutThreadsLog : kRolloutThreads);
+  const int grid = div_up(a->B, threads);
   size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
   p.coeff_cache_offset = -1;
   const bool from_table = a->shared_targets != nullptr && a->mission_seg_begin == nullptr;
   if (!from_table && sizeof(R) == 4) {                            // fp32 kernels stage the current spline in shared memory
     smem = (smem + 7) / 8 * 8;
     p.coeff_cache_offset = (int)(smem / 8);
-    smem += sizeof(double) * 24 * kRolloutThreads;
+    smem += sizeof(double) * 24 * threads;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool mc_any = a->mc_mass || a->mc_inertia || a->mc_gains || a->mc_wind;
-  const bool log = a->log_stride > 0;
   if constexpr (sizeof(R) == 8) {                      // validation build
     launch_rollout_f64(log, mc_any, grid, smem, st, p);
   } else {
     int sms = 0;
     rc = sm_count_cached(&sms);
     if (rc) return rc;
-    // fp32 launches ALWAYS run the time-sliced persistent kernel (8 CTAs x 64 drones per SM, 128 registers), with a single
+    // fp32 launches ALWAYS run the time-sliced persistent kernel (16 warps per SM at 128 registers, CTA shapes in rollout_impl.cuh), with a single
     // slice when slicing has nothing to gain; a state log is written slice by slice into its place.  One compiled body for every batch size keeps
     // per-rollout results independent of how a job is sharded (ptxas fuses mul+add differently under different register
     // caps, so differently compiled variants are NOT bit-identical to each other).
-    const int slots = sms * kRolloutCtasPerSm;
+    const int slots = sms * (log ? kRolloutCtasPerSmLog : kRolloutCtasPerSm);
     // ~32 items per resident CTA keep the tail near 3 % of the launch; slices are whole outer periods of >= 100 ticks
     constexpr int kMinChunkTicks = 100;
     long long want = grid > slots ? (32LL * slots + grid - 1) / grid : 1;
