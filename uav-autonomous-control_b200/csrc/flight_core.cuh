@@ -22,7 +22,10 @@
 // the kernel parameter block (constant-bank operands, no registers), products of constants are
 // folded on the host (kf dt/m, dt/I, arm kf ...), the gyroscopic term uses the diagonal-inertia
 // identity w x (I w) = ((Iz-Iy) wy wz, (Ix-Iz) wz wx, (Iy-Ix) wx wy), the allocation takes a
-// division-free path whenever no rotor limit binds, sqrt/rcp/rsqrt are single MUFU instructions.
+// division-free path whenever no rotor limit binds, sqrt/rcp/rsqrt are single MUFU instructions, and the
+// persistent rollout's tick (inner_tick) works in "rotor units" -- moments / (4 arm kf), forces / kf -- so the
+// mixer, the limits and the rotor speed commands need no scaling; the SI forms of the same stages serve the
+// stage kernels (one controller / vehicle method per launch).
 #pragma once
 
 #include <math.h>
