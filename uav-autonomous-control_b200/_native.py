@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libuavb.so")
 
 N_GAINS = 11
 N_METRICS = 8
+ABI_VERSION = 111          # UAVB_VERSION of include/uavb.h this module's struct mirrors were written against
 CARRY_WORDS = 52
 STATE_DIM = 13
 MAX_SPLINES = 64
@@ -101,6 +102,8 @@ def lib() -> ctypes.CDLL:
                         "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
     L = ctypes.CDLL(LIB_PATH)
     L.uavb_version.restype = c_int
+    if L.uavb_version() != ABI_VERSION:
+        raise UavbError(f"libuavb.so reports ABI {L.uavb_version()}, this package expects {ABI_VERSION}: rebuild with uav-autonomous-control_b200/build.py")
     L.uavb_last_error.restype = c_char_p
     L.uavb_device_count.restype = c_int
     L.uavb_device_info.argtypes = [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]
