@@ -79,8 +79,8 @@ class RRTStar:
             obs = torch.as_tensor(np.asarray(self.obstacles, dtype=float).reshape(-1, 6), **f64).contiguous()
         L = nat.lib()
         ws = torch.empty(int(L.uavb_rrt_workspace_bytes(B, self.max_iterations)), dtype=torch.uint8, device=dev)
-        path = torch.zeros((B, self.max_path, 3), **f64)
-        simple = torch.zeros((B, self.max_path, 3), **f64)
+        path = torch.empty((B, self.max_path, 3), **f64)           # rows [0, plen) / [0, slen) are written by the kernel
+        simple = torch.empty((B, self.max_path, 3), **f64)
         plen = torch.zeros(B, dtype=torch.int32, device=dev)
         slen = torch.zeros(B, dtype=torch.int32, device=dev)
         cost = torch.empty(B, **f64)
@@ -91,7 +91,10 @@ class RRTStar:
                                       self.max_path, nat.ptr(plen), nat.ptr(simple), nat.ptr(slen), nat.ptr(cost), nat.ptr(status), nat.ptr(stats),
                                       nat.stream_ptr(dev)), "uavb_rrt_star_f64")
         torch.cuda.synchronize(dev)
-        path, simple, plen, slen = path.cpu().numpy(), simple.cpu().numpy(), plen.cpu().numpy(), slen.cpu().numpy()
+        plen, slen = plen.cpu().numpy(), slen.cpu().numpy()
+        # only the used prefix of the path buffers travels to the host (B x max_path x 24 bytes each otherwise)
+        pmax, smax = int(plen.max(initial=0)), int(slen.max(initial=0))
+        path, simple = path[:, :pmax].cpu().numpy(), simple[:, :smax].cpu().numpy()
         self.status, self.cost, self.stats = status.cpu().numpy(), cost.cpu().numpy(), stats.cpu().numpy()
         paths = [path[b, :plen[b]] for b in range(B)]
         simples = [simple[b, :slen[b]] for b in range(B)]
