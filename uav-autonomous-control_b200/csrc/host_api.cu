@@ -33,6 +33,24 @@ struct DevPool {
   }
 };
 
+// The stream of the host-buffer calls: one per host thread and device, created on first use and kept for the life of the
+// thread (creating and destroying a stream costs ~55 + ~65 us on the B200 box, 2 % of a 5.7 ms mission call).  Never
+// destroyed explicitly: at thread / process exit the context owns it.
+static cudaError_t host_call_stream(cudaStream_t* out) {
+  constexpr int kMaxDevices = 64;
+  thread_local cudaStream_t streams[kMaxDevices] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (streams[dev] == nullptr) {
+    e = cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+    if (e != cudaSuccess) { streams[dev] = nullptr; return e; }
+  }
+  *out = streams[dev];
+  return cudaSuccess;
+}
+
 }  // namespace uavb
 
 using namespace uavb;
@@ -56,7 +74,7 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
   const double dt_outer = m->veh.dt * m->frequency;
 
   cudaStream_t st = nullptr;
-  UAVB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  UAVB_CUDA_OK(host_call_stream(&st));
   int result = UAVB_OK;
   {
     DevPool pool(st);
@@ -135,7 +153,6 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
       }
     }
   }
-  cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
+  cudaStreamSynchronize(st);                               // also on the failing paths: nothing of this call is in flight afterwards
   return result;
 }
