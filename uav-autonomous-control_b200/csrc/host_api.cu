@@ -33,21 +33,31 @@ struct DevPool {
   }
 };
 
-// The stream of the host-buffer calls: one per host thread and device, created on first use and kept for the life of the
-// thread (creating and destroying a stream costs ~55 + ~65 us on the B200 box, 2 % of a 5.7 ms mission call).  Never
-// destroyed explicitly: at thread / process exit the context owns it.
-static cudaError_t host_call_stream(cudaStream_t* out) {
+// Streams and events of the host-buffer calls: one set per host thread and device, created on first use and kept for the
+// life of the thread (creating and destroying a stream costs ~55 + ~65 us on the B200 box, 2 % of a 5.7 ms mission call).
+// Never destroyed explicitly: at thread / process exit the context owns them.
+//   st        everything except the bulk uploads
+//   st_up     the per-rollout inputs (the bulk of the host->device bytes): they travel while the mission is planned on `st`
+//   ev_alloc  `st` -> `st_up`: the upload buffers exist;  ev_up  `st_up` -> `st`: the uploads are complete
+struct HostCallSet {
+  cudaStream_t st = nullptr, st_up = nullptr;
+  cudaEvent_t ev_alloc = nullptr, ev_up = nullptr;
+};
+
+static cudaError_t host_call_set(HostCallSet** out) {
   constexpr int kMaxDevices = 64;
-  thread_local cudaStream_t streams[kMaxDevices] = {};
+  thread_local HostCallSet sets[kMaxDevices];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-  if (streams[dev] == nullptr) {
-    e = cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
-    if (e != cudaSuccess) { streams[dev] = nullptr; return e; }
-  }
-  *out = streams[dev];
+  HostCallSet& h = sets[dev];
+  if (h.st == nullptr) e = cudaStreamCreateWithFlags(&h.st, cudaStreamNonBlocking);
+  if (e == cudaSuccess && h.st_up == nullptr) e = cudaStreamCreateWithFlags(&h.st_up, cudaStreamNonBlocking);
+  if (e == cudaSuccess && h.ev_alloc == nullptr) e = cudaEventCreateWithFlags(&h.ev_alloc, cudaEventDisableTiming);
+  if (e == cudaSuccess && h.ev_up == nullptr) e = cudaEventCreateWithFlags(&h.ev_up, cudaEventDisableTiming);
+  if (e != cudaSuccess) return e;
+  *out = &h;
   return cudaSuccess;
 }
 
@@ -73,11 +83,32 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
   const size_t B = (size_t)m->B;
   const double dt_outer = m->veh.dt * m->frequency;
 
-  cudaStream_t st = nullptr;
-  UAVB_CUDA_OK(host_call_stream(&st));
+  HostCallSet* hs = nullptr;
+  UAVB_CUDA_OK(host_call_set(&hs));
+  cudaStream_t st = hs->st, st_up = hs->st_up;
   int result = UAVB_OK;
   {
     DevPool pool(st);
+    // per-rollout inputs: allocated in `st` order, copied on `st_up` while the plan below runs and its results travel back
+    const bool have_mc = m->mc_mass || m->mc_inertia || m->mc_gains || m->mc_wind;
+    bool uploads_in_flight = false;
+    float* d_mc_mass = nullptr; float* d_mc_inertia = nullptr; float* d_mc_gains = nullptr; float* d_mc_wind = nullptr;
+    if (have_mc && B > 0) {
+      if (m->mc_mass) d_mc_mass = pool.alloc<float>(B);
+      if (m->mc_inertia) d_mc_inertia = pool.alloc<float>(3 * B);
+      if (m->mc_gains) d_mc_gains = pool.alloc<float>((size_t)UAVB_N_GAINS * B);
+      if (m->mc_wind) d_mc_wind = pool.alloc<float>(3 * B);
+      cudaError_t e = pool.err;
+      if (e == cudaSuccess) e = cudaEventRecord(hs->ev_alloc, st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st_up, hs->ev_alloc, 0);
+      if (e == cudaSuccess) uploads_in_flight = true;
+      if (e == cudaSuccess && d_mc_mass) e = cudaMemcpyAsync(d_mc_mass, m->mc_mass, sizeof(float) * B, cudaMemcpyHostToDevice, st_up);
+      if (e == cudaSuccess && d_mc_inertia) e = cudaMemcpyAsync(d_mc_inertia, m->mc_inertia, sizeof(float) * 3 * B, cudaMemcpyHostToDevice, st_up);
+      if (e == cudaSuccess && d_mc_gains) e = cudaMemcpyAsync(d_mc_gains, m->mc_gains, sizeof(float) * UAVB_N_GAINS * B, cudaMemcpyHostToDevice, st_up);
+      if (e == cudaSuccess && d_mc_wind) e = cudaMemcpyAsync(d_mc_wind, m->mc_wind, sizeof(float) * 3 * B, cudaMemcpyHostToDevice, st_up);
+      if (e == cudaSuccess) e = cudaEventRecord(hs->ev_up, st_up);
+      if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
+    }
     double* d_wp = pool.upload(m->waypoints, (size_t)m->n_waypoints * 3);
     const double vel2[2] = {m->velocity, m->velocity};
     double* d_vel = pool.upload(vel2, 2);
@@ -122,10 +153,7 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
       a.B = m->B; a.n_ticks = n_ticks; a.inner_per_outer = m->frequency; a.thrust_frame_lag = m->thrust_frame_lag;
       a.n_obs = m->n_obs; a.n_obs_sets = m->n_obs > 0 ? 1 : 0;
       a.veh = m->veh;
-      a.mc_mass = pool.upload(m->mc_mass, B);
-      a.mc_inertia = pool.upload(m->mc_inertia, 3 * B);
-      a.mc_gains = pool.upload(m->mc_gains, UAVB_N_GAINS * B);
-      a.mc_wind = pool.upload(m->mc_wind, 3 * B);
+      a.mc_mass = d_mc_mass; a.mc_inertia = d_mc_inertia; a.mc_gains = d_mc_gains; a.mc_wind = d_mc_wind;
       a.seg_coeffs = d_coeffs; a.seg_rows = d_rows;
       a.seg_table = pool.upload(seg_table.data(), n_seg);
       a.seg_yaw0 = pool.upload(seg_yaw0.data(), n_seg);
@@ -144,6 +172,10 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
       float* d_state = state_out ? pool.alloc<float>(B * UAVB_STATE_DIM) : nullptr;
       a.metrics_out = d_metrics; a.state_out = d_state;
       if (pool.err != cudaSuccess) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
+      if (!result && uploads_in_flight) {                    // the rollout reads what `st_up` wrote
+        const cudaError_t e = cudaStreamWaitEvent(st, hs->ev_up, 0);
+        if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
+      }
       if (!result) result = uavb_rollout_f32(&a, st);
       if (!result && B > 0) {
         cudaError_t e = cudaMemcpyAsync(metrics_out, d_metrics, sizeof(float) * B * UAVB_N_METRICS, cudaMemcpyDeviceToHost, st);
@@ -152,6 +184,8 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
         if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
       }
     }
+    // every path, also the failing ones: the pool's destructor (next brace) frees in `st` order, so the uploads must be over
+    if (uploads_in_flight) cudaStreamSynchronize(st_up);
   }
   cudaStreamSynchronize(st);                               // also on the failing paths: nothing of this call is in flight afterwards
   return result;
