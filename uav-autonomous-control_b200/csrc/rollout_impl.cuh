@@ -15,26 +15,32 @@
 #pragma once
 
 #include "rollout_core.cuh"
+#include "rollout_pair.cuh"
 #include "uavb_common.cuh"
 #include "veh_setup.cuh"
 
 namespace uavb {
 
-// CTA shapes at the register cap of 128 (registers are allocated per warp in units of 512 = 16 per thread, so 16 warps per SM;
-// measured on B200 -- DESIGN.md "K2 optimisation log" -- the spill-free 128-register body with 16 warps per SM sustains the
-// highest tick rate, so it is the only variant that is compiled):
-//   * metrics-only fp32 rollouts: ONE warp per CTA, 16 CTAs per SM.  A work item ends with a CTA barrier, and with
+// CTA shapes of the fp32 production rollout (two drones per thread, rollout_pair.cuh).  A pair needs ~200 registers, so the
+// cap is 255 and an SM holds 8 warps = 512 drones -- the same number of drones in flight as the scalar kernel had with 16
+// warps at 128 registers -- and two warps per scheduler fill the FMA pipe with packed instructions (measured,
+// profiles/r02_ffma2_probe.md: 94 % at two independent chains per warp).
+//   * metrics-only rollouts: ONE warp per CTA (64 drones), 8 CTAs per SM.  A work item ends with a CTA barrier, and with
 //     per-rollout missions the warps of a CTA do different amounts of work (obstacle watching, rotor saturation): a second warp
-//     only adds waiting at that barrier (ncu: 4.9 % of the warp samples of BASELINE configs[3] with 2 warps per CTA).
-//   * rollouts with a state log: 64 threads, 8 CTAs per SM -- a CTA writes 256 contiguous bytes per field and sample, which
-//     the DRAM pages like better than 128 (5.0 vs 4.7 TB/s of log writes).
-//   * fp64 validation build: 64 threads.
+//     only adds waiting at that barrier.
+//   * rollouts with a state log: 64 threads (128 drones), 4 CTAs per SM -- a CTA writes 512 contiguous bytes per field and sample.
+//   * fp64 validation build: one drone per thread, 64 threads, one-shot launch, 128 registers.
+#ifndef UAVB_PAIR_REGS
+#define UAVB_PAIR_REGS 255
+#endif
+constexpr int kRolloutPairRegs = UAVB_PAIR_REGS;      // fp32 production build
+constexpr int kPairWarpsPerSm = 65536 / (32 * ((UAVB_PAIR_REGS + 15) / 16 * 16));   // registers are allocated in units of 16 per thread
 constexpr int kRolloutThreads = 32;
-constexpr int kRolloutCtasPerSm = 16;
+constexpr int kRolloutCtasPerSm = kPairWarpsPerSm;
 constexpr int kRolloutThreadsLog = 64;
-constexpr int kRolloutCtasPerSmLog = 8;
+constexpr int kRolloutCtasPerSmLog = kPairWarpsPerSm / 2;
 constexpr int kRolloutThreadsF64 = 64;
-constexpr int kRolloutRegs = 128;
+constexpr int kRolloutRegs = 128;          // fp64 validation build
 
 template <class R> struct RolloutDev {
   uavb_rollout_args a;
@@ -262,6 +268,156 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
   }
 }
 
+// Per-rollout constants of drone i (Monte-Carlo overrides applied).
+template <class R> __device__ __forceinline__ void load_vehp(VehP<R>& v, const uavb_rollout_args& a, long long i) {
+  const long long B = a.B;
+  McValues mc;
+  mc_from_vehicle(mc, a.veh);
+  if (a.mc_mass) mc.mass = (double)a.mc_mass[i];
+  if (a.mc_inertia) { mc.inertia[0] = (double)a.mc_inertia[i]; mc.inertia[1] = (double)a.mc_inertia[B + i]; mc.inertia[2] = (double)a.mc_inertia[2 * B + i]; }
+  if (a.mc_gains) {
+#pragma unroll
+    for (int k = 0; k < UAVB_N_GAINS; ++k) mc.gains[k] = (double)a.mc_gains[k * B + i];
+  }
+  if (a.mc_wind) { mc.wind[0] = (double)a.mc_wind[i]; mc.wind[1] = (double)a.mc_wind[B + i]; mc.wind[2] = (double)a.mc_wind[2 * B + i]; }
+  make_vehp<R>(v, a.veh, mc);
+}
+
+__device__ __forceinline__ void mission_view(MissionView& m, const RolloutDev<float>& p, long long i, int column, int columns) {
+  const uavb_rollout_args& a = p.a;
+  m.coeffs = a.seg_coeffs; m.rows = a.seg_rows; m.table = a.seg_table; m.yaw0 = a.seg_yaw0;
+  m.seg_begin = a.mission_seg_begin ? a.mission_seg_begin[i] : 0;
+  m.seg_count = a.mission_seg_count ? a.mission_seg_count[i] : a.n_seg_shared;
+  m.dt_outer = a.dt_outer;
+  m.trows = a.mission_seg_begin ? nullptr : static_cast<const TargetRow*>(a.shared_targets);
+  m.n_trows = a.n_target_rows;
+  m.cache = nullptr; m.cache_stride = 0;
+  if (p.coeff_cache_offset >= 0) {             // on-the-fly evaluation: this drone's column of the CTA's coefficient staging area
+    extern __shared__ double s_dyn_f64[];
+    m.cache = s_dyn_f64 + p.coeff_cache_offset + column;
+    m.cache_stride = columns;
+  }
+}
+
+// Final outputs of one drone (state, metrics) -- shared by the pair path; same values as drone_slice's epilogue.
+__device__ __forceinline__ void write_outputs(const uavb_rollout_args& a, long long i, Drone<float>& d, const Cursor<float>& c,
+                                              const Accum<float>& acc, bool log) {
+  const long long B = a.B;
+  const double fx = d.px + (double)d.dx, fy = d.py + (double)d.dy, fz = d.pz + (double)d.dz;
+  if (a.state_out) {
+    float* o = reinterpret_cast<float*>(a.state_out) + i;
+    o[0 * B] = (float)fx; o[1 * B] = (float)fy; o[2 * B] = (float)fz;
+    if (!log && c.phase != 0) renormalise_q<float>(d);       // the reported state is unit even in the middle of an outer period
+    o[3 * B] = d.q0; o[4 * B] = d.q1; o[5 * B] = d.q2; o[6 * B] = d.q3;
+    o[7 * B] = d.vx; o[8 * B] = d.vy; o[9 * B] = d.vz;
+    o[10 * B] = d.wx; o[11 * B] = d.wy; o[12 * B] = d.wz;
+  }
+  if (a.metrics_out) {
+    float fd = 0.f;
+    if (a.goal) {
+      const double* g = a.goal + (size_t)a.goal_stride * i;
+      const float ex = (float)(g[0] - fx), ey = (float)(g[1] - fy), ez = (float)(g[2] - fz);
+      fd = Math<float>::sqrt(ex * ex + ey * ey + ez * ez);
+    }
+    const float np = acc.periods > 0 ? 1.f / (float)acc.periods : 0.f;
+    float* o = reinterpret_cast<float*>(a.metrics_out) + (size_t)i * UAVB_N_METRICS;
+    o[UAVB_M_FINAL_DIST] = fd;
+    o[UAVB_M_COLLISION] = (float)acc.collided;
+    o[UAVB_M_RMSE] = Math<float>::sqrt(acc.sum_e2 * np);
+    o[UAVB_M_MEAN_ERR] = acc.sum_e * np;
+    o[UAVB_M_MAX_ERR] = acc.max_e;
+    o[UAVB_M_STATUS] = (float)acc.status;
+    o[UAVB_M_FIRST_HIT] = (float)acc.first_hit;
+    o[UAVB_M_PERIODS] = (float)acc.periods;
+  }
+}
+
+// One PAIR of drones (2j, 2j+1), one slice of their mission: the production fp32 path (rollout_pair.cuh).  Arguments as
+// drone_slice.  When B is odd the last pair's second lane re-flies the first drone and writes nothing.
+template <bool LOG, bool MC, bool TABLE>
+__device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long j, int n_ticks, bool from_carry, bool to_carry,
+                                           bool finish, int launch_tick0) {
+  const uavb_rollout_args& a = p.a;
+  const long long B = a.B;
+  const long long i0 = 2 * j;
+  const bool second = i0 + 1 < B;
+  const long long i1 = second ? i0 + 1 : i0;
+  const bool shared_boxes = a.n_obs > 0 && a.aabb_set == nullptr;
+  const VehU<float>& u = p.u;
+
+  VehP<float> vloc[2];
+  VehP2 v2;
+  if constexpr (MC) {
+    load_vehp<float>(vloc[0], a, i0);
+    load_vehp<float>(vloc[1], a, i1);
+    zip_vehp(v2, vloc[0], vloc[1]);
+  }
+  const VehP<float>& va = MC ? vloc[0] : p.vp;
+  const VehP<float>& vb = MC ? vloc[1] : p.vp;
+
+  MissionView ma, mb;
+  mission_view(ma, p, i0, 2 * (int)threadIdx.x, 2 * (int)blockDim.x);
+  mission_view(mb, p, i1, 2 * (int)threadIdx.x + 1, 2 * (int)blockDim.x);
+
+  Drone2 d;
+  Cursor<float> c[2];
+  Accum<float> acc[2];
+  int tick0 = 0;
+  if (from_carry) {
+    Drone<float> s;
+    Carry{a.carry + i0, B}.load(s, c[0], acc[0], u, &tick0);
+    put_lane<0>(d, s);
+    Carry{a.carry + i1, B}.load(s, c[1], acc[1], u, &tick0);
+    put_lane<1>(d, s);
+  } else {
+    Drone<float> s;
+    const double* s0 = a.start + (size_t)a.start_stride * i0;
+    drone_init<float>(s, u, s0[0], s0[1], s0[2]);
+    put_lane<0>(d, s);
+    const double* s1 = a.start + (size_t)a.start_stride * i1;
+    drone_init<float>(s, u, s1[0], s1[1], s1[2]);
+    put_lane<1>(d, s);
+    cursor_init<float>(c[0]); cursor_init<float>(c[1]);
+    accum_init<float>(acc[0]); accum_init<float>(acc[1]);
+  }
+
+  auto fly = [&](const auto& oa, const auto& ob) {
+    auto with_log = [&](auto& lg) {
+      if constexpr (MC) rollout_run_pair<TABLE>(d, c, acc, u, va, vb, v2, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
+      else rollout_run_pair<TABLE>(d, c, acc, u, va, vb, p.vp, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
+    };
+    if constexpr (LOG) {
+      PairLog lg;
+      lg.out = reinterpret_cast<float*>(a.log_out) + (size_t)(launch_tick0 / a.log_stride) * 13 * B + i0;
+      lg.B = (unsigned)B; lg.stride = a.log_stride; lg.left = a.log_stride - launch_tick0 % a.log_stride;
+      lg.vec = (B & 1) == 0; lg.second = second;
+      with_log(lg);
+    } else {
+      NoPairLog lg;
+      with_log(lg);
+    }
+  };
+  if (a.n_obs > 0) {
+    if (shared_boxes) {
+      fly(BoxesT<true>{nullptr, a.n_obs}, BoxesT<true>{nullptr, a.n_obs});
+    } else {
+      fly(BoxesT<false>{a.aabbs + (size_t)a.aabb_set[i0] * a.n_obs * 6, a.n_obs}, BoxesT<false>{a.aabbs + (size_t)a.aabb_set[i1] * a.n_obs * 6, a.n_obs});
+    }
+  } else {
+    fly(NoObstacles{}, NoObstacles{});
+  }
+
+  Drone<float> s;
+  get_lane<0>(d, s);
+  if (to_carry) Carry{a.carry + i0, B}.store(s, c[0], acc[0], tick0 + n_ticks);
+  if (finish) write_outputs(a, i0, s, c[0], acc[0], LOG);
+  if (second) {
+    get_lane<1>(d, s);
+    if (to_carry) Carry{a.carry + i1, B}.store(s, c[1], acc[1], tick0 + n_ticks);
+    if (finish) write_outputs(a, i1, s, c[1], acc[1], LOG);
+  }
+}
+
 __device__ __forceinline__ void stage_shared_boxes(const uavb_rollout_args& a, float* s_boxes) {
   if (a.n_obs > 0 && a.aabb_set == nullptr) {
     for (int j = threadIdx.x; j < a.n_obs * 6; j += blockDim.x) s_boxes[j] = a.aabbs[j];
@@ -308,7 +464,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 template <bool MC, bool TABLE, bool LOG>
-__global__ void __maxnreg__(kRolloutRegs) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
+__global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
   extern __shared__ float s_boxes[];
   __shared__ int s_item;
   stage_shared_boxes(p.a, s_boxes);
@@ -326,11 +482,11 @@ __global__ void __maxnreg__(kRolloutRegs) rollout_sliced_kernel(const __grid_con
     const int it = s_item;
     if (it >= n_items) return;
     const int c = it / sch.n_groups, g = it - c * sch.n_groups;
-    const long long i = (long long)g * blockDim.x + threadIdx.x;
-    if (i < p.a.B) {
+    const long long j = (long long)g * blockDim.x + threadIdx.x;        // pair index: drones 2j, 2j+1
+    if (2 * j < p.a.B) {
       const bool last = c == sch.n_chunks - 1;
       const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
-      drone_slice<float, LOG, MC, TABLE>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
+      pair_slice<LOG, MC, TABLE>(p, j, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
     }
     __threadfence();
     __syncthreads();

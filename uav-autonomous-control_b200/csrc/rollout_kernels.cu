@@ -126,14 +126,16 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   make_vehp<R>(p.vp, a->veh, mc);
   const bool log = a->log_stride > 0;
   const int threads = sizeof(R) == 8 ? kRolloutThreadsF64 : (log ? kRolloutThreadsLog : kRolloutThreads);
-  const int grid = div_up(a->B, threads);
+  // fp32: a thread flies a PAIR of drones (rollout_pair.cuh), so a CTA (= one work group of the slice scheduler) covers 2 x threads
+  const int per_cta = sizeof(R) == 8 ? threads : 2 * threads;
+  const int grid = div_up(a->B, per_cta);
   size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
   p.coeff_cache_offset = -1;
   const bool from_table = a->shared_targets != nullptr && a->mission_seg_begin == nullptr;
   if (!from_table && sizeof(R) == 4) {                            // fp32 kernels stage the current spline in shared memory
     smem = (smem + 7) / 8 * 8;
     p.coeff_cache_offset = (int)(smem / 8);
-    smem += sizeof(double) * 24 * threads;
+    smem += sizeof(double) * 24 * per_cta;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool mc_any = a->mc_mass || a->mc_inertia || a->mc_gains || a->mc_wind;
