@@ -139,6 +139,7 @@ template <class R> UAVB_HD R clampr(R x, R lo, R hi) { return Math<R>::fmin(Math
 // its parameter block, so every field is a constant-bank operand.
 template <class R> struct VehU {
   R dt, half_dt, half_dt_sq, dt_outer, g;
+  R half_dt_cu3, small_rot_wn2;                    // (dt/2)^3 / 3 and the |w|^2 below which the pair tick's two-term tan series holds (flight_pair.cuh)
   R kf, inv_kf, arm_kf, kappa_kf;                  // arm*kf, kappa*kf: torque per unit of summed w^2
   R inv_arm4, inv_kappa4;                          // 1/(4 arm), 1/(4 kappa): mixer division by 4 folded in (quad.py:112)
   R fmin, fmax, fmin4, fmax4, a_rise, a_fall;      // a_* = 1 - exp(-dt/tau) (quad.py:102)

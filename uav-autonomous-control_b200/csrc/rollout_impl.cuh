@@ -354,6 +354,8 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
   }
   const VehP<float>& va = MC ? vloc[0] : p.vp;
   const VehP<float>& vb = MC ? vloc[1] : p.vp;
+  VehO2 vo;
+  zip_veho(vo, va, vb);
 
   MissionView ma, mb;
   mission_view(ma, p, i0, 2 * (int)threadIdx.x, 2 * (int)blockDim.x);
@@ -366,25 +368,25 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
   if (from_carry) {
     Drone<float> s;
     Carry{a.carry + i0, B}.load(s, c[0], acc[0], u, &tick0);
-    put_lane<0>(d, s);
+    put_lane<0>(d, s, u);
     Carry{a.carry + i1, B}.load(s, c[1], acc[1], u, &tick0);
-    put_lane<1>(d, s);
+    put_lane<1>(d, s, u);
   } else {
     Drone<float> s;
     const double* s0 = a.start + (size_t)a.start_stride * i0;
     drone_init<float>(s, u, s0[0], s0[1], s0[2]);
-    put_lane<0>(d, s);
+    put_lane<0>(d, s, u);
     const double* s1 = a.start + (size_t)a.start_stride * i1;
     drone_init<float>(s, u, s1[0], s1[1], s1[2]);
-    put_lane<1>(d, s);
+    put_lane<1>(d, s, u);
     cursor_init<float>(c[0]); cursor_init<float>(c[1]);
     accum_init<float>(acc[0]); accum_init<float>(acc[1]);
   }
 
   auto fly = [&](const auto& oa, const auto& ob) {
     auto with_log = [&](auto& lg) {
-      if constexpr (MC) rollout_run_pair<TABLE>(d, c, acc, u, va, vb, v2, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
-      else rollout_run_pair<TABLE>(d, c, acc, u, va, vb, p.vp, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
+      if constexpr (MC) rollout_run_pair<TABLE>(d, c, acc, u, va, vb, v2, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
+      else rollout_run_pair<TABLE>(d, c, acc, u, va, vb, p.vp, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
     };
     if constexpr (LOG) {
       PairLog lg;

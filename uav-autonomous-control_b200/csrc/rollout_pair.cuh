@@ -1,7 +1,7 @@
 // rollout_pair.cuh -- the fp32 production rollout, two drones per thread: thread j of the launch flies drones 2j and
 // 2j+1 in the two lanes of float2 registers (flight_pair.cuh: the 1 kHz tick in packed fp32x2 instructions); the 100 Hz
-// outer loop, the table cursor, the metrics and the collision flag are the scalar code of rollout_core.cuh run once per
-// lane.  Both drones of a pair tick in lock-step (same tick count, same outer/inner schedule, main.py:37-45), so the
+// outer loop is its packed restatement (outer_update_pair); the table cursor, the fp64 set-point evaluation and fold, and
+// the collision flag are the scalar code of rollout_core.cuh run once per lane.  Both drones of a pair tick in lock-step (same tick count, same outer/inner schedule, main.py:37-45), so the
 // schedule below is rollout_run's with every per-drone step done twice.
 //
 // A pair's two rollouts never mix: each lane runs exactly the operation sequence a lone drone would, so per-rollout
@@ -47,32 +47,38 @@ struct NoPairLog {
   UAVB_DEV void tick(const Drone2&) {}
 };
 
-// Outer update of lane L (TrajectoryController._update_outer_loop, main.py:47-61) on the fresh state of that drone.
-template <int L, bool TABLE> UAVB_DEV void pair_outer(Drone2& d, Cursor<float>& c, const VehU<float>& u, const VehP<float>& v,
-                                                     const MissionView& m, const Target<float>* shared_t) {
-  Target<float> t;
-  if constexpr (TABLE) {
-    t = *shared_t;                                           // shared mission: one row for both lanes
-  } else {
-    cursor_target<float>(c, m, &t);
-    cursor_advance(&c.seg, &c.row, m);
+// Set-points of the coming outer period and the position errors (set-point - position, fp64, rounded once): one table row
+// for both lanes of a shared mission, otherwise each lane's own cursor.
+template <bool TABLE> struct PairTarget;
+template <> struct PairTarget<true> {
+  typedef float T;
+  static UAVB_DEV void fetch(const Drone2& d, Cursor<float> (&c)[2], const MissionView& ma, const MissionView&, Target2<float>& t2, V2& ex, V2& ey, V2& ez) {
+    Target<float> t;
+    table_target<float>(ma.trows, c[0].row, &t);
+    if (c[0].row + 1 < ma.n_trows) ++c[0].row;               // index clamp of main.py:61
+    c[1].row = c[0].row;
+    t2.vx = t.vx; t2.vy = t.vy; t2.vz = t.vz; t2.ax = t.ax; t2.ay = t.ay; t2.az = t.az; t2.yc = t.yc; t2.ys = t.ys;
+    ex = make_float2((float)(t.x - d.px[0]), (float)(t.x - d.px[1]));
+    ey = make_float2((float)(t.y - d.py[0]), (float)(t.y - d.py[1]));
+    ez = make_float2((float)(t.z - d.pz[0]), (float)(t.z - d.pz[1]));
   }
-  c.ex = (float)(t.x - d.px[L]); c.ey = (float)(t.y - d.py[L]); c.ez = (float)(t.z - d.pz[L]);   // the position is folded here
-  Drone<float> s;
-  get_lane<L>(d, s);
-  outer_update<float>(s, u, v, t, c.ex, c.ey, c.ez);
-  put_lane_commands<L>(d, s);
-}
-
-// End of an outer period for lane L: tracking error |set-point - p| (test_mujoco_trajectory_tracking.py:27-31), fold.
-template <int L> UAVB_DEV void pair_period_end(Drone2& d, Cursor<float>& c, Accum<float>& a) {
-  const float ex = c.ex - lane<L>(d.dx), ey = c.ey - lane<L>(d.dy), ez = c.ez - lane<L>(d.dz);
-  d.px[L] += (double)lane<L>(d.dx); d.py[L] += (double)lane<L>(d.dy); d.pz[L] += (double)lane<L>(d.dz);
-  const float e2 = ex * ex + ey * ey + ez * ez;
-  const float e = Math<float>::sqrt_fast(e2);
-  a.sum_e += e; a.sum_e2 += e2; a.max_e = fmaxf(a.max_e, e);
-  ++a.periods;
-}
+};
+template <> struct PairTarget<false> {
+  typedef V2 T;
+  static UAVB_DEV void fetch(const Drone2& d, Cursor<float> (&c)[2], const MissionView& ma, const MissionView& mb, Target2<V2>& t2, V2& ex, V2& ey, V2& ez) {
+    Target<float> ta, tb;
+    cursor_target<float>(c[0], ma, &ta);
+    cursor_advance(&c[0].seg, &c[0].row, ma);
+    cursor_target<float>(c[1], mb, &tb);
+    cursor_advance(&c[1].seg, &c[1].row, mb);
+    t2.vx = make_float2(ta.vx, tb.vx); t2.vy = make_float2(ta.vy, tb.vy); t2.vz = make_float2(ta.vz, tb.vz);
+    t2.ax = make_float2(ta.ax, tb.ax); t2.ay = make_float2(ta.ay, tb.ay); t2.az = make_float2(ta.az, tb.az);
+    t2.yc = make_float2(ta.yc, tb.yc); t2.ys = make_float2(ta.ys, tb.ys);
+    ex = make_float2((float)(ta.x - d.px[0]), (float)(tb.x - d.px[1]));
+    ey = make_float2((float)(ta.y - d.py[0]), (float)(tb.y - d.py[1]));
+    ez = make_float2((float)(ta.z - d.pz[0]), (float)(tb.z - d.pz[1]));
+  }
+};
 
 template <int L, class OBST> UAVB_DEV bool pair_watch(const Drone2& d, const Accum<float>& a, const VehU<float>& u, const VehP<float>& v,
                                                      const OBST& obst, int n, float& clear) {
@@ -98,20 +104,17 @@ template <int L, class OBST> UAVB_DEV void pair_hit(const Drone2& d, Accum<float
 // (rollout_core.cuh), see there.  c[0].phase is the phase of both lanes.  VP2: VehP2 or VehP<float> (see inner_tick_pair).
 template <bool TABLE, class VP2, class OBST, class LOG>
 UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&a)[2], const VehU<float>& u, const VehP<float>& va,
-                               const VehP<float>& vb, const VP2& v2, const MissionView& ma, const MissionView& mb, int tick0,
+                               const VehP<float>& vb, const VP2& v2, const VehO2& vo, const MissionView& ma, const MissionView& mb, int tick0,
                                int n_ticks, int freq, int lag, const OBST& oa, const OBST& ob, LOG& logger) {
   int k = 0;
   float clear_a = 0.f, clear_b = 0.f;                        // not part of the carry: every launch / slice measures first
   while (k < n_ticks) {
     if (c[0].phase == 0) {
-      Target<float> t;
-      if constexpr (TABLE) {
-        table_target<float>(ma.trows, c[0].row, &t);
-        if (c[0].row + 1 < ma.n_trows) ++c[0].row;           // index clamp of main.py:61
-        c[1].row = c[0].row;
-      }
-      pair_outer<0, TABLE>(d, c[0], u, va, ma, &t);
-      pair_outer<1, TABLE>(d, c[1], u, vb, mb, &t);
+      Target2<typename PairTarget<TABLE>::T> t;
+      V2 ex, ey, ez;
+      PairTarget<TABLE>::fetch(d, c, ma, mb, t, ex, ey, ez);    // the position is folded here (d.dx = 0)
+      c[0].ex = ex.x; c[1].ex = ex.y; c[0].ey = ey.x; c[1].ey = ey.y; c[0].ez = ez.x; c[1].ez = ez.y;
+      outer_update_pair(d, u, vo, t, ex, ey, ez);
     }
     const int n = (freq - c[0].phase < n_ticks - k) ? (freq - c[0].phase) : (n_ticks - k);
     bool watch = false;
@@ -142,8 +145,17 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
     if (c[0].phase == freq) {
       c[0].phase = 0;
       if (!LOG::kNormEveryTick) renormalise_q_pair(d);       // once per outer period (not per launch: chunked runs stay bit-identical)
-      pair_period_end<0>(d, c[0], a[0]);
-      pair_period_end<1>(d, c[1], a[1]);
+      // tracking error |set-point - p| after the period (test_mujoco_trajectory_tracking.py:27-31): p = fold + displacement
+      const V2 fx = sub2(make_float2(c[0].ex, c[1].ex), d.dx), fy = sub2(make_float2(c[0].ey, c[1].ey), d.dy), fz = sub2(make_float2(c[0].ez, c[1].ez), d.dz);
+      const V2 e2 = fma2(fx, fx, fma2(fy, fy, mul2(fz, fz)));
+      const V2 e = sqrt2(e2);
+      const V2 se = add2(make_float2(a[0].sum_e, a[1].sum_e), e), se2 = add2(make_float2(a[0].sum_e2, a[1].sum_e2), e2);
+      a[0].sum_e = se.x; a[1].sum_e = se.y; a[0].sum_e2 = se2.x; a[1].sum_e2 = se2.y;
+      a[0].max_e = fmaxf(a[0].max_e, e.x); a[1].max_e = fmaxf(a[1].max_e, e.y);
+      ++a[0].periods; ++a[1].periods;
+      // fold the displacement into the fp64 position
+      d.px[0] += (double)d.dx.x; d.py[0] += (double)d.dy.x; d.pz[0] += (double)d.dz.x;
+      d.px[1] += (double)d.dx.y; d.py[1] += (double)d.dy.y; d.pz[1] += (double)d.dz.y;
       d.dx = d.dy = d.dz = make_float2(0.f, 0.f);
     }
     c[1].phase = c[0].phase;

@@ -43,6 +43,7 @@ UAVB_HD void mc_from_vehicle(McValues& o, const uavb_vehicle& u) {
 // Launch-uniform constants; built on the host (exp() for the motor-lag responses of quad.py:102).
 template <class R> inline void make_vehu(VehU<R>& v, const uavb_vehicle& u, double dt_outer) {
   v.dt = (R)u.dt; v.half_dt = (R)(0.5 * u.dt); v.half_dt_sq = v.half_dt * v.half_dt; v.dt_outer = (R)dt_outer; v.g = (R)u.g;
+  v.half_dt_cu3 = (R)(0.125 * u.dt * u.dt * u.dt / 3.0); v.small_rot_wn2 = (R)(5e-4 / (0.25 * u.dt * u.dt));
   v.kf = (R)u.kf; v.inv_kf = (R)(1.0 / u.kf); v.arm_kf = (R)(u.arm * u.kf); v.kappa_kf = (R)(u.kappa * u.kf);
   v.inv_arm4 = (R)(0.25 / u.arm); v.inv_kappa4 = (R)(0.25 / u.kappa);
   v.fmin = (R)u.min_thrust; v.fmax = (R)u.max_thrust; v.fmin4 = (R)(4.0 * u.min_thrust); v.fmax4 = (R)(4.0 * u.max_thrust);
