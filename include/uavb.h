@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UAVB_VERSION 111            /* 0.1.11: carry block of 52 words (contents private to the library version that wrote it; 0.1.11 changed them), stage ABI v2, host mission call, set-point table, RRT* */
+#define UAVB_VERSION 200            /* 0.2.0: fp32 rollouts fly two drones per thread (packed fp32x2 tick), uavb_rollout_args.n_slices, carry block contents changed (private to the library version that wrote it) */
 
 #define UAVB_OK          0
 #define UAVB_EINVAL     -1          /* bad argument (null pointer, size out of range) */
@@ -183,6 +183,9 @@ typedef struct uavb_rollout_args {
                                      uavb_rollout_targets_f64 ([n_target_rows] records of 56 bytes); NULL = the kernel
                                      evaluates the polynomials itself.  Both forms give bit-identical rollouts.        */
   int           n_target_rows;
+  int           n_slices;     /* 0 = library policy.  > 0: cut the launch into this many time slices (fp32 only; clamped to whole
+                                 outer periods of >= 100 ticks).  Per-rollout results do not depend on it -- the tests fly the
+                                 same batch with several values to prove exactly that.                                  */
 
   const double* start;        /* initial position, [3] (start_stride 0) or [B][3] (start_stride 3)    */
   int           start_stride;
@@ -207,7 +210,8 @@ typedef struct uavb_rollout_args {
 int uavb_rollout_targets_f64(const double* seg_coeffs, const int* seg_rows, const int* seg_table, const double* seg_yaw0,
                              int n_seg, double dt_outer, void* targets_out, int n_rows, void* stream);
 
-/* Execution (DESIGN.md "K2"): fp32 launches run a persistent grid of 8 CTAs x 64 drones per SM at 128 registers; when the
+/* Execution (DESIGN.md "K2"): fp32 launches fly TWO drones per thread (rollouts 2j and 2j+1 in the two lanes of packed
+ * fp32x2 registers) on a persistent grid of 8 one-warp CTAs (64 drones each) per SM at 255 registers; when the
  * batch exceeds that capacity the mission is cut into time slices that CTAs pull from an atomic work queue, a drone
  * resting in the carry block between slices (scratch comes from a library-private stream-ordered pool when `carry` is
  * NULL); a state log is written slice by slice into its place.  One compiled body per mode serves every batch size, so

@@ -357,13 +357,11 @@ def test_time_sliced_schedule_is_bit_identical_to_a_single_slice(cuda, monkeypat
     sets = (torch.arange(B, device=cuda) % 4).to(torch.int32)
     n = 6000 + 7                                                     # not a multiple of the outer period
     runs = []
-    for chunks in ("1", "7", "60"):
-        monkeypatch.setenv("UAVB_ROLLOUT_CHUNKS", chunks)
+    for chunks in (1, 7, 60):
         r = kernels.rollout(plan, B, n, start=ground.contiguous(), goal=wp[:, -1].contiguous(), mc_wind=wind, obstacles=boxes, obstacle_set=sets,
-                            want_carry=True)
+                            want_carry=True, n_slices=chunks)
         torch.cuda.synchronize()
         runs.append(r)
-    monkeypatch.delenv("UAVB_ROLLOUT_CHUNKS")
     for r in runs[1:]:
         assert torch.equal(r.metrics, runs[0].metrics) and torch.equal(r.state, runs[0].state) and torch.equal(r.carry.view(torch.int32)[:50], runs[0].carry.view(torch.int32)[:50])
     assert float(runs[0].metrics[:, 1].mean()) > 0.02                # collisions happen, so first-hit ticks cross slice boundaries
@@ -403,11 +401,9 @@ def test_state_log_is_identical_across_slice_counts(cuda, monkeypatch):
     mc = mc_arrays(cuda, B, rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3)))
     for stride in (1, 7, 50):
         logs = []
-        for chunks in ("1", "9"):
-            monkeypatch.setenv("UAVB_ROLLOUT_CHUNKS", chunks)
-            r = _fly(cuda, plan, B, n, log_stride=stride, **mc)
+        for chunks in (1, 9):
+            r = _fly(cuda, plan, B, n, log_stride=stride, n_slices=chunks, **mc)
             logs.append(r)
-        monkeypatch.delenv("UAVB_ROLLOUT_CHUNKS")
         assert logs[0].log.shape == (n // stride, 13, B)
         assert torch.equal(logs[0].log, logs[1].log) and torch.equal(logs[0].state, logs[1].state) and torch.equal(logs[0].metrics, logs[1].metrics)
         if n % stride == 0:

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libuavb.so")
 
 N_GAINS = 11
 N_METRICS = 8
-ABI_VERSION = 111          # UAVB_VERSION of include/uavb.h this module's struct mirrors were written against
+ABI_VERSION = 200          # UAVB_VERSION of include/uavb.h this module's struct mirrors were written against
 CARRY_WORDS = 52
 STATE_DIM = 13
 MAX_SPLINES = 64
@@ -61,7 +61,7 @@ class RolloutArgs(Structure):
         ("mc_mass", c_void_p), ("mc_inertia", c_void_p), ("mc_gains", c_void_p), ("mc_wind", c_void_p),
         ("seg_coeffs", c_void_p), ("seg_rows", c_void_p), ("seg_table", c_void_p), ("seg_yaw0", c_void_p),
         ("mission_seg_begin", c_void_p), ("mission_seg_count", c_void_p), ("n_seg_shared", c_int), ("dt_outer", c_double),
-        ("shared_targets", c_void_p), ("n_target_rows", c_int),
+        ("shared_targets", c_void_p), ("n_target_rows", c_int), ("n_slices", c_int),
         ("start", c_void_p), ("start_stride", c_int), ("goal", c_void_p), ("goal_stride", c_int),
         ("aabbs", c_void_p), ("aabb_set", c_void_p),
         ("carry", c_void_p), ("state_out", c_void_p), ("metrics_out", c_void_p), ("log_out", c_void_p),

@@ -1,4 +1,7 @@
 // capi.cu -- library-level C-ABI entry points: version, errors, device probing, FMA peak probe.
+#include <atomic>
+#include <mutex>
+
 #include "uavb_common.cuh"
 
 namespace uavb {
@@ -27,13 +30,14 @@ int require_device() {
   return UAVB_OK;
 }
 
+// One pool per device, created on first use; std::call_once publishes it to every host thread (the *_host entry points are
+// meant to be called from several threads at once).
 cudaMemPool_t scratch_pool() {
-  static cudaMemPool_t pools[64] = {nullptr};
-  static bool tried[64] = {false};
+  static cudaMemPool_t pools[kMaxDevices] = {nullptr};
+  static std::once_flag once[kMaxDevices];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!tried[dev]) {
-    tried[dev] = true;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::call_once(once[dev], [dev]() {
     cudaMemPoolProps props = {};
     props.allocType = cudaMemAllocationTypePinned;
     props.handleTypes = cudaMemHandleTypeNone;
@@ -47,8 +51,22 @@ cudaMemPool_t scratch_pool() {
     } else {
       cudaGetLastError();
     }
-  }
+  });
   return pools[dev];
+}
+
+// SM count of the current device (one query per device and process, thread-safe).
+int sm_count_cached(int* sms) {
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  UAVB_CUDA_OK(cudaGetDevice(&dev));
+  int n = (dev >= 0 && dev < kMaxDevices) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (n == 0) {
+    UAVB_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < kMaxDevices) cache[dev].store(n, std::memory_order_relaxed);
+  }
+  *sms = n;
+  return UAVB_OK;
 }
 
 // Dependent-chain-free FMA loops: 8 independent accumulators per thread, enough CTAs to fill the chip.

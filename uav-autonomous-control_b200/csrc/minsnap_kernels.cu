@@ -395,6 +395,7 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
   if (rc) return rc;
   if (B == 0) return UAVB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#ifdef UAVB_DEV
   if (const char* dev_mode = getenv("UAVB_K1_VARIANT")) {             // development override: staging / residency experiments at S <= 4
     const int v = atoi(dev_mode);
     if (S <= 4 && S > 2) {
@@ -411,6 +412,7 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
       }
     }
   }
+#endif
   if (S == 1) return launch_solve<1, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
   if (S == 2) return launch_solve<2, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
   // S <= 4 (BASELINE configs[1]): 6 CTAs per SM (168 registers) measured fastest -- 0.216 ms per 10^6 solves against 0.250 ms

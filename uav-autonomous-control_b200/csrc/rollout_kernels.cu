@@ -1,7 +1,9 @@
 // rollout_kernels.cu -- K2 host side: argument checks, launch policy (time slicing, scratch), the set-point table of a
 // shared mission, and the C entry points.  The device code lives in rollout_impl.cuh and is instantiated in
 // rollout_sliced.cu / rollout_log.cu / rollout_f64.cu.
+#ifdef UAVB_DEV
 #include <stdlib.h>
+#endif
 
 #include "rollout_impl.cuh"
 
@@ -74,6 +76,7 @@ static int check_args(const uavb_rollout_args* a, bool f64) {
   UAVB_REQUIRE(!a->resume || a->carry != nullptr, "rollout: resume = 1 needs a carry block");
   UAVB_REQUIRE(!(f64 && (a->resume || a->carry)), "rollout_f64: the fp64 validation rollout has no carry/resume");
   UAVB_REQUIRE(a->log_stride >= 0, "rollout: log_stride must be >= 0");
+  UAVB_REQUIRE(a->n_slices >= 0, "rollout: n_slices must be >= 0");
   UAVB_REQUIRE(a->log_stride == 0 || a->log_out != nullptr, "rollout: log_stride > 0 needs log_out");
   UAVB_REQUIRE(a->log_stride == 0 || a->B <= 300000000LL, "rollout: a state log supports at most 3e8 rollouts per launch");
   UAVB_REQUIRE(a->n_obs >= 0 && a->n_obs <= 1024, "rollout: n_obs out of range");
@@ -81,22 +84,6 @@ static int check_args(const uavb_rollout_args* a, bool f64) {
   UAVB_REQUIRE(a->dt_outer > 0.0 && a->veh.dt > 0.0 && a->veh.mass > 0.0, "rollout: dt_outer, veh.dt and veh.mass must be positive");
   UAVB_REQUIRE(a->shared_targets == nullptr || (a->mission_seg_begin == nullptr && a->n_target_rows >= 1),
                "rollout: shared_targets needs a shared mission and n_target_rows >= 1");
-  return UAVB_OK;
-}
-
-// SM count of the current device (one query per device and process).
-static int sm_count_cached(int* sms) {
-  static int cache[64] = {0};
-  int dev = 0;
-  UAVB_CUDA_OK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || cache[dev] == 0) {
-    int n = 0;
-    UAVB_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    if (dev >= 0 && dev < 64) cache[dev] = n;
-    *sms = n;
-    return UAVB_OK;
-  }
-  *sms = cache[dev];
   return UAVB_OK;
 }
 
@@ -153,7 +140,13 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     // ~32 items per resident CTA keep the tail near 3 % of the launch; slices are whole outer periods of >= 100 ticks
     constexpr int kMinChunkTicks = 100;
     long long want = grid > slots ? (32LL * slots + grid - 1) / grid : 1;
-    if (const char* force = getenv("UAVB_ROLLOUT_CHUNKS")) want = atoi(force) > 0 ? atoi(force) : want;   // development override
+#ifdef UAVB_DEV
+    if (const char* force = getenv("UAVB_ROLLOUT_CHUNKS")) {       // development builds only (build.py --variant dev -DUAVB_DEV): force the slice count
+      const int f = atoi(force);
+      if (f > 0) want = f < 4096 ? f : 4096;
+    }
+#endif
+    if (a->n_slices > 0) want = a->n_slices < 4096 ? a->n_slices : 4096;         // uavb.h: results are independent of the slice count
     const int period = a->inner_per_outer;
     int chunk = (int)((a->n_ticks + want - 1) / want);
     chunk = ((chunk + period - 1) / period) * period;

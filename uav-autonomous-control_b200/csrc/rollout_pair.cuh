@@ -57,6 +57,10 @@ template <> struct PairTarget<true> {
     table_target<float>(ma.trows, c[0].row, &t);
     if (c[0].row + 1 < ma.n_trows) ++c[0].row;               // index clamp of main.py:61
     c[1].row = c[0].row;
+    // the row of the NEXT outer period, one stretch of ticks ahead: into L1 now, so that its loads do not wait on L2 then
+    const char* nxt = reinterpret_cast<const char*>(ma.trows + c[0].row);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + sizeof(TargetRow) - 4));
     t2.vx = t.vx; t2.vy = t.vy; t2.vz = t.vz; t2.ax = t.ax; t2.ay = t.ay; t2.az = t.az; t2.yc = t.yc; t2.ys = t.ys;
     ex = make_float2((float)(t.x - d.px[0]), (float)(t.x - d.px[1]));
     ey = make_float2((float)(t.y - d.py[0]), (float)(t.y - d.py[1]));
@@ -80,17 +84,20 @@ template <> struct PairTarget<false> {
   }
 };
 
-template <int L, class OBST> UAVB_DEV bool pair_watch(const Drone2& d, const Accum<float>& a, const VehU<float>& u, const VehP<float>& v,
-                                                     const OBST& obst, int n, float& clear) {
-  if (a.collided) return false;
-  const float T = (float)n * u.dt;
-  const float vx = lane<L>(d.vx), vy = lane<L>(d.vy), vz = lane<L>(d.vz);
-  const float speed = Math<float>::sqrt_fast(vx * vx + vy * vy + vz * vz);
-  const float reach = 1.01f * (speed + v.acc_max * T) * T + 1e-4f;
-  if (!(clear > reach))
-    clear = obst.gap((float)(d.px[L] + (double)lane<L>(d.dx)), (float)(d.py[L] + (double)lane<L>(d.dy)), (float)(d.pz[L] + (double)lane<L>(d.dz)));
-  const bool watch = !(clear > reach);                       // NaN positions keep measuring and watching
-  clear -= reach;
+// Obstacle culling for the coming stretch of n ticks (rollout_run, "clearance budget"): true when either drone could reach a
+// box before the next check, i.e. the per-tick inclusive test must run.  `clear` = lower bounds of the Chebyshev gaps.
+template <class OBST> UAVB_DEV bool pair_watch(const Drone2& d, const Accum<float> (&a)[2], const VehU<float>& u, V2 acc_max,
+                                               const OBST& oa, const OBST& ob, int n, V2& clear) {
+  const float T = __fmul_rn((float)n, u.dt);
+  const V2 speed = sqrt2(fma2(d.vx, d.vx, fma2(d.vy, d.vy, mul2(d.vz, d.vz))));
+  const V2 reach = fma2(mul2(fma2(acc_max, T, speed), T), 1.01f, 1e-4f);
+  const bool live_a = !a[0].collided, live_b = !a[1].collided;
+  if ((live_a && !(clear.x > reach.x)) || (live_b && !(clear.y > reach.y))) {      // measure (rare): NaN positions keep measuring
+    if (live_a && !(clear.x > reach.x)) clear.x = oa.gap((float)(d.px[0] + (double)d.dx.x), (float)(d.py[0] + (double)d.dy.x), (float)(d.pz[0] + (double)d.dz.x));
+    if (live_b && !(clear.y > reach.y)) clear.y = ob.gap((float)(d.px[1] + (double)d.dx.y), (float)(d.py[1] + (double)d.dy.y), (float)(d.pz[1] + (double)d.dz.y));
+  }
+  const bool watch = (live_a && !(clear.x > reach.x)) || (live_b && !(clear.y > reach.y));
+  clear = sub2(clear, reach);
   return watch;
 }
 
@@ -107,7 +114,8 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
                                const VehP<float>& vb, const VP2& v2, const VehO2& vo, const MissionView& ma, const MissionView& mb, int tick0,
                                int n_ticks, int freq, int lag, const OBST& oa, const OBST& ob, LOG& logger) {
   int k = 0;
-  float clear_a = 0.f, clear_b = 0.f;                        // not part of the carry: every launch / slice measures first
+  V2 clear = make_float2(0.f, 0.f);                          // not part of the carry: every launch / slice measures first
+  const V2 acc_max = make_float2(va.acc_max, vb.acc_max);
   while (k < n_ticks) {
     if (c[0].phase == 0) {
       Target2<typename PairTarget<TABLE>::T> t;
@@ -118,11 +126,7 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
     }
     const int n = (freq - c[0].phase < n_ticks - k) ? (freq - c[0].phase) : (n_ticks - k);
     bool watch = false;
-    if (OBST::kAny) {
-      const bool wa = pair_watch<0>(d, a[0], u, va, oa, n, clear_a);
-      const bool wb = pair_watch<1>(d, a[1], u, vb, ob, n, clear_b);
-      watch = __any_sync(__activemask(), wa || wb);          // one decision per warp; watching is always correct
-    }
+    if (OBST::kAny) watch = __any_sync(__activemask(), pair_watch(d, a, u, acc_max, oa, ob, n, clear));   // one decision per warp; watching is always correct
     auto stretch = [&](auto watch_c, auto lag_c) {
       constexpr bool kWatch = decltype(watch_c)::value, kLag = decltype(lag_c)::value;
 #pragma unroll 2

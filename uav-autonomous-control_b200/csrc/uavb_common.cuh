@@ -35,6 +35,11 @@ int require_device();
 // milliseconds per 100 MB).  Returns nullptr if pools are unavailable; callers then fall back to the default pool.
 cudaMemPool_t scratch_pool();
 
+// SM count of the current device, cached per device (thread-safe).
+int sm_count_cached(int* sms);
+
+constexpr int kMaxDevices = 64;
+
 inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace uavb
