@@ -1,26 +1,31 @@
 #!/usr/bin/env python
-"""Headline benchmark of the batched closed-loop flight path (BASELINE.json metric: drone-sim-steps/s).
+"""Headline benchmark of the batched closed-loop flight path (BASELINE.json metric: drone-sim-steps/s; min-snap solves/s).
 
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-    python bench.py --impl reference ...          # the reference-style CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...          # the reference's own classes (oracle/_ref) on the host cores
 
-Workload (config.workload): BASELINE.json configs[2] -- 10^5 lab_course rollouts per GPU with
-Monte-Carlo PID gains and mass/inertia perturbations, velocity 3.0 (config.ini) => 10 760 ticks each,
-1.076e9 drone-sim-steps per GPU and step.  One "step" = one pass of the hot path over the batch:
-min-snap solve of the mission (K1, take-off + course tables), table geometry, persistent rollout
-(K2) of every drone over the whole mission, metrics written.  Weak scaling: every rank flies its own
-10^5 rollouts (Monte-Carlo inputs keyed by the global rollout index) and the per-rollout metrics are
-all-gathered over NCCL inside the timed region.
+Workload (config.workload): BASELINE.json configs[2] -- 10^5 lab_course rollouts per GPU with Monte-Carlo PID gains and
+mass/inertia perturbations, velocity 3.0 (config.ini) => 10 760 ticks each, 1.076e9 drone-sim-steps per GPU and step.  One "step" =
+one pass of the hot path over the batch: min-snap solve of the mission (K1, take-off + course tables), table geometry, persistent
+rollout (K2) of every drone over the whole mission, metrics written.  Weak scaling: every rank flies its own 10^5 rollouts
+(Monte-Carlo inputs keyed by the global rollout index); the per-rollout metrics of a step are all-gathered over NCCL
+asynchronously (sharding.MetricGather), overlapping the next step's kernels, and the last gather is inside the timed region.
 
-`value`  : steps/s with inputs resident in HBM (CUDA events around the K timed steps, max over ranks).
-`e2e`    : same metric through the reference-facing C-ABI call uavb_fly_mission_host with HOST buffers: per step
-           the waypoints and the Monte-Carlo arrays are copied from pinned host memory, the mission is planned and
-           flown, the metrics are copied back and the call synchronises.
-`roofline`: K2 is FP32-issue bound (no dense contraction => no tensor path, ~0 HBM bytes per tick in
-           metrics-only mode); `achieved` = 269 algorithmic flop/tick x ticks / K2 time,
-           `peak` = FP32 FMA rate measured in this run by uavb_measure_fma_peak.  `roofline_log` is the
-           HBM roofline of the full-rate state-log mode (52 B/tick) against MEASURED_PEAKS.json.
+`value`   : steps/s with inputs resident in HBM (CUDA events around the K timed steps, max over ranks).
+`e2e`     : same metric through the reference-facing C-ABI call uavb_fly_mission_host with HOST buffers: per step the waypoints and
+            the Monte-Carlo arrays are copied from pinned host memory, the mission is planned and flown, the metrics are copied back
+            and the call synchronises.
+`roofline`: K2 moves ~0 HBM bytes per tick in metrics-only mode and has no dense contraction (no tensor path): it is bound by the
+            SM's register-operand bandwidth (profiles/r02_ffma2_probe.md).  `achieved` = 269 algorithmic flop/tick x
+            ticks / K2 time; `peak` = FP32 FMA rate measured in this run (uavb_measure_fma_rates); `peak_three_operand` = the rate
+            of FMAs with three distinct register sources measured in the same call; `peak_nominal` = SMs x 128 x 2 x max clock.
+`roofline_log`, `solves`, `per_rollout_missions`, `long_horizon`, `sample_table`, `rrt`: the other BASELINE configs and kernels, each
+            with its own roofline where one applies; `parity`: the CUDA path against the oracle / the reference's own classes on
+            seeded inputs (checker leg, outside every timed region).
+`cpu_baseline` / `--impl reference`: the reference's own TrajectoryController + CascadedController + Quad + MinimumSnap objects,
+            byte-compiled into oracle/_ref (oracle/build_ref.py), with MuJoCo's rigid-body step restated by oracle/freebody.py --
+            kind "reference"; the NumPy port is the fallback (kind "port") when oracle/_ref is absent.
 """
 from __future__ import annotations
 
@@ -36,11 +41,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_TICK = 269          # algorithmic flop per drone tick with 4 AABBs: 239 in the 1 kHz body + 298/10 from the 100 Hz loop (DESIGN.md "K2 work per tick")
-K2_DRAM_BYTES_PER_LAUNCH = 8.65e6   # ncu: 6.18 MB read + 2.46 MB written per launch of the bench workload (metrics-only: ~0 B per tick)
+K2_DRAM_BYTES_PER_LAUNCH = 8.8e6    # ncu: 6.2 MB read + 2.6 MB written per launch of the bench workload (metrics-only: ~0 B per tick; profiles/r02_ncu_rollout_v12.md)
 LOG_BYTES_PER_TICK = 52      # 13 fp32 state words
 ROLLOUTS_PER_GPU = 100_000   # BASELINE configs[2]
 VELOCITY = 3.0               # config.ini:7
 FREQUENCY = 10               # config.ini:2
+TICKS_PER_ROLLOUT = 10_760   # lab_course at v = 3: 1076 table rows x 10 (read back from the plan in the GPU arm)
 METRIC = "drone-sim-steps/s"
 
 
@@ -52,67 +58,133 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rollouts", type=int, default=ROLLOUTS_PER_GPU, help="rollouts per GPU (default: BASELINE configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the solves/s and log-mode side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other configs, K1 / K3 / RRT*, log mode, parity)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall-clock budget of the CPU baseline sample")
     return ap.parse_args()
+
+
+def workload_name(rollouts):
+    return (f"BASELINE configs[2]: {rollouts} lab_course rollouts per GPU, Monte-Carlo gains x U(0.8,1.2), mass/inertia x U(0.9,1.1), "
+            f"v={VELOCITY} m/s, 10760 ticks each, 4 AABBs, metrics only")
+
+
+def config_dict(rollouts, n_ticks):
+    """`config` of the JSON line -- the same dict in both arms."""
+    return {"workload": workload_name(rollouts), "rollouts_per_gpu": rollouts, "ticks_per_rollout": n_ticks, "frequency": FREQUENCY,
+            "l2": "256 MB buffer written between timed iterations (L2 flush)", "fp64_parts": "K1 solve and 100 Hz set-point evaluation"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
 _TABLE_CACHE = {}
 
 
+def cpu_kind():
+    from oracle import ref_arm
+    return "reference" if ref_arm.available() else "port"
+
+
 def lab_course_table(velocity):
-    """(table, waypoints, obstacles) of the lab_course mission from the oracle planner (cached per process)."""
+    """(table, waypoints, obstacles) of the lab_course mission: the reference's own _generate_mission_trajectory when oracle/_ref is
+    built, else the oracle planner (cached per process)."""
     if velocity not in _TABLE_CACHE:
-        from oracle import minsnap_np
+        from oracle import minsnap_np, ref_arm
         from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES, LAB_COURSE_WAYPOINTS
-        tab = minsnap_np.mission_table(LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES, velocity, 0.01)
+        if ref_arm.available():
+            tab = ref_arm.mission_table(LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES, velocity, 0.01)
+        else:
+            tab = minsnap_np.mission_table(LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES, velocity, 0.01)
         _TABLE_CACHE[velocity] = (tab, LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES)
     return _TABLE_CACHE[velocity]
 
 
 def _cpu_worker(job):
-    """Fly `ticks` ticks of a Monte-Carlo-perturbed lab_course mission with the NumPy oracle port."""
-    seed, ticks = job
+    """Fly `missions` whole Monte-Carlo-perturbed lab_course missions (or `ticks` ticks of one when ticks > 0); (ticks, seconds)."""
+    seed, missions, ticks = job
     import numpy as np
-    from oracle import flight_np
-    rng = np.random.default_rng(seed)
-    veh = flight_np.Vehicle().perturbed(rng.uniform(0.8, 1.2, 11), rng.uniform(0.9, 1.1), rng.uniform(0.9, 1.1, 3))
+    from oracle import flight_np, ref_arm
     tab, wp, obs = lab_course_table(VELOCITY)
-    t0 = time.perf_counter()
-    flight_np.closed_loop(veh, tab, wp[0], obstacles=obs, goal=wp[-1], n_ticks=ticks)
-    return ticks, time.perf_counter() - t0
+    total, t0 = 0, time.perf_counter()
+    for m in range(max(1, missions)):
+        n = ticks if ticks > 0 else FREQUENCY * len(tab)
+        if ref_arm.available():
+            ref_arm.timed_ticks(seed * 1000 + m, n, tab, wp[0], obs, wp[-1])
+        else:
+            rng = np.random.default_rng(seed * 1000 + m)
+            veh = flight_np.Vehicle().perturbed(rng.uniform(0.8, 1.2, 11), rng.uniform(0.9, 1.1), rng.uniform(0.9, 1.1, 3))
+            flight_np.closed_loop(veh, tab, wp[0], obstacles=obs, goal=wp[-1], n_ticks=n)
+        total += n
+        if ticks > 0:
+            break
+    return total, time.perf_counter() - t0
 
 
-def cpu_rollout_rate(seconds: float, cores: int | None = None):
-    """Whole-machine rate of the oracle port (the reference's Python/NumPy style: one drone per
-    process, small-array NumPy calls per tick) on a bounded sample of the same workload."""
+def cpu_rollout_rate(seconds: float, cores: int | None = None, pool=None):
+    """Whole-machine rate of the reference's Python path (one drone per process, small-array NumPy calls per tick) on a bounded sample
+    of the headline workload: every host core flies the same number (>= 1) of WHOLE Monte-Carlo missions.  One estimator for
+    `cpu_baseline` and for every step of `--impl reference`."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        ticks_probe = 400
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+    try:
+        probe = pool.map(_cpu_worker, [(i, 0, 300) for i in range(cores)])       # also warms imports and the table
+        per_mission = TICKS_PER_ROLLOUT * max(p[1] for p in probe) / 300.0
+        missions = max(1, int(seconds / per_mission))
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(i, ticks_probe) for i in range(cores)])       # also warms imports and the table
-        per_core = ticks_probe / max(time.perf_counter() - t0, 1e-6)
-        ticks = max(1000, int(per_core * seconds * 0.8))
-        ticks = min(ticks, FREQUENCY * 1076)
-        t0 = time.perf_counter()
-        done = pool.map(_cpu_worker, [(1000 + i, ticks) for i in range(cores)])
+        done = pool.map(_cpu_worker, [(1000 + i, missions, 0) for i in range(cores)])
         wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     total = sum(d[0] for d in done)
-    return total / wall, cores, f"{cores} processes x {ticks} ticks of Monte-Carlo lab_course rollouts (v={VELOCITY}), oracle/flight_np.py"
+    src = "TrajectoryController + CascadedController + Quad of the reference (oracle/_ref) + oracle/freebody.py" if cpu_kind() == "reference" else "oracle/flight_np.py"
+    return total / wall, cores, f"{cores} processes x {missions} whole Monte-Carlo lab_course missions of {total // (cores * missions)} ticks (v={VELOCITY}), {src}"
+
+
+def _solve_worker(job):
+    seed, n = job
+    import numpy as np
+    from oracle import minsnap_np, ref_arm
+    rng = np.random.default_rng(seed)
+    wp = rng.uniform([2, 2, -5], [22, 12, -1], (n, 5, 3))
+    t0 = time.perf_counter()
+    for i in range(n):
+        if ref_arm.available():
+            ref_arm.solve_lstsq(wp[i], 2.5, "lstsq")
+        else:
+            minsnap_np.solve_coeffs(wp[i], 2.5, "lstsq")
+    return n, time.perf_counter() - t0
+
+
+def cpu_solve_rate(seconds: float = 3.0):
+    """MinimumSnap._compute_spline_parameters("lstsq") (minimum_snap.py:138-153, the reference default) on 5-waypoint missions, one process
+    per host core."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    with mp.get_context("fork").Pool(cores) as pool:
+        probe = pool.map(_solve_worker, [(i, 20) for i in range(cores)])
+        per = max(p[1] for p in probe) / 20.0
+        n = max(20, int(seconds / per))
+        t0 = time.perf_counter()
+        done = pool.map(_solve_worker, [(100 + i, n) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    return {"value": sum(d[0] for d in done) / wall, "unit": "solves/s", "cores": cores, "kind": cpu_kind(),
+            "sample": f"{cores} processes x {n} solves of MinimumSnap._compute_spline_parameters('lstsq'), 5 waypoints"}
 
 
 def cpu_rollout_rate_c(seconds: float):
-    """The C twin of the oracle (oracle/oracle_c.c, -O2, one thread per host core) on the same bounded sample: what an
-    optimised scalar CPU implementation of the path reaches on this host (reported next to the NumPy-style figure)."""
+    """The C twin of the oracle (oracle/oracle_c.c, -O2, one thread per host core) on whole missions: what an optimised scalar CPU
+    implementation of the path reaches on this host (reported next to the reference's own figure)."""
     import numpy as np
-    from oracle import c_port, flight_np
+    from oracle import c_port, flight_np, minsnap_np
+    from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES, LAB_COURSE_WAYPOINTS
     cores = os.cpu_count() or 1
-    tab, wp, obs = lab_course_table(VELOCITY)
+    tab = minsnap_np.mission_table(LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES, VELOCITY, 0.01)
+    wp, obs = LAB_COURSE_WAYPOINTS, LAB_COURSE_OBSTACLES
     rng = np.random.default_rng(7)
     def vehicles(n):
         return [flight_np.Vehicle().perturbed(rng.uniform(0.8, 1.2, 11), rng.uniform(0.9, 1.1), rng.uniform(0.9, 1.1, 3)) for _ in range(n)]
@@ -128,34 +200,34 @@ def cpu_rollout_rate_c(seconds: float):
 
 
 def run_reference(args):
-    """--impl reference: the reference-style CPU implementation (oracle port; the reference itself is
-    Python + MuJoCo and cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    """--impl reference: the reference's own classes (oracle/_ref; fallback: the oracle port) on all host cores.  A step is a bounded
+    sample of the workload -- one whole Monte-Carlo mission per host core -- and ms_per_step is extrapolated to the full batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = max(2.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_rollout_rate(per_step)
-        if i >= args.warmup:
-            vals.append(v)
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    vals, sample = [], ""
+    with mp.get_context("fork").Pool(cores) as pool:
+        for i in range(args.warmup + args.steps):
+            v, cores, sample = cpu_rollout_rate(1.0, cores, pool)              # 1 s budget => exactly one whole mission per core
+            if i >= args.warmup:
+                vals.append(v)
     value = statistics.mean(vals)
-    ms = 1e3 * ROLLOUTS_PER_GPU * FREQUENCY * 1076 / value
+    ms = 1e3 * args.rollouts * TICKS_PER_ROLLOUT / value
     line = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": workload_name(args.rollouts), "note": "bounded sample per step; ms_per_step extrapolated to the full batch"},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_dict(args.rollouts, TICKS_PER_ROLLOUT),
+        "note": "each step is a bounded sample (one whole mission per host core); ms_per_step is extrapolated to the full batch",
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": cpu_kind(), "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
-
-
-def workload_name(rollouts):
-    return (f"BASELINE configs[2]: {rollouts} lab_course rollouts per GPU, Monte-Carlo gains x U(0.8,1.2), mass/inertia x U(0.9,1.1), "
-            f"v={VELOCITY} m/s, 10760 ticks each, 4 AABBs, metrics only")
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -243,6 +315,7 @@ def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
+    import bench_workloads as wl
     from uav_ac_b200 import _native as nat, host_api, kernels, sharding
     from uav_ac_b200.simulation.scene import LAB_COURSE_GOAL, LAB_COURSE_OBSTACLES, LAB_COURSE_START, LAB_COURSE_WAYPOINTS
 
@@ -259,10 +332,7 @@ def run_b200(args):
 
     # ---- host inputs (pinned): waypoints, velocity, Monte-Carlo scales as a user would hand them over
     veh = nat.default_vehicle()
-    base = np.array(list(veh.gains) + [veh.mass] + list(veh.inertia), dtype=np.float32)
-    lo, hi = [0.8] * 11 + [0.9] * 4, [1.2] * 11 + [1.1] * 4
-    scales = kernels.mc_uniform(20261017, B, lo, hi, index_base=begin, device=dev)          # keyed by the global rollout index
-    mc_dev = (scales * torch.tensor(base, device=dev)[:, None]).contiguous()                # [15, B] fp32: 11 gains, mass, 3 inertia
+    mc_dev = wl.mc_vehicle_arrays(kernels, nat, dev, B, index_base=begin)                   # [15, B] fp32, keyed by the global rollout index
     mc_host = mc_dev.cpu().pin_memory()
     wp_host = torch.tensor(LAB_COURSE_WAYPOINTS, dtype=torch.float64).pin_memory()
     vel_host = torch.tensor([VELOCITY], dtype=torch.float64).pin_memory()
@@ -272,23 +342,30 @@ def run_b200(args):
     metrics_host = torch.empty((B, nat.N_METRICS), dtype=torch.float32).pin_memory()
     wp_dev = wp_host.to(dev)
     vel_dev = vel_host.to(dev)
-    result = kernels.RolloutResult(torch.empty((B, nat.N_METRICS), dtype=torch.float32, device=dev), None, None, None)
-    n_ticks_holder = {}
+    gather = sharding.MetricGather(B, nat.N_METRICS, total, dev)
+    results = [kernels.RolloutResult(gather.shard[i], None, None, None) for i in range(2)]
+    state = {"n": None, "k": 0}
 
-    def hot_path(wp, vel, mc):
-        """K1 (two tables) + table geometry + K2 over the shard; returns the per-rollout metrics."""
-        n_ticks = n_ticks_holder.get("n")
+    def hot_path(wp, vel, mc, result):
+        """K1 (two tables) + table geometry + K2 over the shard; the per-rollout metrics land in result.metrics."""
+        n_ticks = state["n"]
         plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True,
                                      table_rows=None if n_ticks is None else n_ticks // FREQUENCY)
         if n_ticks is None:                                  # mission length is data dependent: read it once, outside the timed steps
-            n_ticks = n_ticks_holder["n"] = FREQUENCY * int(plan.total_rows.item())
+            n_ticks = state["n"] = FREQUENCY * int(plan.total_rows.item())
         kernels.rollout(plan, B, n_ticks, start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc[:11], mc_mass=mc[11],
                         mc_inertia=mc[12:15], obstacles=obs, want_state=False, out=result, index_base=begin)
-        return result.metrics
 
     def step_device():
-        m = hot_path(wp_dev, vel_dev, mc_dev)
-        return sharding.gather_metrics(m, total) if world > 1 else m
+        k = state["k"]
+        gather.local(k)                                      # orders this step's K2 after the gather that last read the same shard buffer
+        hot_path(wp_dev, vel_dev, mc_dev, results[k % 2])
+        gather.launch(k)                                     # asynchronous: overlaps the next step's K1 / K2
+        state["k"] = k + 1
+
+    def drain():
+        if state["k"]:
+            gather.result(state["k"] - 1)                    # the last gather belongs to the timed region
 
     mc_mass_h, mc_inertia_h, mc_gains_h = mc_host[11], mc_host[12:15], mc_host[:11]     # contiguous pinned views, SoA
     wp_np = np.ascontiguousarray(LAB_COURSE_WAYPOINTS, dtype=np.float64)
@@ -302,11 +379,13 @@ def run_b200(args):
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)                    # > 126 MB L2
 
-    def timed(fn, steps, warmup, sampler=None, wall=False):
+    def timed(fn, steps, warmup, sampler=None, wall=False, after=None):
         """K timed steps between barriers + synchronize; device time from CUDA events on the launching (current torch)
         stream, or host wall-clock for the synchronous host-buffer call (wall=True); max over ranks."""
         for _ in range(warmup):
             fn()
+        if after:
+            after()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -325,6 +404,8 @@ def run_b200(args):
             else:
                 ev[s][0].record()
                 fn()
+                if after and s == steps - 1:
+                    after()
                 ev[s][1].record()
         torch.cuda.synchronize()
         if world > 1:
@@ -339,18 +420,19 @@ def run_b200(args):
 
     W = max(args.warmup, 3)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, clocks = timed(step_device, args.steps, W, sampler)
-    n_ticks = n_ticks_holder["n"]
+    ms_dev, clocks = timed(step_device, args.steps, W, sampler, after=drain)
+    n_ticks = state["n"]
     ms_e2e, _ = timed(step_e2e, args.steps, 2, wall=True)
     torch.cuda.synchronize()
     sim_steps = float(total) * n_ticks                                                       # whole job, one step
     value = sim_steps * args.steps / (ms_dev * 1e-3)
     e2e = sim_steps * args.steps / (ms_e2e * 1e-3)
+    last = results[(state["k"] - 1) % 2]
 
     # ---- K2 alone: average launch duration with events on the launching stream
     plan = kernels.plan_missions([(wp_dev[None, :2].contiguous(), vel_dev), (wp_dev[None, 1:].contiguous(), vel_dev)], FREQUENCY * veh.dt, shared=True)
     kw = dict(start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc_dev[:11], mc_mass=mc_dev[11], mc_inertia=mc_dev[12:15],
-              obstacles=obs, want_state=False, out=result)
+              obstacles=obs, want_state=False, out=last)
     k2 = []
     for i in range(2 + args.steps):
         flush_and_space(flush, i)
@@ -360,49 +442,83 @@ def run_b200(args):
         if i >= 2:
             k2.append(a.elapsed_time(b))
     k2_ms = statistics.mean(k2)
-    summary = sharding.summarize(result.metrics)
+    # per-rank K2 time: the skew the max-over-ranks timing pays for
+    k2_all = torch.tensor([k2_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        k2_list = [torch.zeros_like(k2_all) for _ in range(world)]
+        dist.all_gather(k2_list, k2_all)
+        k2_ranks = [float(x.item()) for x in k2_list]
+    else:
+        k2_ranks = [k2_ms]
+    summary = sharding.summarize(last.metrics)
+
+    # ---- the north-star job shape under torchrun: every rank flies one GPU's share of configs[4] (10^7 x 60 s over 8 GPUs), metrics gathered
+    long_h = None
+    if not args.no_extras:
+        long_h = long_horizon(wl, kernels, nat, sharding, dev, rank, world, dist)
 
     line = None
     if rank == 0:
-        fp32_peak, fp64_peak = nat.measure_fma_peak(local)
+        fp32_peak, fp32_peak3, fp64_peak = nat.measure_fma_rates(local)
+        sms = nat.device_info(local)[0]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         achieved = FLOP_PER_TICK * float(B) * n_ticks / (k2_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(B), "rollouts_per_gpu": B, "ticks_per_rollout": n_ticks, "frequency": FREQUENCY,
-                       "l2": "256 MB buffer written between timed iterations (L2 flush)", "fp64_parts": "K1 solve and 100 Hz set-point evaluation"},
+            "config": config_dict(B, n_ticks),
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(mc_host.numel() * 4 + wp_host.numel() * 8 + 8),
                     "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                     "call": "uavb_fly_mission_host (C ABI, pinned host buffers, synchronous); host wall-clock, max over ranks"},
             "gpu_launches": 6 * args.steps,        # own kernels per step: 2x minsnap_solve, table_meta, target_rows + target_heading, rollout_sliced (torch glue not counted)
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                         "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r01_ncu_rollout_v10.md)",
-                         "kernel": "rollout_sliced_kernel<MC,TABLE>", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,
-                         "peak_source": "uavb_measure_fma_peak in this run (MEASURED_PEAKS.json carries no fp32 figure)",
-                         "fp64_peak_tflops": fp64_peak, "ticks_per_s_k2": float(B) * n_ticks / (k2_ms * 1e-3)},
+                         "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_rollout_v12.md)",
+                         "kernel": "rollout_sliced_kernel<MC,TABLE> (two drones per thread, packed fp32x2)", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,
+                         "peak_source": "uavb_measure_fma_rates in this run (MEASURED_PEAKS.json carries no fp32 figure)",
+                         "peak_three_operand": fp32_peak3, "frac_of_three_operand_peak": achieved / fp32_peak3 if fp32_peak3 else None,
+                         "peak_nominal": sms * 128 * 2 * sm_max * 1e6 / 1e12,
+                         "limit": "register-operand bandwidth: a scheduler reads two register words per cycle, so FMAs with three distinct register "
+                                  "sources run at peak_three_operand (profiles/r02_ffma2_probe.md); frac is against the FMA peak with reuse-cached operands",
+                         "fp64_peak_tflops": fp64_peak, "ticks_per_s_k2": float(B) * n_ticks / (k2_ms * 1e-3),
+                         "k2_ms_per_rank": k2_ranks},
             "mission_report": summary,
         }
+        if long_h is not None:
+            line["long_horizon"] = long_h
         if not args.no_extras:
             line["roofline_log"] = log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush)
-            line["solves"] = solve_rate(kernels, dev, flush, peaks)
+            line["solves"] = solve_rate(kernels, host_api, dev, flush, peaks)
+            if world == 1:
+                for name, fn in (("per_rollout_missions", lambda: per_rollout_missions(wl, kernels, dev, fp32_peak, fp32_peak3)),
+                                 ("sample_table", lambda: wl.sample_table_rate(kernels, dev, peaks)), ("rrt", lambda: wl.rrt_rate(dev)),
+                                 ("parity", lambda: wl.parity_block(kernels, nat, dev))):
+                    try:
+                        line[name] = fn()
+                    except Exception as e:  # noqa: BLE001  (a side measurement must not take the headline down)
+                        line[name] = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
         dist.barrier()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_rollout_rate(args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": cpu_kind(), "sample": sample}
+            if "solves" in line:
+                try:
+                    line["solves"]["cpu_baseline"] = cpu_solve_rate()
+                except Exception as e:  # noqa: BLE001
+                    line["solves"]["cpu_baseline"] = {"unavailable": str(e)}
             try:
                 vc, cc, sc = cpu_rollout_rate_c(min(args.cpu_seconds, 8.0))
                 line["cpu_baseline_c"] = {"value": vc, "unit": "steps/s", "cores": cc, "kind": "port", "sample": sc,
                                           "note": "optimised C restatement; the reference itself is Python/NumPy (cpu_baseline)"}
-            except Exception as e:  # noqa: BLE001  (no C compiler on the box: the NumPy figure stands alone)
+            except Exception as e:  # noqa: BLE001  (no C compiler on the box: the reference figure stands alone)
                 line["cpu_baseline_c"] = {"unavailable": str(e)}
         emit(line)
     if world > 1:
@@ -417,16 +533,61 @@ def flush_and_space(flush, i):
         flush.fill_((i + k) & 0xFF)
 
 
+def long_horizon(wl, kernels, nat, sharding, dev, rank, world, dist):
+    """BASELINE configs[4] in the north-star job shape: every rank flies ONE GPU's share of 10^7 x 60 s x 1 kHz (1.25e6 rollouts x
+    60 000 ticks, three chunked launches through the carry block) and the [B, 8] metrics are all-gathered; at N = 8 this is the whole
+    job.  Device time (events), max over ranks, gather included."""
+    import torch
+    B, ticks = 1_250_000, 60_000
+    lo = rank * B
+    fly, _ = wl.config4_share(kernels, nat, dev, B=B, ticks=ticks, index_base=lo)
+    fly()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    res = fly()
+    m = sharding.gather_metrics(res.metrics, B * world) if world > 1 else res.metrics
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank != 0:
+        return None
+    return {"workload": f"BASELINE configs[4] share: {B} lab_course rollouts per GPU x {ticks} ticks (60 s at 1 kHz), Monte-Carlo vehicles, metrics only, "
+                        f"3 chunked launches + metric all-gather; {world} GPU(s) = {B * world} rollouts",
+            "rollouts_total": B * world, "ticks": ticks, "ms": ms, "value": float(B) * world * ticks / (ms * 1e-3), "unit": "steps/s",
+            "periods_ok": bool((m[:, 7] == ticks // FREQUENCY).all()), "hover_final_dist_max": float(m[:, 0].max()), **sharding.summarize(m)}
+
+
+def per_rollout_missions(wl, kernels, dev, fp32_peak, fp32_peak3):
+    """BASELINE configs[3] at full size: 10^6 rollouts, per-rollout missions (on-the-fly fp64 set-points), wind, 64 sets x 6 AABBs."""
+    import torch
+    B = 1_000_000
+    fly, n_ticks, info = wl.config3(kernels, dev, B=B)
+    res = kernels.RolloutResult(torch.empty((B, 8), dtype=torch.float32, device=dev), None, None, None)
+    ms, _ = wl.event_ms(lambda: fly(res), reps=2, warm=1)
+    m = res.metrics
+    achieved = FLOP_PER_TICK * float(B) * n_ticks / (ms * 1e-3) / 1e12
+    return {"workload": f"BASELINE configs[3]: {B} rollouts, random 5-waypoint missions (take-off + course), wind +-0.08 N, 64 obstacle sets x 6 AABBs, metrics only",
+            "value": float(B) * n_ticks / (ms * 1e-3), "unit": "steps/s", "rollouts": B, "ticks": n_ticks, "kernel_ms": ms,
+            "collision_fraction": float((m[:, 1] > 0).float().mean()), "failed_fraction": float((m[:, 5] != 0).float().mean()),
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+                         "peak_three_operand": fp32_peak3, "flop_per_tick": FLOP_PER_TICK, "kernel": "rollout_sliced_kernel<MC,!TABLE>", "traffic": None}}
+
+
 def log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush):
     """Full-rate state log (52 B/tick): HBM roofline of the logging epilogue (north_star)."""
     import torch
     Bl = 151552                                           # two full waves of 148 SMs x 8 CTAs x 64 drones
     ticks = 400                                           # 151552 x 400 x 52 B = 3.15 GB of log per launch
     from uav_ac_b200 import _native as nat
+    import bench_workloads as wl
     kw = dict(kw)
-    veh = nat.default_vehicle()
-    base = torch.tensor(list(veh.gains) + [veh.mass] + list(veh.inertia), dtype=torch.float32, device=dev)[:, None]
-    mc = (kernels.mc_uniform(20261017, Bl, [0.8] * 11 + [0.9] * 4, [1.2] * 11 + [1.1] * 4, device=dev) * base).contiguous()
+    mc = wl.mc_vehicle_arrays(kernels, nat, dev, Bl)
     kw.update(mc_gains=mc[:11], mc_mass=mc[11], mc_inertia=mc[12:15])
     kw["out"] = None
     kw["want_metrics"] = False
@@ -451,8 +612,9 @@ def log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush):
             "note": "full-rate state log: rollouts x ticks x 52 B written per launch (write-only traffic against the read+write copy peak)"}
 
 
-def solve_rate(kernels, dev, flush, peaks):
-    """BASELINE configs[1]: 10^6 random 5-waypoint missions, K1 only (second half of the headline metric)."""
+def solve_rate(kernels, host_api, dev, flush, peaks):
+    """BASELINE configs[1]: 10^6 random 5-waypoint missions -- K1 with inputs resident in HBM, and end to end through the host-buffer
+    call uavb_minsnap_solve_f64_host (pinned host buffers in and out)."""
     import torch
     Bm = 1_000_000
     wp, vel = kernels.mc_missions(99, Bm, 4, device=dev)
@@ -467,9 +629,27 @@ def solve_rate(kernels, dev, flush, peaks):
     t = statistics.mean(ms) * 1e-3
     byts = 928.0 * Bm                                      # 128 B in + 800 B out per solve
     peak = peaks.get("hbm_gbs", 6650.0)
-    return {"metric": "min-snap solves/s", "value": Bm / t, "unit": "solves/s", "missions": Bm, "splines": 4, "kernel_ms": t * 1e3,
-            "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peak, "unit": "GB/s", "frac": byts / t / 1e9 / peak,
-                         "traffic": None, "kernel": "minsnap_solve_kernel<4,kStagePair,6>", "note": "includes output allocation by torch (cached allocator)"}}
+    out = {"metric": "min-snap solves/s", "value": Bm / t, "unit": "solves/s", "missions": Bm, "splines": 4, "kernel_ms": t * 1e3,
+           "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peak, "unit": "GB/s", "frac": byts / t / 1e9 / peak,
+                        "traffic": None, "kernel": "minsnap_solve_kernel<4,kStagePair,6>", "note": "includes output allocation by torch (cached allocator)"}}
+    if hasattr(host_api, "minsnap_solve_host"):
+        wp_h, vel_h = wp.cpu().pin_memory(), vel.cpu().pin_memory()
+        c_h = torch.empty((Bm, 32, 3), dtype=torch.float64).pin_memory()
+        t_h = torch.empty((Bm, 4), dtype=torch.float64).pin_memory()
+        s_h = torch.empty((Bm,), dtype=torch.int32).pin_memory()
+        ws = []
+        for i in range(5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            host_api.minsnap_solve_host(wp_h, vel_h, coeffs_out=c_h, times_out=t_h, status_out=s_h)
+            if i >= 2:
+                ws.append(time.perf_counter() - t0)
+        te = statistics.mean(ws)
+        h2d, d2h = Bm * 128, Bm * 804
+        out["e2e"] = {"value": Bm / te, "unit": "solves/s", "ms": te * 1e3, "h2d_bytes": h2d, "d2h_bytes": d2h,
+                      "call": "uavb_minsnap_solve_f64_host (C ABI, pinned host buffers, chunked H2D -> K1 -> D2H pipeline, synchronous)",
+                      "link_GBps": (h2d + d2h) / te / 1e9, "note": "bound by the host link: 932 B cross PCIe per solve, 804 of them device-to-host"}
+    return out
 
 
 def emit(line: dict) -> None:

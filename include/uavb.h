@@ -338,6 +338,11 @@ int uavb_segments_hit_aabbs_f64(const double* p, const double* q, int n, const d
  * that MEASURED_PEAKS.json does not carry.  Synchronous. */
 int uavb_measure_fma_peak(int dev, double* fp32_tflops, double* fp64_tflops);
 
+/* The same plus the fp32 rate of FMAs whose three sources are three DIFFERENT registers (x = y * z + x with nothing for the
+ * operand reuse cache): a scheduler reads two register operands per cycle, so this is ~2/3 of fp32_tflops on sm_100 and the
+ * practical ceiling of three-operand code such as the rollout's tick (profiles/r02_ffma2_probe.md).  Synchronous. */
+int uavb_measure_fma_rates(int dev, double* fp32_tflops, double* fp32_three_operand_tflops, double* fp64_tflops);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer (end-to-end) entry points: HOST pointers in and out, copies and synchronisation inside.
  */

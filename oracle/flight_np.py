@@ -75,6 +75,15 @@ class Vehicle:
         kw["inertia"] = np.asarray(self.inertia, dtype=float) * np.asarray(inertia_scale, dtype=float)
         return Vehicle(**kw)
 
+    def with_values(self, gains: np.ndarray, mass: float, inertia: np.ndarray) -> "Vehicle":
+        """Copy with the 11 gains, the mass and the three inertias SET (e.g. to the fp32-rounded values a kernel launch was given)."""
+        kw = {k: getattr(self, k) for k in self.__dataclass_fields__}
+        for n, g in zip(self.GAIN_NAMES, gains):
+            kw[n] = float(g)
+        kw["mass"] = float(mass)
+        kw["inertia"] = np.asarray(inertia, dtype=float).copy()
+        return Vehicle(**kw)
+
 
 # ----------------------------------------------------------------------------- attitude helpers
 def euler_from_quat(q):

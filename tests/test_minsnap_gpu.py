@@ -220,3 +220,33 @@ def test_table_hits_match_oracle_point_in_cuboid(cuda, golden):
             if minsnap_np.point_in_cuboid(*tab[r, :3], boxes[i]):
                 want |= 1 << int(tab[r, 10])
         assert mask[i] == want and want != 0
+
+
+@pytest.mark.parametrize("B", [1, 5, 32768, 70001])
+def test_host_buffer_solve_is_the_device_solve_chunk_by_chunk(cuda, B):
+    """uavb_minsnap_solve_f64_host (pooled scratch, three-lane H2D -> K1 -> D2H pipeline in chunks of 2^15 missions) returns the
+    bits of the device-pointer solve, for batches below, at and across chunk boundaries, with pinned and with pageable buffers."""
+    import torch
+    from uav_ac_b200 import host_api, kernels
+    wp, vel = kernels.mc_missions(5, B, 4)
+    c, t, st = kernels.minsnap_solve(wp, vel)
+    torch.cuda.synchronize()
+    wp_h, vel_h = wp.cpu(), vel.cpu()
+    ch, th, sh = host_api.minsnap_solve_host(wp_h.numpy(), vel_h.numpy())                    # pageable NumPy in, fresh arrays out
+    assert np.array_equal(ch, c.cpu().numpy()) and np.array_equal(th, t.cpu().numpy()) and np.array_equal(sh, st.cpu().numpy())
+    cp = torch.empty((B, 32, 3), dtype=torch.float64).pin_memory()
+    tp = torch.empty((B, 4), dtype=torch.float64).pin_memory()
+    sp = torch.empty((B,), dtype=torch.int32).pin_memory()
+    for _ in range(2):                                                                       # second call reuses the pooled scratch
+        cp.zero_()
+        host_api.minsnap_solve_host(wp_h.pin_memory(), vel_h.pin_memory(), coeffs_out=cp, times_out=tp, status_out=sp)
+        assert torch.equal(cp, c.cpu()) and torch.equal(tp, t.cpu()) and torch.equal(sp, st.cpu())
+
+
+def test_fma_rate_probe_reports_the_three_operand_ceiling(cuda):
+    """uavb_measure_fma_rates: FMAs with three distinct register sources run at about 2/3 of the FMA peak on sm_100
+    (two register operand words per cycle and scheduler; profiles/r02_ffma2_probe.md)."""
+    from uav_ac_b200 import _native as nat
+    fp32, fp32_3, fp64 = nat.measure_fma_rates(0)
+    assert 30.0 < fp32 < 90.0 and 10.0 < fp64 < 50.0
+    assert 0.55 * fp32 < fp32_3 < 0.8 * fp32

@@ -68,3 +68,41 @@ def test_gather_metrics_world_size_2_gloo(total):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, (total, 8)), (1, True, (total, 8))]
+
+
+def _worker_async(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, _, w = sharding.init_from_env("gloo")
+    b, e = sharding.shard_range(total, r, w)
+    g = sharding.MetricGather(e - b, 8, total, torch.device("cpu"))
+    ok = True
+    for k in range(5):                                                        # five batches back to back through two buffers
+        local = g.local(k)
+        idx = torch.arange(b, e, dtype=torch.float32) + 1000.0 * k
+        local.copy_(torch.stack([idx * (c + 1) for c in range(8)], dim=1))
+        g.launch(k)
+        if k >= 1:                                                            # batch k-1 is read while batch k is in flight
+            want = (torch.arange(total, dtype=torch.float32) + 1000.0 * (k - 1))[:, None] * torch.arange(1, 9, dtype=torch.float32)[None, :]
+            ok &= bool(torch.equal(g.result(k - 1), want))
+    want = (torch.arange(total, dtype=torch.float32) + 4000.0)[:, None] * torch.arange(1, 9, dtype=torch.float32)[None, :]
+    ok &= bool(torch.equal(g.result(4), want))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [10, 11])
+def test_async_double_buffered_gather_world_size_2_gloo(total):
+    """MetricGather: equal shards gather straight into place asynchronously, unequal ones fall back to the padded gather;
+    a batch's result stays intact while the next batch is being written and gathered."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_async, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

@@ -33,7 +33,7 @@ SYMBOLS = (
     "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_yaw_profile_f64",
     "uavb_minsnap_table_hits_f64",
     "uavb_rollout_targets_f64", "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
-    "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host", "uavb_rrt_workspace_bytes", "uavb_rrt_star_f64", "uavb_segments_hit_aabbs_f64",
+    "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_measure_fma_rates", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host", "uavb_rrt_workspace_bytes", "uavb_rrt_star_f64", "uavb_segments_hit_aabbs_f64",
 )
 
 
@@ -122,6 +122,7 @@ def lib() -> ctypes.CDLL:
     L.uavb_mc_uniform_f32.argtypes = [c_ulonglong, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.uavb_mc_missions_f64.argtypes = [c_ulonglong, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.uavb_measure_fma_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
+    L.uavb_measure_fma_rates.argtypes = [c_int, POINTER(c_double), POINTER(c_double), POINTER(c_double)]
     L.uavb_minsnap_solve_f64_host.argtypes = [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]
     L.uavb_rrt_workspace_bytes.argtypes = [c_int, c_int]
     L.uavb_rrt_star_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_int, c_ulonglong, c_longlong, c_void_p,
@@ -176,3 +177,10 @@ def measure_fma_peak(dev: int = 0):
     a, b = c_double(), c_double()
     check(lib().uavb_measure_fma_peak(dev, ctypes.byref(a), ctypes.byref(b)), "uavb_measure_fma_peak")
     return a.value, b.value
+
+
+def measure_fma_rates(dev: int = 0):
+    """(fp32, fp32 with three distinct register operands, fp64) FMA rates in TFLOP/s."""
+    a, b, c = c_double(), c_double(), c_double()
+    check(lib().uavb_measure_fma_rates(dev, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "uavb_measure_fma_rates")
+    return a.value, b.value, c.value

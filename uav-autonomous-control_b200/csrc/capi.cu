@@ -107,6 +107,53 @@ template <class T> static int measure_one(int sms, double* tflops) {
   return UAVB_OK;
 }
 
+// The same with THREE distinct register operands per FMA (x_i = y_i * z_i + x_i, nothing for the operand reuse cache): the
+// register file delivers two operand words per cycle and scheduler, so these issue every 1.5 cycles (profiles/r02_ffma2_probe.md).
+__global__ void __launch_bounds__(256) fma3_peak_kernel(const float* in, float* out, int iters) {
+  float x[8], y[8], z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = in[threadIdx.x + 256 * i]; y[i] = in[threadIdx.x + 256 * (i + 8)]; z[i] = in[threadIdx.x + 256 * (i + 16)]; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __fmaf_rn(y[i], z[i], x[i]);
+    }
+  }
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += x[i] + y[i] + z[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+static int measure_three_operand(int sms, double* tflops) {
+  const int threads = 256, blocks = sms * 8, iters = 4096;
+  float *in = nullptr, *buf = nullptr;
+  UAVB_CUDA_OK(cudaMalloc(&in, sizeof(float) * 256 * 24));
+  UAVB_CUDA_OK(cudaMemset(in, 0, sizeof(float) * 256 * 24));
+  UAVB_CUDA_OK(cudaMalloc(&buf, sizeof(float) * threads * blocks));
+  cudaEvent_t e0, e1;
+  UAVB_CUDA_OK(cudaEventCreate(&e0));
+  UAVB_CUDA_OK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    UAVB_CUDA_OK(cudaEventRecord(e0));
+    fma3_peak_kernel<<<blocks, threads>>>(in, buf, iters);
+    UAVB_CUDA_OK(cudaEventRecord(e1));
+    UAVB_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    UAVB_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 64.0 * (double)iters * threads * blocks;
+    if (rep > 0 && ms > 0.f) best = fmax(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(in);
+  *tflops = best;
+  return UAVB_OK;
+}
+
 }  // namespace uavb
 
 extern "C" int uavb_version(void) { return UAVB_VERSION; }
@@ -145,5 +192,17 @@ extern "C" int uavb_measure_fma_peak(int dev, double* fp32_tflops, double* fp64_
   if (rc) return rc;
   if (fp32_tflops) *fp32_tflops = a;
   if (fp64_tflops) *fp64_tflops = b;
+  return UAVB_OK;
+}
+
+extern "C" int uavb_measure_fma_rates(int dev, double* fp32_tflops, double* fp32_three_operand_tflops, double* fp64_tflops) {
+  int rc = uavb_measure_fma_peak(dev, fp32_tflops, fp64_tflops);
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  UAVB_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  double c = 0.0;
+  rc = uavb::measure_three_operand(prop.multiProcessorCount, &c);
+  if (rc) return rc;
+  if (fp32_three_operand_tflops) *fp32_three_operand_tflops = c;
   return UAVB_OK;
 }

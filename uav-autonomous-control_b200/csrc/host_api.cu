@@ -40,12 +40,11 @@ struct DevPool {
 //   st_up     the per-rollout inputs (the bulk of the host->device bytes): they travel while the mission is planned on `st`
 //   ev_alloc  `st` -> `st_up`: the upload buffers exist;  ev_up  `st_up` -> `st`: the uploads are complete
 struct HostCallSet {
-  cudaStream_t st = nullptr, st_up = nullptr;
+  cudaStream_t st = nullptr, st_up = nullptr, st_aux = nullptr;     // st_aux: third lane of the chunked solve pipeline
   cudaEvent_t ev_alloc = nullptr, ev_up = nullptr;
 };
 
 static cudaError_t host_call_set(HostCallSet** out) {
-  constexpr int kMaxDevices = 64;
   thread_local HostCallSet sets[kMaxDevices];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -54,6 +53,7 @@ static cudaError_t host_call_set(HostCallSet** out) {
   HostCallSet& h = sets[dev];
   if (h.st == nullptr) e = cudaStreamCreateWithFlags(&h.st, cudaStreamNonBlocking);
   if (e == cudaSuccess && h.st_up == nullptr) e = cudaStreamCreateWithFlags(&h.st_up, cudaStreamNonBlocking);
+  if (e == cudaSuccess && h.st_aux == nullptr) e = cudaStreamCreateWithFlags(&h.st_aux, cudaStreamNonBlocking);
   if (e == cudaSuccess && h.ev_alloc == nullptr) e = cudaEventCreateWithFlags(&h.ev_alloc, cudaEventDisableTiming);
   if (e == cudaSuccess && h.ev_up == nullptr) e = cudaEventCreateWithFlags(&h.ev_up, cudaEventDisableTiming);
   if (e != cudaSuccess) return e;
@@ -64,6 +64,71 @@ static cudaError_t host_call_set(HostCallSet** out) {
 }  // namespace uavb
 
 using namespace uavb;
+
+// B missions, host buffers in and out (BASELINE configs[1] end to end).  The batch is cut into chunks of 2^15 missions that run
+// H2D -> K1 -> D2H on three cached streams in rotation, so the upload of chunk k+1 and the download of chunk k-1 overlap the solve
+// of chunk k; device scratch for the three lanes comes from the library's stream-ordered pool (no cudaMalloc / cudaFree per
+// call).  928 B per solve cross the host link, 804 of them device-to-host: with pinned host buffers the call is bound by that
+// link; pageable buffers work but are staged by the driver.
+extern "C" int uavb_minsnap_solve_f64_host(const double* waypoints, const double* velocity, int B, int S, double factor,
+                                           double* coeffs_out, double* times_out, int* status_out) {
+  UAVB_REQUIRE(waypoints && velocity && coeffs_out && times_out, "minsnap_solve_host: NULL pointer");
+  UAVB_REQUIRE(B >= 0 && S >= 1 && S <= UAVB_MAX_SPLINES, "minsnap_solve_host: B >= 0 and 1 <= S <= UAVB_MAX_SPLINES required");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  HostCallSet* hs = nullptr;
+  UAVB_CUDA_OK(host_call_set(&hs));
+  cudaStream_t lanes[3] = {hs->st, hs->st_up, hs->st_aux};
+  constexpr int kChunk = 1 << 15;
+  const int n_chunks = (B + kChunk - 1) / kChunk, n_lanes = n_chunks < 3 ? n_chunks : 3;
+  const size_t cw = (size_t)(S + 1) * 3, cc = (size_t)24 * S, ct = (size_t)S;        // doubles per mission
+  const size_t chunk = (size_t)(B < kChunk ? B : kChunk);
+  int result = UAVB_OK;
+  cudaError_t e = cudaSuccess;
+  {
+    DevPool pool(hs->st);
+    double *dw[3], *dv[3], *dc[3], *dtm[3];
+    int* ds[3];
+    for (int l = 0; l < n_lanes; ++l) {
+      dw[l] = pool.alloc<double>(chunk * cw); dv[l] = pool.alloc<double>(chunk); dc[l] = pool.alloc<double>(chunk * cc);
+      dtm[l] = pool.alloc<double>(chunk * ct); ds[l] = pool.alloc<int>(chunk);
+    }
+    if (pool.err != cudaSuccess) {
+      result = set_error(UAVB_ENOMEM, "minsnap_solve_host: %s", cudaGetErrorString(pool.err));
+    } else {
+      e = cudaEventRecord(hs->ev_alloc, hs->st);                      // the buffers exist once `st` reaches this point
+      for (int l = 1; l < n_lanes && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(lanes[l], hs->ev_alloc, 0);
+      for (int k = 0; k < n_chunks && e == cudaSuccess && !result; ++k) {
+        const int l = k % n_lanes;
+        cudaStream_t st = lanes[l];
+        const size_t first = (size_t)k * kChunk, n = (size_t)B - first < (size_t)kChunk ? (size_t)B - first : (size_t)kChunk;
+        e = cudaMemcpyAsync(dw[l], waypoints + first * cw, n * cw * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dv[l], velocity + first, n * 8, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        result = uavb_minsnap_solve_f64(dw[l], dv[l], (int)n, S, factor, dc[l], dtm[l], ds[l], st);
+        if (result) break;
+        e = cudaMemcpyAsync(coeffs_out + first * cc, dc[l], n * cc * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(times_out + first * ct, dtm[l], n * ct * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out + first, ds[l], n * 4, cudaMemcpyDeviceToHost, st);
+      }
+      // the frees of `pool` are ordered on `st`: make it wait for the other lanes, then wait for everything
+      for (int l = 1; l < n_lanes; ++l) {
+        cudaError_t e2 = cudaEventRecord(hs->ev_up, lanes[l]);
+        if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(hs->st, hs->ev_up, 0);
+        if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
+      }
+      const cudaError_t e3 = cudaStreamSynchronize(hs->st);
+      if (e == cudaSuccess) e = e3;
+      if (e != cudaSuccess && !result) {
+        for (int l = 0; l < n_lanes; ++l) cudaStreamSynchronize(lanes[l]);
+        cudaGetLastError();
+        result = set_error(UAVB_ECUDA, "minsnap_solve_host: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  return result;
+}
 
 extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_out, float* state_out, int* n_ticks_out) {
   UAVB_REQUIRE(m != nullptr && metrics_out != nullptr, "fly_mission_host: mission and metrics_out are required");

@@ -492,36 +492,3 @@ extern "C" int uavb_minsnap_table_hits_f64(const double* table, const int* row_o
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }
-
-extern "C" int uavb_minsnap_solve_f64_host(const double* waypoints, const double* velocity, int B, int S, double factor,
-                                           double* coeffs_out, double* times_out, int* status_out) {
-  UAVB_REQUIRE(waypoints && velocity && coeffs_out && times_out, "minsnap_solve_host: NULL pointer");
-  UAVB_REQUIRE(B >= 0 && S >= 1 && S <= UAVB_MAX_SPLINES, "minsnap_solve_host: B >= 0 and 1 <= S <= UAVB_MAX_SPLINES required");
-  int rc = require_device();
-  if (rc) return rc;
-  if (B == 0) return UAVB_OK;
-  const size_t nw = (size_t)B * (S + 1) * 3, nc = (size_t)B * 24 * S, nt = (size_t)B * S;
-  double *dw = nullptr, *dv = nullptr, *dc = nullptr, *dtm = nullptr;
-  int* ds = nullptr;
-  cudaStream_t st = nullptr;
-  auto cleanup = [&]() { cudaFree(dw); cudaFree(dv); cudaFree(dc); cudaFree(dtm); cudaFree(ds); };
-  if (cudaMalloc(&dw, nw * 8) != cudaSuccess || cudaMalloc(&dv, (size_t)B * 8) != cudaSuccess || cudaMalloc(&dc, nc * 8) != cudaSuccess ||
-      cudaMalloc(&dtm, nt * 8) != cudaSuccess || cudaMalloc(&ds, (size_t)B * 4) != cudaSuccess) {
-    cleanup();
-    cudaGetLastError();
-    return set_error(UAVB_ENOMEM, "minsnap_solve_host: device allocation failed");
-  }
-  cudaError_t e = cudaMemcpyAsync(dw, waypoints, nw * 8, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dv, velocity, (size_t)B * 8, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    rc = uavb_minsnap_solve_f64(dw, dv, B, S, factor, dc, dtm, ds, st);
-    if (rc) { cleanup(); return rc; }
-    e = cudaMemcpyAsync(coeffs_out, dc, nc * 8, cudaMemcpyDeviceToHost, st);
-  }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(times_out, dtm, nt * 8, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out, ds, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cleanup();
-  if (e != cudaSuccess) return set_error(UAVB_ECUDA, "minsnap_solve_host: %s", cudaGetErrorString(e));
-  return UAVB_OK;
-}

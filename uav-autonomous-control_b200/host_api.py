@@ -34,6 +34,34 @@ def _host_ptr(x, dtype, shape, name):
     return ctypes.c_void_p(a.ctypes.data), a
 
 
+def minsnap_solve_host(waypoints, velocity, *, start_end_time_factor: float = 1.5, coeffs_out=None, times_out=None, status_out=None):
+    """B minimum-snap solves, host arrays in and out, through ``uavb_minsnap_solve_f64_host``: waypoints (B, S+1, 3) f64 and
+    velocity (B,) f64 in; coeffs (B, 8 S, 3), times (B, S) f64 and status (B,) i32 out (preallocated -- e.g. pinned -- buffers are
+    filled in place).  Replaces B calls of ``MinimumSnap._compute_spline_parameters`` (uav_ac/planning/minimum_snap.py:138-153)."""
+    shape = tuple(waypoints.shape)
+    if len(shape) != 3 or shape[2] != 3 or shape[1] < 2:
+        raise ValueError("waypoints must have shape (B, S+1 >= 2, 3)")
+    B, S = shape[0], shape[1] - 1
+    wp_p, wp_k = _host_ptr(waypoints, np.float64, shape, "waypoints")
+    v_p, v_k = _host_ptr(velocity, np.float64, (B,), "velocity")
+    coeffs = coeffs_out if coeffs_out is not None else np.empty((B, 8 * S, 3), dtype=np.float64)
+    times = times_out if times_out is not None else np.empty((B, S), dtype=np.float64)
+    status = status_out if status_out is not None else np.empty((B,), dtype=np.int32)
+    c_p, c_k = _host_ptr(coeffs, np.float64, (B, 8 * S, 3), "coeffs_out")
+    t_p, t_k = _host_ptr(times, np.float64, (B, S), "times_out")
+    if hasattr(status, "data_ptr"):
+        s_p = ctypes.c_void_p(status.data_ptr())
+    else:
+        if status.dtype != np.int32 or not status.flags.c_contiguous or status.shape != (B,):
+            raise ValueError("status_out must be a C-contiguous int32 array of shape (B,)")
+        s_p = ctypes.c_void_p(status.ctypes.data)
+    for given, kept, name in ((coeffs_out, c_k, "coeffs_out"), (times_out, t_k, "times_out")):
+        if given is not None and kept is not given:
+            raise ValueError(f"{name} must be C-contiguous float64 of the right shape")
+    nat.check(nat.lib().uavb_minsnap_solve_f64_host(wp_p, v_p, int(B), int(S), float(start_end_time_factor), c_p, t_p, s_p), "uavb_minsnap_solve_f64_host")
+    return (c_k if coeffs_out is None else coeffs_out), (t_k if times_out is None else times_out), status
+
+
 def fly_mission_host(waypoints, velocity: float, B: int, *, n_takeoff_waypoints: int = 2, frequency: int = 10, n_ticks: int = 0,
                      vehicle: Optional[nat.Vehicle] = None, mc_mass=None, mc_inertia=None, mc_gains=None, mc_wind=None,
                      obstacles=None, start=None, goal=None, thrust_frame_lag: int = 1, start_end_time_factor: float = 1.5,

@@ -58,6 +58,50 @@ def gather_metrics(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
     return torch.cat(parts, dim=0)
 
 
+class MetricGather:
+    """Double-buffered, asynchronous form of gather_metrics for a job that flies several batches back to back.
+
+    launch(k) enqueues the all-gather of shard buffer k % 2 on the communicator's own stream, ordered after everything already
+    enqueued on the current stream, and returns at once: the next batch's kernels (which write the OTHER shard buffer) run while
+    the gather is in flight.  local(k) hands out shard buffer k % 2 after making the current stream wait for the gather that last
+    read it; result(k) returns the global [total, C] tensor of batch k once its gather is ordered before the current stream.
+    Equal shards (the weak-scaling case) are gathered straight into place; unequal ones go through gather_metrics' padding.
+    """
+
+    def __init__(self, rows_local: int, width: int, total: int, device, dtype=torch.float32, group=None):
+        self.group, self.total, self.width = group, int(total), int(width)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rows = int(rows_local)
+        self.equal = self.world == 1 or self.rows * self.world == self.total
+        self.shard = [torch.empty((self.rows, width), dtype=dtype, device=device) for _ in range(2)]
+        self.out = [torch.empty((self.total, width), dtype=dtype, device=device) if self.world > 1 and self.equal else None for _ in range(2)]
+        self.work = [None, None]
+
+    def local(self, k: int) -> torch.Tensor:
+        w = self.work[k % 2]
+        if w is not None:
+            w.wait()                                   # stream-ordered: the current stream waits, the host does not
+            self.work[k % 2] = None
+        return self.shard[k % 2]
+
+    def launch(self, k: int) -> None:
+        if self.world == 1:
+            return
+        if self.equal:
+            self.work[k % 2] = dist.all_gather_into_tensor(self.out[k % 2], self.shard[k % 2], group=self.group, async_op=True)
+        else:
+            self.out[k % 2] = gather_metrics(self.shard[k % 2], self.total, self.group)
+
+    def result(self, k: int) -> torch.Tensor:
+        if self.world == 1:
+            return self.shard[k % 2]
+        w = self.work[k % 2]
+        if w is not None:
+            w.wait()
+            self.work[k % 2] = None
+        return self.out[k % 2]
+
+
 def summarize(metrics: torch.Tensor, min_dist_target: float = 0.5) -> dict:
     """Mission report of main.py:115-120 over a batch: reached fraction, collision fraction, error stats."""
     m = metrics.double()
