@@ -2,8 +2,9 @@
 
     python oracle/build_ref.py            (called by __graft_entry__.build(); needs /root/reference)
 
-The reference is pure Python, so "building" it means compiling its modules to sourceless byte-code (`*.pyc` placed as
-`oracle/_ref/uav_ac/<pkg>/<module>.pyc`, which CPython imports like a module).  No reference SOURCE is written into this
+The reference is pure Python, so "building" it means compiling its modules to sourceless byte-code (the .pyc format, written
+as `oracle/_ref/uav_ac/<pkg>/<module>.bin` -- not `*.pyc`, which file synchronisers and .gitignore rules routinely drop -- and
+imported through a small finder in oracle/ref_arm.py).  No reference SOURCE is written into this
 repository: only compiler output goes to oracle/_ref/, which is git-ignored (not gpurun-ignored, so it travels to the GPU
 box like the built .so files).  Compiled: uav_ac/{__init__,main,utils}.py, control/controller.py, planning/minimum_snap.py,
 planning/rrt.py, quadrotor/quad.py, simulation/{__init__,mujoco_sim}.py -- everything `uav_ac.main` imports.  The one
@@ -28,7 +29,7 @@ MODULES = ["uav_ac/__init__.py", "uav_ac/main.py", "uav_ac/utils.py", "uav_ac/co
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(OUT, "STAMP"))
+    return os.path.exists(os.path.join(OUT, "STAMP")) and all(os.path.exists(os.path.join(OUT, m[:-3] + ".bin")) for m in MODULES)
 
 
 def build(force: bool = False) -> str | None:
@@ -40,10 +41,11 @@ def build(force: bool = False) -> str | None:
         with open(os.path.join(REF, m), "rb") as f:
             h.update(m.encode()); h.update(f.read())
     stamp = os.path.join(OUT, "STAMP")
-    if not force and os.path.exists(stamp) and open(stamp).read().split()[0] == h.hexdigest():
+    if not force and os.path.exists(stamp) and open(stamp).read().split()[0] == h.hexdigest() and all(
+            os.path.exists(os.path.join(OUT, m[:-3] + ".bin")) for m in MODULES):
         return OUT
     for m in MODULES:
-        dst = os.path.join(OUT, m[:-3] + ".pyc")
+        dst = os.path.join(OUT, m[:-3] + ".bin")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile: the path shown in tracebacks points back at the reference, not at a file of this repository
         py_compile.compile(os.path.join(REF, m), cfile=dst, dfile=os.path.join(REF, m), doraise=True,

@@ -12,6 +12,9 @@ Quad, TrajectoryController.
 """
 from __future__ import annotations
 
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 import time
@@ -32,6 +35,20 @@ def available() -> bool:
     return build_ref.available()
 
 
+class _RefFinder(importlib.abc.MetaPathFinder):
+    """Imports `uav_ac[.x[.y]]` from the byte-code files oracle/build_ref.py wrote (<module>.bin, .pyc format)."""
+
+    def find_spec(self, name, path=None, target=None):
+        if name != "uav_ac" and not name.startswith("uav_ac."):
+            return None
+        base = os.path.join(build_ref.OUT, *name.split("."))
+        for cand, pkg in ((os.path.join(base, "__init__.bin"), True), (base + ".bin", False)):
+            if os.path.exists(cand):
+                loader = importlib.machinery.SourcelessFileLoader(name, cand)
+                return importlib.util.spec_from_file_location(name, cand, loader=loader, submodule_search_locations=[base] if pkg else None)
+        return None
+
+
 def load() -> types.SimpleNamespace:
     """The reference classes (cached).  Raises when oracle/_ref has not been built."""
     global _NS
@@ -39,14 +56,15 @@ def load() -> types.SimpleNamespace:
         if not available():
             raise RuntimeError("oracle/_ref is not built: run oracle/build_ref.py where /root/reference exists")
         sys.modules.setdefault("mujoco", unittest.mock.MagicMock())
-        if build_ref.OUT not in sys.path:
-            sys.path.insert(0, build_ref.OUT)
+        if "uav_ac" in sys.modules and "oracle/_ref" not in str(getattr(sys.modules["uav_ac"].__spec__, "origin", "")):
+            raise RuntimeError("uav_ac is already imported from somewhere else in this process")
+        if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+            sys.meta_path.insert(0, _RefFinder())
         from uav_ac.control.controller import CascadedController
         from uav_ac.main import TrajectoryController, _generate_mission_trajectory
         from uav_ac.planning.minimum_snap import MinimumSnap
         from uav_ac.quadrotor.quad import Quad
-        import uav_ac
-        assert os.path.dirname(os.path.abspath(uav_ac.__file__ or uav_ac.__spec__.origin)).startswith(build_ref.OUT), "uav_ac was imported from elsewhere"
+        assert sys.modules["uav_ac.quadrotor.quad"].__spec__.origin.startswith(build_ref.OUT), "uav_ac was imported from elsewhere"
         _NS = types.SimpleNamespace(CascadedController=CascadedController, TrajectoryController=TrajectoryController, MinimumSnap=MinimumSnap,
                                     Quad=Quad, generate_mission_trajectory=_generate_mission_trajectory)
     return _NS

@@ -17,7 +17,7 @@ def test_ref_arm_imports_the_byte_compiled_reference_not_the_source_tree():
     ns = ref_arm.load()
     assert ns.Quad.__module__ == "uav_ac.quadrotor.quad"
     origin = sys.modules["uav_ac.quadrotor.quad"].__spec__.origin
-    assert origin.endswith(".pyc") and "oracle/_ref" in origin
+    assert origin.endswith(".bin") and "oracle/_ref" in origin
 
 
 def test_ref_arm_reproduces_the_golden_closed_loop_bit_for_bit(golden):
