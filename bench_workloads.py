@@ -181,8 +181,10 @@ def parity_block(kernels, nat, dev, n_rollouts=2048, n_missions=256):
                                             threads=os.cpu_count() or 1)
     X = res.state.double().cpu().numpy().T                      # [B, 13]
     dpos = float(np.abs(X[:, :3] - X_ref[:, :3]).max())
-    qd = np.abs(np.sum(X[:, 3:7] * X_ref[:, 3:7], axis=1)).clip(0, 1)
-    dang = float((2 * np.arccos(qd)).max())
+    qa, qb = X[:, 3:7] / np.linalg.norm(X[:, 3:7], axis=1, keepdims=True), X_ref[:, 3:7] / np.linalg.norm(X_ref[:, 3:7], axis=1, keepdims=True)
+    # angle of the relative rotation from the VECTOR part of conj(qb) * qa (well conditioned near zero, unlike acos of the dot product)
+    vec = qb[:, :1] * qa[:, 1:] - qa[:, :1] * qb[:, 1:] - np.cross(qb[:, 1:], qa[:, 1:])
+    dang = float((2 * np.arcsin(np.linalg.norm(vec, axis=1).clip(0, 1))).max())
     m = res.metrics.cpu().numpy()
     out["k2"] = {"rollouts": B, "ticks": n_ticks, "against": "oracle/oracle_c.c (fp64)", "dpos_max_m": dpos, "dang_max_rad": dang, "tol": 1e-4,
                  "flags_exact": bool(np.array_equal(m[:, 1] != 0, m_ref[:, 1] != 0)), "drmse_max": float(np.abs(m[:, 2] - m_ref[:, 2]).max())}

@@ -35,6 +35,7 @@ template <class A, class B, class C> UAVB_DEV V2 fma2(A a, B b, C c) { return __
 template <class A, class B> UAVB_DEV V2 add2(A a, B b) { return __fadd2_rn(as2(a), as2(b)); }
 template <class A, class B> UAVB_DEV V2 sub2(A a, B b) { return __fadd2_rn(as2(a), neg2(as2(b))); }
 template <class A, class B> UAVB_DEV V2 mul2(A a, B b) { return __fmul2_rn(as2(a), as2(b)); }
+UAVB_DEV V2 clamp_pair(V2 x, float lo, float hi) { return make_float2(fminf(fmaxf(x.x, lo), hi), fminf(fmaxf(x.y, lo), hi)); }
 UAVB_DEV V2 sqrt2(V2 x) { return make_float2(Math<float>::sqrt_fast(x.x), Math<float>::sqrt_fast(x.y)); }
 template <int L> UAVB_DEV float& lane(V2& v) { return L ? v.y : v.x; }
 template <int L> UAVB_DEV float lane(const V2& v) { return L ? v.y : v.x; }
@@ -99,19 +100,31 @@ template <int L> UAVB_DEV void put_lane(Drone2& p, const Drone<float>& d, const 
   lane<L>(p.zbx) = d.zbx; lane<L>(p.zby) = d.zby; lane<L>(p.zbz) = d.zbz;
 }
 // Mixer + rotor limits (quad.py:105-122) in rotor units for the pair.  The unclipped outputs come from the packed
-// butterfly.  |p_bar| + |q_bar| + |r_bar| <= margin (see limit_margin) proves them inside the limits with three instructions; a
-// pair that fails it re-runs the scalar mix_and_limit<float> per lane (the exact test of quad.py:114-121, the ratio scaling
-// and the clip) -- for a lane inside its limits that is the identity on the packed values, bit for bit.
+// butterfly.  |p_bar| + |q_bar| + |r_bar| <= margin (see limit_margin) proves them inside the limits with three instructions.  A
+// pair that fails it runs the limit path for BOTH lanes as straight-line packed code (a saturating lane must not cost its warp a
+// chain of branch diamonds -- in BASELINE configs[3] some lane of a warp is at a limit in most ticks): the exact test of
+// quad.py:114-121 per lane, the ratio scaling of :116-119 and the clip; a lane whose unclipped outputs pass the exact test keeps
+// them.  Same operations as mix_and_limit<float> (flight_core.cuh), see there for the two-reciprocal form of the ratios.
+UAVB_DEV float limit_scale(float m_hi, float m_lo, float room_hi, float room_lo) {
+  const float l_hi = (m_hi > 0.f) ? __fmul_rn(room_hi, Math<float>::rcp_fast(m_hi)) : 1.f;
+  const float l_lo = (m_lo < 0.f) ? __fmul_rn(room_lo, Math<float>::rcp_fast(m_lo)) : 1.f;
+  return fminf(fmaxf(fminf(l_hi, l_lo), 0.f), 1.f);
+}
 UAVB_DEV void mix_and_limit_pair(V2 pb, V2 qb, V2 rb, V2 coll, V2 margin, float lo, float hi, V2& f0, V2& f1, V2& f2, V2& f3) {
   const V2 s1 = add2(pb, qb), s2 = sub2(pb, qb), t1 = add2(coll, rb), t2 = sub2(coll, rb);
   f0 = add2(t1, s1); f1 = sub2(t2, s2); f2 = sub2(t1, s1); f3 = add2(t2, s2);
   const V2 need = add2(add2(abs2(pb), abs2(qb)), abs2(rb));
   if (!(need.x <= margin.x && need.y <= margin.y)) {
-    float f[4];
-    mix_and_limit<float>(pb.x, qb.x, rb.x, coll.x, lo, hi, f);
-    f0.x = f[0]; f1.x = f[1]; f2.x = f[2]; f3.x = f[3];
-    mix_and_limit<float>(pb.y, qb.y, rb.y, coll.y, lo, hi, f);
-    f0.y = f[0]; f1.y = f[1]; f2.y = f[2]; f3.y = f[3];
+    const bool ok_x = fmaxf(fmaxf(f0.x, f1.x), fmaxf(f2.x, f3.x)) <= hi && fminf(fminf(f0.x, f1.x), fminf(f2.x, f3.x)) >= lo;
+    const bool ok_y = fmaxf(fmaxf(f0.y, f1.y), fmaxf(f2.y, f3.y)) <= hi && fminf(fminf(f0.y, f1.y), fminf(f2.y, f3.y)) >= lo;
+    const V2 m0 = add2(s1, rb), m1 = neg2(add2(s2, rb)), m2 = sub2(rb, s1), m3 = sub2(s2, rb);
+    const V2 room_hi = sub2(hi, coll), room_lo = sub2(lo, coll);          // >= 0 and <= 0: coll is a clipped collective share
+    const V2 sc = make_float2(limit_scale(fmaxf(fmaxf(m0.x, m1.x), fmaxf(m2.x, m3.x)), fminf(fminf(m0.x, m1.x), fminf(m2.x, m3.x)), room_hi.x, room_lo.x),
+                              limit_scale(fmaxf(fmaxf(m0.y, m1.y), fmaxf(m2.y, m3.y)), fminf(fminf(m0.y, m1.y), fminf(m2.y, m3.y)), room_hi.y, room_lo.y));
+    const V2 g0 = clamp_pair(fma2(sc, m0, coll), lo, hi), g1 = clamp_pair(fma2(sc, m1, coll), lo, hi);
+    const V2 g2 = clamp_pair(fma2(sc, m2, coll), lo, hi), g3 = clamp_pair(fma2(sc, m3, coll), lo, hi);
+    f0 = make_float2(ok_x ? f0.x : g0.x, ok_y ? f0.y : g0.y); f1 = make_float2(ok_x ? f1.x : g1.x, ok_y ? f1.y : g1.y);
+    f2 = make_float2(ok_x ? f2.x : g2.x, ok_y ? f2.y : g2.y); f3 = make_float2(ok_x ? f3.x : g3.x, ok_y ? f3.y : g3.y);
   }
 }
 
@@ -211,7 +224,7 @@ template <bool NORM, bool LAG, class VP> UAVB_DEV void inner_tick_pair(Drone2& d
 // lateral (:58-97), roll/pitch (:132-154), yaw (:156-168) on the fresh state, stage by stage as outer_update<float>.
 
 UAVB_DEV V2 rcp2(V2 x) { return make_float2(Math<float>::rcp_fast(x.x), Math<float>::rcp_fast(x.y)); }
-UAVB_DEV V2 clamp2(V2 x, float lo, float hi) { return make_float2(fminf(fmaxf(x.x, lo), hi), fminf(fmaxf(x.y, lo), hi)); }
+UAVB_DEV V2 clamp2(V2 x, float lo, float hi) { return clamp_pair(x, lo, hi); }
 
 // s = limit / |(x, y)| when the norm exceeds the limit, else 1 (multiplying by 1 is exact: the unclamped vector keeps its bits)
 UAVB_DEV V2 norm_limit_scale(V2 n2, float limit) {

@@ -334,7 +334,7 @@ __device__ __forceinline__ void write_outputs(const uavb_rollout_args& a, long l
 
 // One PAIR of drones (2j, 2j+1), one slice of their mission: the production fp32 path (rollout_pair.cuh).  Arguments as
 // drone_slice.  When B is odd the last pair's second lane re-flies the first drone and writes nothing.
-template <bool LOG, bool MC, bool TABLE>
+template <bool LOG, bool MC, bool TABLE, bool LAG>
 __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long j, int n_ticks, bool from_carry, bool to_carry,
                                            bool finish, int launch_tick0) {
   const uavb_rollout_args& a = p.a;
@@ -385,8 +385,8 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
 
   auto fly = [&](const auto& oa, const auto& ob) {
     auto with_log = [&](auto& lg) {
-      if constexpr (MC) rollout_run_pair<TABLE>(d, c, acc, u, va, vb, v2, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
-      else rollout_run_pair<TABLE>(d, c, acc, u, va, vb, p.vp, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, oa, ob, lg);
+      if constexpr (MC) rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, v2, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg);
+      else rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, p.vp, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg);
     };
     if constexpr (LOG) {
       PairLog lg;
@@ -465,7 +465,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-template <bool MC, bool TABLE, bool LOG>
+template <bool MC, bool TABLE, bool LOG, bool LAG>
 __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
   extern __shared__ float s_boxes[];
   __shared__ int s_item;
@@ -488,7 +488,7 @@ __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid
     if (2 * j < p.a.B) {
       const bool last = c == sch.n_chunks - 1;
       const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
-      pair_slice<LOG, MC, TABLE>(p, j, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
+      pair_slice<LOG, MC, TABLE, LAG>(p, j, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
     }
     __threadfence();
     __syncthreads();

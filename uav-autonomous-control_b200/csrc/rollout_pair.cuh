@@ -109,10 +109,13 @@ template <int L, class OBST> UAVB_DEV void pair_hit(const Drone2& d, Accum<float
 
 // n_ticks ticks of the closed loop for the pair; the schedule, the obstacle culling and the metrics are rollout_run's
 // (rollout_core.cuh), see there.  c[0].phase is the phase of both lanes.  VP2: VehP2 or VehP<float> (see inner_tick_pair).
-template <bool TABLE, class VP2, class OBST, class LOG>
+// LAG (thrust_frame_lag of the launch) is a compile-time switch of the kernel: one stretch body per (kernel, watch) keeps the
+// instruction footprint of a warp's working set inside the instruction cache (ncu: with all four (watch, lag) bodies in one kernel
+// the per-rollout-mission workload spent as long waiting for instructions as for operands).
+template <bool TABLE, bool LAG, class VP2, class OBST, class LOG>
 UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&a)[2], const VehU<float>& u, const VehP<float>& va,
                                const VehP<float>& vb, const VP2& v2, const VehO2& vo, const MissionView& ma, const MissionView& mb, int tick0,
-                               int n_ticks, int freq, int lag, const OBST& oa, const OBST& ob, LOG& logger) {
+                               int n_ticks, int freq, const OBST& oa, const OBST& ob, LOG& logger) {
   int k = 0;
   V2 clear = make_float2(0.f, 0.f);                          // not part of the carry: every launch / slice measures first
   const V2 acc_max = make_float2(va.acc_max, vb.acc_max);
@@ -127,11 +130,13 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
     const int n = (freq - c[0].phase < n_ticks - k) ? (freq - c[0].phase) : (n_ticks - k);
     bool watch = false;
     if (OBST::kAny) watch = __any_sync(__activemask(), pair_watch(d, a, u, acc_max, oa, ob, n, clear));   // one decision per warp; watching is always correct
-    auto stretch = [&](auto watch_c, auto lag_c) {
-      constexpr bool kWatch = decltype(watch_c)::value, kLag = decltype(lag_c)::value;
-#pragma unroll 2
+    auto stretch = [&](auto watch_c) {
+      constexpr bool kWatch = decltype(watch_c)::value;
+      // two ticks per iteration where the body is lean (the tail of one tick overlaps the head of the next); the watching
+      // variants carry the per-tick box tests and stay rolled to keep the instruction footprint down
+#pragma unroll(kWatch ? 1 : 2)
       for (int j = 0; j < n; ++j) {
-        inner_tick_pair<LOG::kNormEveryTick, kLag>(d, u, v2);
+        inner_tick_pair<LOG::kNormEveryTick, LAG>(d, u, v2);
         if constexpr (kWatch) {
           pair_hit<0>(d, a[0], oa, tick0 + k + j);
           pair_hit<1>(d, a[1], ob, tick0 + k + j);
@@ -140,9 +145,9 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
       }
     };
     if (watch) {
-      if (lag) stretch(BoolC<true>{}, BoolC<true>{}); else stretch(BoolC<true>{}, BoolC<false>{});
+      stretch(BoolC<true>{});
     } else {
-      if (lag) stretch(BoolC<false>{}, BoolC<true>{}); else stretch(BoolC<false>{}, BoolC<false>{});
+      stretch(BoolC<false>{});
     }
     k += n;
     c[0].phase += n;
