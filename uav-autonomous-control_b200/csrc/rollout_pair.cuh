@@ -132,9 +132,11 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
     if (OBST::kAny) watch = __any_sync(__activemask(), pair_watch(d, a, u, acc_max, oa, ob, n, clear));   // one decision per warp; watching is always correct
     auto stretch = [&](auto watch_c) {
       constexpr bool kWatch = decltype(watch_c)::value;
-      // two ticks per iteration where the body is lean (the tail of one tick overlaps the head of the next); the watching
-      // variants carry the per-tick box tests and stay rolled to keep the instruction footprint down
-#pragma unroll(kWatch ? 1 : 2)
+      // two ticks per iteration (the tail of one tick overlaps the head of the next: +2 % on the table-driven headline workload)
+      // only where the instruction footprint allows it: the watching bodies carry the per-tick box tests, and kernels that
+      // evaluate the set-points on the fly carry two inlined fp64 evaluations per period -- unrolled, BASELINE configs[3]
+      // waits for instruction fetches and runs 10 % slower (measured)
+#pragma unroll((kWatch || !TABLE) ? 1 : 2)
       for (int j = 0; j < n; ++j) {
         inner_tick_pair<LOG::kNormEveryTick, LAG>(d, u, v2);
         if constexpr (kWatch) {
