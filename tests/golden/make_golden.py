@@ -276,6 +276,41 @@ def closed_loops():
     print("variants:", {k: float(v) for k, v in var.items() if k.endswith("final_dist") or k.endswith("first_collision_tick")})
 
 
+def actual_trajectory():
+    """D5: the 20 Hz position list of the viewer (mujoco_sim.py:201-218), produced by the reference's OWN
+    MujocoSimulation._record_actual_trajectory running on a stand-in object (MuJoCo itself is absent): after every tick the
+    simulation time advances by dt (mj_step) and the method decides -- take-off gate on quad.z, then one sample per
+    ACTUAL_TRAJECTORY_SAMPLE_INTERVAL -- whether quad.position is appended.  Stored: the ticks after which a sample was taken, the
+    sampled positions, and the full-rate position log they were taken from."""
+    import types
+    from uav_ac.simulation import mujoco_sim as ms
+    table = _generate_mission_trajectory(WAYPOINTS, OBSTACLES, 3.0, 0.01)
+    quad = make_quad()
+    quad.X[0:3] = WAYPOINTS[0]
+    ctrl = CascadedController(quad.g, quad.dt * FREQ)
+    tc = TrajectoryController(ctrl, quad, table, FREQ)
+    sim = types.SimpleNamespace(mission_waypoints=WAYPOINTS, quad=quad, data=types.SimpleNamespace(time=0.0),
+                                _next_actual_trajectory_sample_time=0.0, _actual_trajectory_positions=[],
+                                _actual_trajectory_segment_ids=None, _set_trajectory_segments=lambda *a, **k: None)
+    R_stale = quad.R()
+    ticks, log = [], []
+    for k in range(FREQ * len(table)):
+        tc.step()
+        R_now = quad.R()
+        quad.X = freebody_step(quad.X, quad.omega, R_stale, g=quad.g, dt=quad.dt, mass=quad.m, inertia=np.array([quad.i_x, quad.i_y, quad.i_z]),
+                               kf=quad.kf, arm=quad.l, kappa=quad.kappa)
+        R_stale = R_now
+        sim.data.time += quad.dt                                  # mj_step advances data.time by the model time step
+        before = len(sim._actual_trajectory_positions)
+        ms.MujocoSimulation._record_actual_trajectory(sim)
+        if len(sim._actual_trajectory_positions) > before:
+            ticks.append(k)
+        log.append(quad.position.copy())
+    np.savez_compressed(os.path.join(HERE, "actual_trajectory.npz"), ticks=np.array(ticks), positions=np.array(sim._actual_trajectory_positions),
+                        log=np.array(log), interval=np.array(ms.ACTUAL_TRAJECTORY_SAMPLE_INTERVAL), takeoff_z=np.array(WAYPOINTS[1][2]))
+    print("actual_trajectory.npz:", len(ticks), "samples, first after tick", ticks[0], "spacing", sorted(set(np.diff(ticks).tolist())))
+
+
 def rrt():
     """Reference RRTStar (uav_ac/planning/rrt.py) fed with the Philox stream of oracle/rrt_np.py (the stream the CUDA kernel draws
     from) through a patched np.random.uniform: best paths, their greedy simplification, slab-test truth table."""
@@ -324,6 +359,6 @@ def rrt():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["planning", "stages", "closed_loops", "rrt"]
+    which = sys.argv[1:] or ["planning", "stages", "closed_loops", "actual_trajectory", "rrt"]
     for w in which:
         globals()[w]()

@@ -97,3 +97,38 @@ def test_config4_share_sixty_seconds_chunked_with_carry(cuda):
     assert bool((m[:, 7] == ticks // 10).all()) and int((m[:, 5] != 0).sum()) == 0 and int((m[:, 1] != 0).sum()) == 0
     assert float(m[:, 0].max()) < 5e-3                                         # 49 s of hover on the last row: every drone sits on the goal
     assert float(whole.state[7:13].abs().max()) < 1e-2                         # at rest
+
+
+def test_config2_every_rollout_of_the_headline_batch_against_the_c_oracle(cuda):
+    """BASELINE configs[2] at FULL size, checked exhaustively: all 10^5 Monte-Carlo lab_course rollouts x 10 760 ticks of the bench
+    workload (same generator, same seed as bench.py) against oracle/oracle_c.c flown with the fp32-rounded vehicles the kernel was
+    given (~7 s on 16 host cores).  North-star tolerances: 1e-4 m, 1e-4 rad, collision flags bit-exact; metrics to 2e-5."""
+    import torch
+    import bench_workloads as wl
+    from oracle import c_port, flight_np, minsnap_np
+    from uav_ac_b200 import _native as nat, kernels
+    from uav_ac_b200.simulation.scene import LAB_COURSE_GOAL, LAB_COURSE_OBSTACLES, LAB_COURSE_START, LAB_COURSE_WAYPOINTS
+    B = 100_000
+    mc = wl.mc_vehicle_arrays(kernels, nat, cuda, B)
+    plan, kw = wl.lab_course(kernels, cuda)
+    n = 10 * int(plan.total_rows.item())
+    kw["want_state"] = True
+    res = kernels.rollout(plan, B, n, mc_gains=mc[:11], mc_mass=mc[11], mc_inertia=mc[12:15], **kw)
+    torch.cuda.synchronize()
+    mch = mc.double().cpu().numpy()
+    base = flight_np.Vehicle()
+    vehicles = [base.with_values(mch[:11, i], mch[11, i], mch[12:15, i]) for i in range(B)]
+    tab = minsnap_np.mission_table(LAB_COURSE_WAYPOINTS, None, 3.0, 0.01, method="solve")
+    assert len(tab) * 10 == n
+    m_ref, X_ref = c_port.closed_loop_batch(vehicles, tab, np.asarray(LAB_COURSE_START, float), obstacles=LAB_COURSE_OBSTACLES, goal=LAB_COURSE_GOAL,
+                                            threads=os.cpu_count() or 1)
+    X, m = res.state.double().cpu().numpy().T, res.metrics.double().cpu().numpy()
+    dpos = np.abs(X[:, :3] - X_ref[:, :3]).max(axis=1)
+    dang = rotation_angle(X[:, 3:7], X_ref[:, 3:7])
+    print(f"10^5 rollouts: max |dpos| {dpos.max():.2e} m, attitude {dang.max():.2e} rad, |dv| {np.abs(X[:, 7:10] - X_ref[:, 7:10]).max():.2e}, "
+          f"|dw| {np.abs(X[:, 10:13] - X_ref[:, 10:13]).max():.2e}, collisions {int(m_ref[:, 1].sum())}")
+    assert dpos.max() < 1e-4 and dang.max() < 1e-4
+    assert np.abs(X[:, 7:10] - X_ref[:, 7:10]).max() < 1e-3 and np.abs(X[:, 10:13] - X_ref[:, 10:13]).max() < 1e-3
+    assert np.array_equal(m[:, 1], m_ref[:, 1]) and np.array_equal(m[:, 6], m_ref[:, 6])            # flags and first-hit ticks, bit for bit
+    assert np.abs(m[:, 0] - m_ref[:, 0]).max() < 1e-4 and np.abs(m[:, 2:5] - m_ref[:, 2:5]).max() < 1e-4 and np.array_equal(m[:, 7], m_ref[:, 7])
+    assert int((m[:, 5] != 0).sum()) == 0
