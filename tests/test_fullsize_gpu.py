@@ -125,7 +125,7 @@ def test_config2_every_rollout_of_the_headline_batch_against_the_c_oracle(cuda):
     X, m = res.state.double().cpu().numpy().T, res.metrics.double().cpu().numpy()
     dpos = np.abs(X[:, :3] - X_ref[:, :3]).max(axis=1)
     dang = rotation_angle(X[:, 3:7], X_ref[:, 3:7])
-    print(f"10^5 rollouts: max |dpos| {dpos.max():.2e} m, attitude {dang.max():.2e} rad, |dv| {np.abs(X[:, 7:10] - X_ref[:, 7:10]).max():.2e}, "
+    print(f"10^5 rollouts: max |dpos| {dpos.max():.2e} m, attitude {dang.max():.2e} rad (median {np.median(dang):.2e}), |dv| {np.abs(X[:, 7:10] - X_ref[:, 7:10]).max():.2e}, "
           f"|dw| {np.abs(X[:, 10:13] - X_ref[:, 10:13]).max():.2e}, collisions {int(m_ref[:, 1].sum())}")
     assert dpos.max() < 1e-4 and dang.max() < 1e-4
     assert np.abs(X[:, 7:10] - X_ref[:, 7:10]).max() < 1e-3 and np.abs(X[:, 10:13] - X_ref[:, 10:13]).max() < 1e-3
