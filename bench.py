@@ -337,6 +337,7 @@ def run_b200(args):
     wp_host = torch.tensor(LAB_COURSE_WAYPOINTS, dtype=torch.float64).pin_memory()
     vel_host = torch.tensor([VELOCITY], dtype=torch.float64).pin_memory()
     obs = torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=dev)
+    obs64 = torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float64, device=dev)
     start = torch.tensor(LAB_COURSE_START, dtype=torch.float64, device=dev)
     goal = torch.tensor(LAB_COURSE_GOAL, dtype=torch.float64, device=dev)
     metrics_host = torch.empty((B, nat.N_METRICS), dtype=torch.float32).pin_memory()
@@ -347,10 +348,11 @@ def run_b200(args):
     state = {"n": None, "k": 0}
 
     def hot_path(wp, vel, mc, result):
-        """K1 (two tables) + table geometry + K2 over the shard; the per-rollout metrics land in result.metrics."""
+        """Plan (both tables through K1 and the obstacle-correction sweep, one host synchronisation; table geometry) + K2 over the
+        shard; the per-rollout metrics land in result.metrics."""
         n_ticks = state["n"]
         plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True,
-                                     table_rows=None if n_ticks is None else n_ticks // FREQUENCY)
+                                     table_rows=None if n_ticks is None else n_ticks // FREQUENCY, obstacles=obs64)
         if n_ticks is None:                                  # mission length is data dependent: read it once, outside the timed steps
             n_ticks = state["n"] = FREQUENCY * int(plan.total_rows.item())
         kernels.rollout(plan, B, n_ticks, start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc[:11], mc_mass=mc[11],
@@ -498,6 +500,7 @@ def run_b200(args):
             if world == 1:
                 for name, fn in (("per_rollout_missions", lambda: per_rollout_missions(wl, kernels, dev, fp32_peak, fp32_peak3)),
                                  ("sample_table", lambda: wl.sample_table_rate(kernels, dev, peaks)), ("rrt", lambda: wl.rrt_rate(dev)),
+                                 ("correction_loop", lambda: wl.correction_rate(kernels, nat, dev)),
                                  ("parity", lambda: wl.parity_block(kernels, nat, dev))):
                     try:
                         line[name] = fn()

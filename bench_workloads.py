@@ -50,7 +50,8 @@ def lab_course(kernels, dev, velocity=3.0, table_rows=None):
     f64 = dict(dtype=torch.float64, device=dev)
     wp = torch.tensor(LAB_COURSE_WAYPOINTS, **f64)
     vel = torch.tensor([velocity], **f64)
-    plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], 0.01, shared=True, table_rows=table_rows)
+    plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], 0.01, shared=True, table_rows=table_rows,
+                                 obstacles=torch.tensor(LAB_COURSE_OBSTACLES, **f64))
     kw = dict(start=torch.tensor(LAB_COURSE_START, **f64), goal=torch.tensor(LAB_COURSE_GOAL, **f64),
               obstacles=torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=dev), want_state=False)
     return plan, kw
@@ -113,6 +114,33 @@ def sample_table_rate(kernels, dev, peaks, B=100_000):
     return {"metric": "sampled table rows/s", "value": n_rows / (ms * 1e-3), "unit": "rows/s", "missions": B, "rows": n_rows, "kernel_ms": ms,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                          "kernel": "sample_table_kernel", "note": "88 B per (N, 11) row written; write-only traffic against the read+write copy peak"}}
+
+
+def correction_rate(kernels, nat, dev, B=100_000, n_obs=4):
+    """The device-side obstacle-correction loop (uavb_minsnap_correct_f64) on B config-1 missions x n_obs shared boxes placed in the
+    mission volume: plan, sweep the sampled points, insert midpoints, re-plan only the missions that were hit, until clean.
+    Wall-clock of the whole call (it synchronises once per round)."""
+    import time
+    import torch
+    wp, vel = kernels.mc_missions(123, B, 4, device=dev)
+    rng = np.random.default_rng(5)
+    ctr, half = rng.uniform([4, 3, -4.5], [20, 11, -1.5], (n_obs, 3)), rng.uniform(0.15, 0.4, (n_obs, 3))
+    boxes = torch.tensor(np.stack((ctr[:, 0] - half[:, 0], ctr[:, 0] + half[:, 0], ctr[:, 1] - half[:, 1], ctr[:, 1] + half[:, 1],
+                                   ctr[:, 2] - half[:, 2], ctr[:, 2] + half[:, 2]), axis=-1), dtype=torch.float64, device=dev)
+    cap = 17
+
+    def run():
+        w, n = kernels.fixed_pitch(wp, cap, dev)
+        return kernels.minsnap_correct(w, n, vel, 0.01, boxes) + (n,)
+    run()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter(); c, t, status, rounds, n = run(); torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
+    return {"metric": "collision-free plans/s", "value": B / best, "unit": "missions/s", "missions": B, "obstacles": n_obs, "ms": best * 1e3,
+            "plan_rounds": rounds, "grown_fraction": float((n > 5).float().mean()), "too_many_fraction": float((status == nat.SOLVE_TOO_MANY).float().mean()),
+            "waypoint_capacity": cap, "call": "uavb_minsnap_correct_f64 (K1 over work lists bucketed by spline count + sampled-point sweep + midpoint "
+            "insertion on the device; one host synchronisation per round)"}
 
 
 def rrt_rate(dev, B=16_384):

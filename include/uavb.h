@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UAVB_VERSION 200            /* 0.2.0: fp32 rollouts fly two drones per thread (packed fp32x2 tick), uavb_rollout_args.n_slices, carry block contents changed (private to the library version that wrote it) */
+#define UAVB_VERSION 210            /* 0.2.1: uavb_minsnap_correct_f64 / uavb_minsnap_pack_f64, uavb_mission_host.plan_aabbs / no_correction (0.2.0: two drones per thread, packed fp32x2 tick, uavb_rollout_args.n_slices) */
 
 #define UAVB_OK          0
 #define UAVB_EINVAL     -1          /* bad argument (null pointer, size out of range) */
@@ -49,6 +49,8 @@ extern "C" {
 #define UAVB_SOLVE_DEGENERATE 1     /* a segment has zero length (T_i = 0) or velocity <= 0: KKT singular
                                        (np.linalg.solve would raise LinAlgError, minimum_snap.py:151) */
 #define UAVB_SOLVE_NONFINITE 2      /* non-finite input or result */
+#define UAVB_SOLVE_TOO_MANY  3      /* more splines than the caller's capacity / UAVB_MAX_SPLINES (the correction loop kept
+                                       inserting midpoints: an obstacle probably contains a waypoint -- the reference loops forever) */
 
 /* per-rollout status bits (metrics column 5 and status_out of uavb_rollout_f32) */
 #define UAVB_ROLLOUT_OK        0
@@ -134,6 +136,44 @@ int uavb_minsnap_yaw_profile_f64(const double* velocities, const int* row_offset
  * [xmin xmax ymin ymax zmin zmax]).  cuboid_stride = 0: one cuboid for all missions, 6: one each. */
 int uavb_minsnap_table_hits_f64(const double* table, const int* row_offsets, int B, const double* cuboid,
                                 int cuboid_stride, unsigned long long* hit_mask_out, void* stream);
+
+/* The obstacle-correction loop of MinimumSnap._generate_collision_free_trajectory (minimum_snap.py:63-95) for B missions,
+ * entirely on the device: for every obstacle in order, plan (K1), find the splines that own a sampled row (j * dt,
+ * j < len(np.arange(0, T_i, dt)), :104) inside the box (is_collision_cuboid, :327-357), insert the midpoint of each as a new
+ * waypoint (insert_midpoints_at_indexes, :359-391) and plan again until the table is clean.  Every mission walks the obstacle
+ * list with its own cursor; only missions that were hit are planned again (DESIGN.md "correction loop").
+ *   waypoints    [B][max_wp][3]  in/out, fixed pitch: mission b uses rows [0, n_waypoints[b])
+ *   n_waypoints  [B]             in/out
+ *   cuboids      [n_obs][6] doubles [xmin xmax ymin ymax zmin zmax] shared by all missions (cuboid_stride 0), or one set per
+ *                mission, cuboid_stride doubles apart;  n_obs = 0 plans without obstacles
+ *   coeffs_out   [B][max_wp-1][8][3], times_out [B][max_wp-1]  fixed pitch, the first n_waypoints[b]-1 splines are valid
+ *   status_out   [B] UAVB_SOLVE_* (required); UAVB_SOLVE_TOO_MANY when a mission would need more than max_wp waypoints
+ *   rounds_out   HOST int, plan rounds run (1 = nothing was hit); may be NULL
+ * max_wp <= UAVB_MAX_SPLINES + 1.  Unlike the other device-pointer entry points this one SYNCHRONISES `stream` (the host reads
+ * four counters per round to size the next one). */
+int uavb_minsnap_correct_f64(double* waypoints, int* n_waypoints, const double* velocity, int B, int max_wp,
+                             double start_end_time_factor, double dt, const double* cuboids, int n_obs, long long cuboid_stride,
+                             double* coeffs_out, double* times_out, int* status_out, int* rounds_out, void* stream);
+
+/* Fixed pitch -> packed segments: spline s of mission b (s < n_waypoints[b]-1) goes to packed segment seg_offsets[b] + s.
+ * seg_offsets [B] (or [B+1]) = exclusive prefix sum of n_waypoints-1, provided by the caller. */
+int uavb_minsnap_pack_f64(const double* coeffs, const double* times, const int* n_waypoints, int B, int max_wp,
+                          const int* seg_offsets, double* coeffs_out, double* times_out, void* stream);
+
+/* One mission made of n_tables consecutive MinimumSnap tables -- _generate_mission_trajectory's vertical take-off + course
+ * (main.py:73-84) -- each planned with the correction loop above, laid out as the packed segment arrays of a shared-mission
+ * rollout (struct uavb_rollout_args).  ONE host synchronisation when nothing is hit (the usual case).
+ *   table_waypoints    HOST array of n_tables DEVICE pointers, table k = [table_n_waypoints[k]][3] doubles
+ *   table_n_waypoints  HOST array [n_tables];   table_velocity  DEVICE array [n_tables]
+ *   cuboids            DEVICE [n_obs][6] doubles, n_obs = 0 plans the waypoints as given
+ *   seg_coeffs [cap_seg][8][3], seg_times / seg_rows / seg_table / seg_yaw0 [cap_seg]   DEVICE outputs; cap_seg >= the splines
+ *                      of the corrected mission (n_tables * UAVB_MAX_SPLINES always suffices)
+ *   n_seg_out, rows_out [n_tables] (table rows of every table), status_out [n_tables] (UAVB_SOLVE_*), rounds_out (may be NULL)  HOST
+ * SYNCHRONISES `stream`.  n_tables <= 8. */
+int uavb_plan_shared_f64(int n_tables, const double* const* table_waypoints, const int* table_n_waypoints, const double* table_velocity,
+                         double start_end_time_factor, double dt, const double* cuboids, int n_obs, int cap_seg, double* seg_coeffs,
+                         double* seg_times, int* seg_rows, int* seg_table, double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out,
+                         int* rounds_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2  persistent closed-loop rollout, fp32 state in registers, one thread per drone.
@@ -356,7 +396,8 @@ int uavb_minsnap_solve_f64_host(const double* waypoints, const double* velocity,
  *     trajectory = _generate_mission_trajectory(waypoints, obstacles, velocity, quad.dt * frequency)   (main.py:73-84)
  *     for target in trajectory: for _ in range(frequency): trajectory_controller.step(); simulation.step()
  *     final distance to goal / collision flag / tracking error                                          (main.py:115-120)
- * The mission is planned on the device (K1 per table + table geometry), every drone flies it in the
+ * The mission is planned on the device (both tables through the obstacle-correction loop uavb_minsnap_correct_f64, then the
+ * table geometry), every drone flies it in the
  * persistent rollout kernel (K2) with its own Monte-Carlo overrides, and the per-rollout metrics
  * (and optionally the final states) are copied back.  Synchronous. */
 typedef struct uavb_mission_host {
@@ -380,6 +421,10 @@ typedef struct uavb_mission_host {
   int n_obs;
   const double* start;          /* [3] or NULL = waypoints[0]                                            */
   const double* goal;           /* [3] or NULL = last waypoint                                           */
+  const double* plan_aabbs;     /* [n_obs][6] fp64 boxes for the planner's correction loop (the reference tests its
+                                   fp64 obstacle array, minimum_snap.py:84-87); NULL = `aabbs` widened to double */
+  int no_correction;            /* 0 = plan like MinimumSnap.get_trajectory() with obstacles (midpoint insertion,
+                                   minimum_snap.py:63-95); 1 = fly the waypoints as given                         */
 } uavb_mission_host;
 int uavb_fly_mission_host(const uavb_mission_host* mission, float* metrics_out /* [B][UAVB_N_METRICS] */,
                           float* state_out /* [13][B] or NULL */, int* n_ticks_out /* or NULL */);

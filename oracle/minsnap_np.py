@@ -168,12 +168,13 @@ def insert_midpoints(points: np.ndarray, indexes) -> np.ndarray:
     return np.array(out)
 
 
-def plan_table(waypoints: np.ndarray, obstacles, velocity: float, dt: float, method: str = "lstsq"):
+def plan_table(waypoints: np.ndarray, obstacles, velocity: float, dt: float, method: str = "lstsq", max_waypoints=None):
     """``MinimumSnap(...).get_trajectory()`` incl. the per-obstacle midpoint loop (ms:59-95).
 
     Returns (table, waypoints_after_insertion, coeffs, T).  ``obstacles=None`` skips the loop; an
     empty obstacle array returns ``None`` for the table exactly like the reference (the loop body
-    never runs).
+    never runs).  ``max_waypoints``: raise RuntimeError once the mission has grown past it (the reference
+    itself never stops when a box contains a waypoint or keeps catching the inserted midpoints).
     """
     w = np.asarray(waypoints, dtype=float)
 
@@ -188,13 +189,14 @@ def plan_table(waypoints: np.ndarray, obstacles, velocity: float, dt: float, met
     for box in obstacles:
         tab, c, T = gen(w)
         while True:
-            hit = set()
-            for n in range(len(tab)):
-                if point_in_cuboid(tab[n, 0], tab[n, 1], tab[n, 2], box):
-                    hit.add(int(tab[n, 10]) + 1)
+            inside = ((box[0] <= tab[:, 0]) & (tab[:, 0] <= box[1]) & (box[2] <= tab[:, 1]) & (tab[:, 1] <= box[3])
+                      & (box[4] <= tab[:, 2]) & (tab[:, 2] <= box[5]))                 # point_in_cuboid on every row
+            hit = {int(sid) + 1 for sid in np.unique(tab[inside, 10])}
             if not hit:
                 break
             w = insert_midpoints(w, hit)
+            if max_waypoints is not None and len(w) > max_waypoints:
+                raise RuntimeError(f"correction loop grew past {max_waypoints} waypoints")
             tab, c, T = gen(w)
     return tab, w, c, T
 

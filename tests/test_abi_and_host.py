@@ -47,9 +47,9 @@ def test_library_exports_every_declared_symbol(nat):
 
 def test_version_and_error_string(nat):
     L = nat.lib()
-    assert L.uavb_version() == nat.ABI_VERSION == 200
+    assert L.uavb_version() == nat.ABI_VERSION == 210
     import uav_ac_b200
-    assert uav_ac_b200.__version__ == "0.2.0"
+    assert uav_ac_b200.__version__ == "0.2.1"
     assert isinstance(L.uavb_last_error(), bytes)
     assert L.uavb_device_count() >= 0
 

@@ -12,4 +12,4 @@ C ABI of ``include/uavb.h``.  Import as ``uav_ac_b200``; the module layout mirro
 There is no CPU fallback: the kernels are the only implementation, and calls raise when libuavb.so
 or a CUDA device is missing.
 """
-__version__ = "0.2.0"            # = UAVB_VERSION 200 of include/uavb.h (checked in tests/test_abi_and_host.py)
+__version__ = "0.2.1"            # = UAVB_VERSION 210 of include/uavb.h (checked in tests/test_abi_and_host.py)

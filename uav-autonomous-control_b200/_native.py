@@ -17,10 +17,11 @@ LIB_PATH = os.path.join(_PKG, "lib", "libuavb.so")
 
 N_GAINS = 11
 N_METRICS = 8
-ABI_VERSION = 200          # UAVB_VERSION of include/uavb.h this module's struct mirrors were written against
+ABI_VERSION = 210          # UAVB_VERSION of include/uavb.h this module's struct mirrors were written against
 CARRY_WORDS = 52
 STATE_DIM = 13
 MAX_SPLINES = 64
+SOLVE_OK, SOLVE_DEGENERATE, SOLVE_NONFINITE, SOLVE_TOO_MANY = range(4)
 TARGET_ROW_BYTES = 56
 GAIN_NAMES = ("kp_xy", "kd_xy", "kp_z", "kd_z", "ki_z", "kp_roll", "kp_pitch", "kp_yaw", "kp_p", "kp_q", "kp_r")
 M_FINAL_DIST, M_COLLISION, M_RMSE, M_MEAN_ERR, M_MAX_ERR, M_STATUS, M_FIRST_HIT, M_PERIODS = range(8)
@@ -31,7 +32,7 @@ M_FINAL_DIST, M_COLLISION, M_RMSE, M_MEAN_ERR, M_MAX_ERR, M_STATUS, M_FIRST_HIT,
 SYMBOLS = (
     "uavb_version", "uavb_last_error", "uavb_device_count", "uavb_device_info", "uavb_minsnap_solve_f64",
     "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_yaw_profile_f64",
-    "uavb_minsnap_table_hits_f64",
+    "uavb_minsnap_table_hits_f64", "uavb_minsnap_correct_f64", "uavb_minsnap_pack_f64", "uavb_plan_shared_f64",
     "uavb_rollout_targets_f64", "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
     "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_measure_fma_rates", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host", "uavb_rrt_workspace_bytes", "uavb_rrt_star_f64", "uavb_segments_hit_aabbs_f64",
 )
@@ -85,7 +86,7 @@ class MissionHost(Structure):
         ("B", c_int), ("n_waypoints", c_int), ("n_takeoff_waypoints", c_int), ("waypoints", c_void_p), ("velocity", c_double),
         ("start_end_time_factor", c_double), ("frequency", c_int), ("n_ticks", c_int), ("thrust_frame_lag", c_int), ("veh", Vehicle),
         ("mc_mass", c_void_p), ("mc_inertia", c_void_p), ("mc_gains", c_void_p), ("mc_wind", c_void_p), ("aabbs", c_void_p),
-        ("n_obs", c_int), ("start", c_void_p), ("goal", c_void_p),
+        ("n_obs", c_int), ("start", c_void_p), ("goal", c_void_p), ("plan_aabbs", c_void_p), ("no_correction", c_int),
     ]
 
 
@@ -113,6 +114,11 @@ def lib() -> ctypes.CDLL:
     L.uavb_minsnap_sample_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]
     L.uavb_minsnap_yaw_profile_f64.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]
     L.uavb_minsnap_table_hits_f64.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    L.uavb_minsnap_correct_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_int, c_longlong, c_void_p, c_void_p,
+                                           c_void_p, POINTER(c_int), c_void_p]
+    L.uavb_minsnap_pack_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.uavb_plan_shared_f64.argtypes = [c_int, POINTER(c_void_p), POINTER(c_int), c_void_p, c_double, c_double, c_void_p, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]
     L.uavb_rollout_targets_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_int, c_void_p]
     L.uavb_rollout_f32.argtypes = [POINTER(RolloutArgs), c_void_p]
     L.uavb_rollout_f64.argtypes = [POINTER(RolloutArgs), c_void_p]

@@ -7,32 +7,6 @@
 
 namespace uavb {
 
-// Stream-ordered device buffer that frees itself; allocation failures are recorded, not thrown.
-struct DevPool {
-  cudaStream_t st;
-  std::vector<void*> owned;
-  cudaError_t err = cudaSuccess;
-  explicit DevPool(cudaStream_t s) : st(s) {}
-  ~DevPool() {
-    for (void* p : owned) cudaFreeAsync(p, st);
-  }
-  template <class T> T* alloc(size_t n) {
-    void* p = nullptr;
-    if (err == cudaSuccess) {
-      cudaMemPool_t pool = scratch_pool();
-      err = pool ? cudaMallocFromPoolAsync(&p, (n ? n : 1) * sizeof(T), pool, st) : cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
-    }
-    if (err == cudaSuccess) owned.push_back(p);
-    return static_cast<T*>(p);
-  }
-  template <class T> T* upload(const T* host, size_t n) {
-    if (!host) return nullptr;
-    T* d = alloc<T>(n);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, st);
-    return d;
-  }
-};
-
 // Streams and events of the host-buffer calls: one set per host thread and device, created on first use and kept for the
 // life of the thread (creating and destroying a stream costs ~55 + ~65 us on the B200 box, 2 % of a 5.7 ms mission call).
 // Never destroyed explicitly: at thread / process exit the context owns them.
@@ -144,7 +118,6 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
   UAVB_REQUIRE(S0 <= UAVB_MAX_SPLINES && S1 <= UAVB_MAX_SPLINES, "fly_mission_host: too many splines in one table");
   int rc = require_device();
   if (rc) return rc;
-  const int n_seg = S0 + S1;
   const size_t B = (size_t)m->B;
   const double dt_outer = m->veh.dt * m->frequency;
 
@@ -174,42 +147,40 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
       if (e == cudaSuccess) e = cudaEventRecord(hs->ev_up, st_up);
       if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
     }
+    // plan: both tables (main.py:80-83) go through the reference's obstacle-correction loop (midpoints are inserted where a
+    // sampled point lies inside a box, minimum_snap.py:63-95; nothing is inserted on lab_course) and are packed into the
+    // segment arrays of a shared-mission rollout -- one synchronisation when nothing is hit (plan_shared_tables)
+    const bool correct = m->n_obs > 0 && !m->no_correction;
+    std::vector<double> boxes;
+    if (correct) {
+      boxes.resize((size_t)m->n_obs * 6);
+      for (size_t k = 0; k < boxes.size(); ++k) boxes[k] = m->plan_aabbs ? m->plan_aabbs[k] : (double)m->aabbs[k];
+    }
     double* d_wp = pool.upload(m->waypoints, (size_t)m->n_waypoints * 3);
+    double* d_boxes = correct ? pool.upload(boxes.data(), boxes.size()) : nullptr;
+    constexpr int kCapSeg = 2 * UAVB_MAX_SPLINES;
+    double* d_coeffs = pool.alloc<double>((size_t)kCapSeg * 24);
+    double* d_times = pool.alloc<double>(kCapSeg);
+    int* d_rows = pool.alloc<int>(kCapSeg);
+    int* d_seg_table = pool.alloc<int>(kCapSeg);
+    double* d_seg_yaw0 = pool.alloc<double>(kCapSeg);
+    if (pool.err != cudaSuccess) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
+    const double* tab_wp[2] = {d_wp, d_wp + 3 * (size_t)(m->n_takeoff_waypoints ? m->n_takeoff_waypoints - 1 : 0)};
+    const int tab_n[2] = {S0 + 1, S1 + 1};
     const double vel2[2] = {m->velocity, m->velocity};
     double* d_vel = pool.upload(vel2, 2);
-    double* d_coeffs = pool.alloc<double>((size_t)n_seg * 24);
-    double* d_times = pool.alloc<double>(n_seg);
-    int* d_status = pool.alloc<int>(2);
-    int* d_rows = pool.alloc<int>(n_seg);
-    double* d_yaw0 = pool.alloc<double>(2);
-    int* d_total = pool.alloc<int>(2);
-    const int offs[3] = {0, S0, n_seg};
-    int* d_offs = pool.upload(offs, 3);
-    if (pool.err != cudaSuccess) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
-    // plan: one K1 launch per table (main.py:80-83), then the table geometry of both
-    if (!result) result = uavb_minsnap_solve_f64(d_wp, d_vel, 1, S0, m->start_end_time_factor, d_coeffs, d_times, d_status, st);
-    if (!result && n_tab == 2)
-      result = uavb_minsnap_solve_f64(d_wp + 3 * (size_t)(m->n_takeoff_waypoints - 1), d_vel + 1, 1, S1, m->start_end_time_factor,
-                                      d_coeffs + (size_t)S0 * 24, d_times + S0, d_status + 1, st);
-    if (!result) result = uavb_minsnap_table_meta_f64(d_coeffs, d_times, d_offs, n_tab, dt_outer, d_rows, d_yaw0, d_total, st);
-    std::vector<int> rows(n_seg), seg_table(n_seg, 0);
-    std::vector<double> seg_yaw0(n_seg, 0.0);
-    double yaw0[2] = {0.0, 0.0};
-    int status[2] = {0, 0};
+    if (pool.err != cudaSuccess && !result) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
+    int status[2] = {0, 0}, tab_rows[2] = {0, 0}, n_seg = 0;
+    if (!result)
+      result = plan_shared_tables(n_tab, tab_wp, tab_n, d_vel, m->start_end_time_factor, dt_outer, d_boxes, correct ? m->n_obs : 0, kCapSeg, d_coeffs,
+                                  d_times, d_rows, d_seg_table, d_seg_yaw0, &n_seg, tab_rows, status, nullptr, st);
+    if (!result && (status[0] == UAVB_SOLVE_TOO_MANY || status[1] == UAVB_SOLVE_TOO_MANY))
+      result = set_error(UAVB_EINVAL, "fly_mission_host: obstacle correction needs more than %d splines (an obstacle probably contains a waypoint; "
+                         "the reference loops forever in this case)", UAVB_MAX_SPLINES);
+    else if (!result && (status[0] || status[1]))
+      result = set_error(UAVB_EINVAL, "fly_mission_host: degenerate mission (zero-length spline): the reference's KKT matrix is singular");
     if (!result) {
-      cudaError_t e = cudaMemcpyAsync(rows.data(), d_rows, sizeof(int) * n_seg, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(yaw0, d_yaw0, sizeof(double) * n_tab, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, sizeof(int) * n_tab, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
-      else if (status[0] || status[1])
-        result = set_error(UAVB_EINVAL, "fly_mission_host: degenerate mission (zero-length spline): the reference's KKT matrix is singular");
-    }
-    if (!result) {
-      long long total_rows = 0;
-      for (int s = 0; s < n_seg; ++s) total_rows += rows[s];
-      seg_table[0] = 1; seg_yaw0[0] = yaw0[0];
-      if (n_tab == 2) { seg_table[S0] = 1; seg_yaw0[S0] = yaw0[1]; }
+      const long long total_rows = (long long)tab_rows[0] + tab_rows[1];
       const long long whole = total_rows * m->frequency;
       const int n_ticks = m->n_ticks ? m->n_ticks : (int)(whole < 2147483647LL ? whole : 2147483647LL);
       if (n_ticks_out) *n_ticks_out = n_ticks;
@@ -220,8 +191,8 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
       a.veh = m->veh;
       a.mc_mass = d_mc_mass; a.mc_inertia = d_mc_inertia; a.mc_gains = d_mc_gains; a.mc_wind = d_mc_wind;
       a.seg_coeffs = d_coeffs; a.seg_rows = d_rows;
-      a.seg_table = pool.upload(seg_table.data(), n_seg);
-      a.seg_yaw0 = pool.upload(seg_yaw0.data(), n_seg);
+      a.seg_table = d_seg_table;
+      a.seg_yaw0 = d_seg_yaw0;
       a.n_seg_shared = n_seg;
       a.dt_outer = dt_outer;
       void* d_targets = total_rows > 0 ? static_cast<void*>(pool.alloc<char>((size_t)total_rows * UAVB_TARGET_ROW_BYTES)) : nullptr;
@@ -230,8 +201,8 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
         a.shared_targets = d_targets;
         a.n_target_rows = (int)total_rows;
       }
-      a.start = m->start ? pool.upload(m->start, 3) : d_wp;
-      a.goal = m->goal ? pool.upload(m->goal, 3) : d_wp + 3 * (size_t)(m->n_waypoints - 1);
+      a.start = pool.upload(m->start ? m->start : m->waypoints, 3);
+      a.goal = pool.upload(m->goal ? m->goal : m->waypoints + 3 * (size_t)(m->n_waypoints - 1), 3);
       a.aabbs = m->n_obs > 0 ? pool.upload(m->aabbs, (size_t)m->n_obs * 6) : nullptr;
       float* d_metrics = pool.alloc<float>(B * UAVB_N_METRICS);
       float* d_state = state_out ? pool.alloc<float>(B * UAVB_STATE_DIM) : nullptr;

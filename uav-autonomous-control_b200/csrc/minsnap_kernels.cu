@@ -120,11 +120,7 @@ __global__ void __launch_bounds__(kSolveThreads) minsnap_solve_ragged_kernel(
 
 // ---------------------------------------------------------------------------------------------
 // Table geometry: rows per segment and the look-ahead yaw of every table (minimum_snap.py:104,126-136).
-// len(np.arange(0, T, dt)) = ceil(T / dt) with the division in fp64 (NumPy's arange length rule).
-__device__ __forceinline__ int arange_len(double T, double dt) {
-  const double n = ceil(T / dt);
-  return n > 0.0 ? (n < 2147483647.0 ? (int)n : 2147483647) : 0;
-}
+// len(np.arange(0, T, dt)): arange_len (minsnap_core.cuh).
 
 // Horizontal velocity of a table row by the nested Horner recurrence of eval_row (flight_core.cuh): the same operations on the
 // same values, so every kernel that decides "is this row's yaw valid" (table geometry, K3, the set-point table of K2 and K2's

@@ -5,6 +5,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <functional>
+#include <vector>
+
 #include "../../include/uavb.h"
 
 namespace uavb {
@@ -34,6 +37,45 @@ int require_device();
 // instead of being returned to the driver at every synchronisation (the default pool does that, which costs
 // milliseconds per 100 MB).  Returns nullptr if pools are unavailable; callers then fall back to the default pool.
 cudaMemPool_t scratch_pool();
+
+// Stream-ordered device buffer that frees itself; allocation failures are recorded, not thrown.
+struct DevPool {
+  cudaStream_t st;
+  std::vector<void*> owned;
+  cudaError_t err = cudaSuccess;
+  explicit DevPool(cudaStream_t s) : st(s) {}
+  ~DevPool() {
+    for (void* p : owned) cudaFreeAsync(p, st);
+  }
+  template <class T> T* alloc(size_t n) {
+    void* p = nullptr;
+    if (err == cudaSuccess) {
+      cudaMemPool_t pool = scratch_pool();
+      err = pool ? cudaMallocFromPoolAsync(&p, (n ? n : 1) * sizeof(T), pool, st) : cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
+    }
+    if (err == cudaSuccess) owned.push_back(p);
+    return static_cast<T*>(p);
+  }
+  template <class T> T* upload(const T* host, size_t n) {
+    if (!host) return nullptr;
+    T* d = alloc<T>(n);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return d;
+  }
+};
+
+// The obstacle-correction loop behind uavb_minsnap_correct_f64 (minsnap_correct.cu) with an optional host copy of the final
+// n_waypoints / status in the same read-back as the loop's counters, and an optional hook that enqueues follow-up work behind
+// round 1 (complete after that round's synchronisation when nothing was hit).
+int correct_missions(double* waypoints, int* n_waypoints, const double* velocity, int B, int max_wp, double factor, double dt, const double* cuboids,
+                     int n_obs, long long cuboid_stride, double* coeffs_out, double* times_out, int* status_out, int* rounds_out, int* n_wp_host,
+                     int* status_host, cudaStream_t st, const std::function<int()>* after_first_round, const int* n_wp_known);
+
+// One mission of T consecutive tables planned with the correction loop into shared-mission segment arrays (uavb_plan_shared_f64).
+constexpr int kMaxSharedTables = 8;
+int plan_shared_tables(int T, const double* const* d_waypoints, const int* n_wp_in, const double* d_velocity, double factor, double dt,
+                       const double* d_cuboids, int n_obs, int cap_seg, double* seg_coeffs, double* seg_times, int* seg_rows, int* seg_table,
+                       double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out, int* rounds_out, cudaStream_t st);
 
 // SM count of the current device, cached per device (thread-safe).
 int sm_count_cached(int* sms);

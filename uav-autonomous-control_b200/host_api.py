@@ -65,11 +65,12 @@ def minsnap_solve_host(waypoints, velocity, *, start_end_time_factor: float = 1.
 def fly_mission_host(waypoints, velocity: float, B: int, *, n_takeoff_waypoints: int = 2, frequency: int = 10, n_ticks: int = 0,
                      vehicle: Optional[nat.Vehicle] = None, mc_mass=None, mc_inertia=None, mc_gains=None, mc_wind=None,
                      obstacles=None, start=None, goal=None, thrust_frame_lag: int = 1, start_end_time_factor: float = 1.5,
-                     want_state: bool = False, metrics_out=None, state_out=None):
+                     want_state: bool = False, metrics_out=None, state_out=None, correct: bool = True):
     """Plan one mission and fly it with B drones; host arrays in, host arrays out.
 
     waypoints (n, 3) f64; mc_mass (B,), mc_inertia (3, B), mc_gains (11, B), mc_wind (3, B) f32 SoA;
-    obstacles (n_obs, 6) f32.  Returns (metrics (B, 8) f32, state (13, B) f32 | None, n_ticks).
+    obstacles (n_obs, 6): the collision flag tests their fp32 copy, the planner's obstacle-correction loop
+    (minimum_snap.py:63-95; ``correct=False`` skips it) the fp64 values.  Returns (metrics (B, 8) f32, state (13, B) f32 | None, n_ticks).
     ``metrics_out`` / ``state_out`` may be preallocated (e.g. pinned) buffers.
     """
     wp = np.ascontiguousarray(waypoints, dtype=np.float64)
@@ -91,6 +92,10 @@ def fly_mission_host(waypoints, velocity: float, B: int, *, n_takeoff_waypoints:
         obs = np.ascontiguousarray(obstacles, dtype=np.float32).reshape(-1, 6)
         keep.append(obs)
         m.aabbs, m.n_obs = ctypes.c_void_p(obs.ctypes.data), obs.shape[0]
+        obs64 = np.ascontiguousarray(obstacles, dtype=np.float64).reshape(-1, 6)     # the planner tests the fp64 boxes, like the reference
+        keep.append(obs64)
+        m.plan_aabbs = ctypes.c_void_p(obs64.ctypes.data)
+    m.no_correction = 0 if correct else 1
     for field, arr in (("start", start), ("goal", goal)):
         p, k = _host_ptr(arr, np.float64, (3,), field)
         setattr(m, field, p)

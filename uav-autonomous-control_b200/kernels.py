@@ -104,6 +104,106 @@ def table_hits(table: torch.Tensor, row_offsets: torch.Tensor, cuboid: torch.Ten
     return hit_mask
 
 
+def fixed_pitch(paths, max_wp: int, device) -> tuple[torch.Tensor, torch.Tensor]:
+    """Waypoint sets of different lengths -> ([B, max_wp, 3] f64, n_waypoints [B] i32), the in/out layout of minsnap_correct.
+    ``paths``: a [B, n, 3] tensor or a sequence of (n_b, 3) arrays / tensors (CUDA tensors are copied on the device)."""
+    if isinstance(paths, torch.Tensor) and paths.dim() == 3:
+        B, n = paths.shape[0], paths.shape[1]
+        wp = torch.zeros((B, max_wp, 3), dtype=torch.float64, device=device)
+        wp[:, :n] = paths.to(device=device, dtype=torch.float64)
+        return wp, torch.full((B,), n, dtype=torch.int32, device=device)
+    counts = [int(len(pth)) for pth in paths]
+    if all(isinstance(pth, torch.Tensor) and pth.is_cuda for pth in paths):
+        wp = torch.zeros((len(paths), max_wp, 3), dtype=torch.float64, device=device)
+        for b, pth in enumerate(paths):
+            wp[b, :counts[b]] = pth
+        return wp, torch.tensor(counts, dtype=torch.int32, device=device)
+    import numpy as np
+    host = np.zeros((len(paths), max_wp, 3))
+    for b, pth in enumerate(paths):
+        host[b, :counts[b]] = pth.detach().cpu().numpy() if isinstance(pth, torch.Tensor) else np.asarray(pth, dtype=float)
+    return torch.tensor(host, dtype=torch.float64, device=device), torch.tensor(counts, dtype=torch.int32, device=device)
+
+
+def minsnap_correct(waypoints: torch.Tensor, n_waypoints: torch.Tensor, velocity: torch.Tensor, dt: float,
+                    obstacles: Optional[torch.Tensor] = None, factor: float = START_END_TIME_FACTOR):
+    """The whole obstacle-correction loop of MinimumSnap._generate_collision_free_trajectory (minimum_snap.py:63-95) on the
+    device: plan, find the splines with a sampled point inside the current obstacle, insert their midpoints, plan again.
+
+    waypoints [B, max_wp, 3] f64 and n_waypoints [B] i32 are updated IN PLACE (fixed pitch, see ``fixed_pitch``); obstacles
+    [n_obs, 6] f64 (shared) or [B, n_obs, 6], None / empty = plain plan.  Returns (coeffs [B, max_wp-1, 8, 3], times
+    [B, max_wp-1], status [B] i32, rounds).  Synchronises the current stream (uavb.h)."""
+    B, max_wp = waypoints.shape[0], waypoints.shape[1]
+    dev = waypoints.device
+    coeffs = torch.empty((B, max_wp - 1, 8, 3), dtype=torch.float64, device=dev)
+    times = torch.empty((B, max_wp - 1), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    n_obs, stride, obs = 0, 0, None
+    if obstacles is not None and obstacles.numel() > 0:
+        obs = obstacles.to(device=dev, dtype=torch.float64).contiguous()
+        if obs.dim() == 3:
+            if obs.shape[0] != B:
+                raise ValueError("per-mission obstacles must have shape (B, n_obs, 6)")
+            n_obs, stride = int(obs.shape[1]), int(obs.shape[1]) * 6
+        else:
+            obs = obs.reshape(-1, 6)
+            n_obs = int(obs.shape[0])
+    rounds = ctypes.c_int(0)
+    nat.check(nat.lib().uavb_minsnap_correct_f64(
+        nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(n_waypoints, torch.int32, "n_waypoints"), nat.ptr(velocity, torch.float64, "velocity"),
+        B, max_wp, float(factor), float(dt), nat.ptr(obs), n_obs, stride, nat.ptr(coeffs), nat.ptr(times), nat.ptr(status), ctypes.byref(rounds),
+        nat.stream_ptr(dev)), "uavb_minsnap_correct_f64")
+    return coeffs, times, status, rounds.value
+
+
+def pack_segments(coeffs: torch.Tensor, times: torch.Tensor, n_waypoints: torch.Tensor, n_seg: Optional[int] = None):
+    """Fixed pitch -> packed: (coeffs [n_seg, 8, 3], times [n_seg], seg_offsets [B+1] i32) in mission order.
+    ``n_seg``: the total spline count when the caller knows it (saves the device->host read)."""
+    B, max_wp = coeffs.shape[0], coeffs.shape[1] + 1
+    dev = coeffs.device
+    seg_offsets = torch.zeros((B + 1,), dtype=torch.int32, device=dev)
+    seg_offsets[1:] = torch.cumsum(n_waypoints - 1, 0)
+    if n_seg is None:
+        n_seg = int(seg_offsets[-1].item())
+    c = torch.empty((n_seg, 8, 3), dtype=torch.float64, device=dev)
+    t = torch.empty((n_seg,), dtype=torch.float64, device=dev)
+    nat.check(nat.lib().uavb_minsnap_pack_f64(nat.ptr(coeffs, torch.float64, "coeffs"), nat.ptr(times, torch.float64, "times"),
+                                              nat.ptr(n_waypoints, torch.int32, "n_waypoints"), B, max_wp, nat.ptr(seg_offsets), nat.ptr(c), nat.ptr(t),
+                                              nat.stream_ptr(dev)), "uavb_minsnap_pack_f64")
+    return c, t, seg_offsets
+
+
+class TooManySplines(RuntimeError):
+    """The correction loop needed more than UAVB_MAX_SPLINES splines (an obstacle probably contains a waypoint: the reference
+    loops forever in that case, minimum_snap.py:80-93)."""
+
+
+def plan_collision_free(paths, velocity: torch.Tensor, dt: float, obstacles: Optional[torch.Tensor], factor: float = START_END_TIME_FACTOR,
+                        device=None):
+    """Plan B missions with the reference's correction loop and return them packed:
+    (coeffs [n_seg, 8, 3], times [n_seg], seg_offsets [B+1], status [B], waypoints [B, max_wp, 3], n_waypoints [B], rounds).
+    The waypoint capacity starts a few midpoints above the longest mission and is raised to the solver's limit once if some
+    mission outgrows it; a mission that outgrows UAVB_MAX_SPLINES raises TooManySplines."""
+    dev = _dev(device) if not isinstance(paths, torch.Tensor) else paths.device
+    longest = int(paths.shape[1]) if isinstance(paths, torch.Tensor) else max(len(p) for p in paths)
+    n_seg0 = int(paths.shape[0] * (paths.shape[1] - 1)) if isinstance(paths, torch.Tensor) else sum(len(p) - 1 for p in paths)
+    if longest - 1 > nat.MAX_SPLINES:
+        raise TooManySplines(f"too many splines ({longest - 1}; the solver accepts at most {nat.MAX_SPLINES})")
+    cap = min(nat.MAX_SPLINES + 1, longest + 8)
+    while True:
+        wp, n_wp = fixed_pitch(paths, cap, dev)
+        coeffs, times, status, rounds = minsnap_correct(wp, n_wp, velocity, dt, obstacles, factor)
+        if not bool((status == nat.SOLVE_TOO_MANY).any()):
+            break
+        if cap == nat.MAX_SPLINES + 1:
+            bad = int((status == nat.SOLVE_TOO_MANY).nonzero()[0])
+            raise TooManySplines(f"mission {bad}: obstacle correction needs more than {nat.MAX_SPLINES} splines -- an obstacle probably "
+                                 "contains a waypoint (the reference loops forever in this case)")
+        cap = nat.MAX_SPLINES + 1
+    c, t, seg_offsets = pack_segments(coeffs, times, n_wp, n_seg0 if rounds <= 1 else None)      # one round: nothing was inserted
+    return c, t, seg_offsets, status, wp, n_wp, rounds
+
+
 # ------------------------------------------------------------------------------------------ missions
 @dataclass
 class MissionPlan:
@@ -120,6 +220,7 @@ class MissionPlan:
     times: Optional[torch.Tensor] = None       # [n_seg] f64 (MinimumSnap.times)
     targets: Optional[torch.Tensor] = None     # shared missions: [n_rows, 56] u8 per-row set-points (uavb_rollout_targets_f64)
     status: Optional[torch.Tensor] = None      # shared missions: [n_tables] i32 UAVB_SOLVE_* of each table
+    correction_rounds: int = 0                 # plan rounds of the obstacle-correction loop (1 = nothing was hit; 0 = not run)
 
     @property
     def shared(self) -> bool:
@@ -135,8 +236,13 @@ class MissionPlan:
 
 
 def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float, shared: bool = False,
-                  factor: float = START_END_TIME_FACTOR, table_rows: Optional[int] = None) -> MissionPlan:
+                  factor: float = START_END_TIME_FACTOR, table_rows: Optional[int] = None, obstacles: Optional[torch.Tensor] = None) -> MissionPlan:
     """Solve and pack missions made of consecutive MinimumSnap tables.
+
+    ``obstacles`` ([n_obs, 6] f64, or [B, n_obs, 6] per mission): every table is planned with the reference's obstacle-correction
+    loop (MinimumSnap(path, obstacles, ...).get_trajectory(), minimum_snap.py:63-95, as _generate_mission_trajectory does for
+    both tables, main.py:80-83) -- midpoints are inserted where a sampled point lies inside a box, so missions may end up with
+    different spline counts.  None plans the given waypoints as they are.
 
     ``tables`` lists (waypoints [B, S_k+1, 3], velocity [B]) per table, e.g. the vertical take-off
     (S=1) followed by the course of ``_generate_mission_trajectory`` (uav_ac/main.py:73-84).  Mission b
@@ -151,7 +257,9 @@ def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float
     if shared:
         if B != 1:
             raise ValueError("shared=True needs a single mission")
-        return _plan_shared(tables, dt, factor, table_rows)
+        return _plan_shared(tables, dt, factor, table_rows, obstacles)
+    if obstacles is not None and obstacles.numel() > 0:
+        return _plan_corrected(tables, dt, factor, obstacles)
     per_table = []
     for wp, vel in tables:
         if wp.shape[0] != B:
@@ -182,10 +290,87 @@ def plan_missions(tables: Sequence[tuple[torch.Tensor, torch.Tensor]], dt: float
 _SHARED_CONSTS: dict = {}
 
 
-def _plan_shared(tables, dt: float, factor: float, table_rows: Optional[int]) -> MissionPlan:
-    """One mission flown by every rollout: K1 per table straight into the packed segment arrays, one table-geometry launch,
-    the set-point table -- T + 5 kernel launches for T tables, no host synchronisation when ``table_rows`` is given."""
+def _plan_corrected(tables, dt: float, factor: float, obstacles: torch.Tensor) -> MissionPlan:
+    """Per-rollout missions planned with the correction loop: every table goes through minsnap_correct (ragged spline counts
+    afterwards), then the tables of a mission are laid out one after the other in the packed segment arrays."""
+    B = tables[0][0].shape[0]
     dev = tables[0][0].device
+    per_table = []
+    for wp, vel in tables:
+        if wp.shape[0] != B:
+            raise ValueError("all tables must have the same batch size")
+        c, t, seg_off, status, _, n_wp, _ = plan_collision_free(wp, vel, dt, obstacles, factor)
+        rows, yaw0, total = table_meta(c, t, seg_off, dt)
+        per_table.append((c, t, seg_off.long(), (n_wp - 1).long(), rows, yaw0, total))
+    count = sum(p[3] for p in per_table)                                   # segments per mission
+    begin = torch.cumsum(count, 0) - count
+    n_seg = int(count.sum().item())
+    seg_coeffs = torch.empty((n_seg, 8, 3), dtype=torch.float64, device=dev)
+    times = torch.empty((n_seg,), dtype=torch.float64, device=dev)
+    seg_rows = torch.empty((n_seg,), dtype=torch.int32, device=dev)
+    seg_table = torch.zeros((n_seg,), dtype=torch.int32, device=dev)
+    seg_yaw0 = torch.zeros((n_seg,), dtype=torch.float64, device=dev)
+    within = torch.zeros_like(count)
+    arange_b = torch.arange(B, device=dev)
+    for c, t, seg_off, S, rows, yaw0, total in per_table:
+        owner = torch.repeat_interleave(arange_b, S)                        # mission of every packed segment of this table
+        dest = (begin + within)[owner] + (torch.arange(c.shape[0], device=dev) - seg_off[:-1][owner])
+        seg_coeffs[dest], times[dest], seg_rows[dest] = c, t, rows
+        first = begin + within
+        seg_table[first] = 1
+        seg_yaw0[first] = yaw0
+        within = within + S
+    plan = MissionPlan(seg_coeffs, seg_rows, seg_table, seg_yaw0, float(dt), rows_per_mission=sum(p[6] for p in per_table).to(torch.int32), times=times)
+    plan.seg_begin = begin.to(torch.int32).contiguous()
+    plan.seg_count = count.to(torch.int32).contiguous()
+    return plan
+
+
+def _plan_shared_corrected(tables, dt: float, factor: float, table_rows: Optional[int], obstacles: torch.Tensor) -> MissionPlan:
+    """uavb_plan_shared_f64: the tables of one mission through the correction loop into the packed segment arrays, one C call
+    (a handful of launches, one synchronisation when nothing is hit), then the set-point table."""
+    dev = tables[0][0].device
+    T = len(tables)
+    for wp, vel in tables:
+        if wp.shape[0] != 1 or vel.shape != (1,):
+            raise ValueError("shared=True needs a single mission per table")
+    cap = T * nat.MAX_SPLINES
+    coeffs = torch.empty((cap, 8, 3), dtype=torch.float64, device=dev)
+    times = torch.empty((cap,), dtype=torch.float64, device=dev)
+    rows = torch.empty((cap,), dtype=torch.int32, device=dev)
+    seg_table = torch.empty((cap,), dtype=torch.int32, device=dev)
+    seg_yaw0 = torch.empty((cap,), dtype=torch.float64, device=dev)
+    obs = obstacles.to(device=dev, dtype=torch.float64).contiguous()
+    ptrs = (ctypes.c_void_p * T)(*[nat.ptr(wp, torch.float64, "waypoints").value for wp, _ in tables])
+    n_wp = (ctypes.c_int * T)(*[int(wp.shape[1]) for wp, _ in tables])
+    vels = torch.cat([vel for _, vel in tables]).contiguous() if T > 1 else tables[0][1]
+    n_seg, rounds = ctypes.c_int(0), ctypes.c_int(0)
+    tab_rows, status = (ctypes.c_int * T)(), (ctypes.c_int * T)()
+    nat.check(nat.lib().uavb_plan_shared_f64(T, ptrs, n_wp, nat.ptr(vels, torch.float64, "velocity"), float(factor), float(dt), nat.ptr(obs), int(obs.shape[0]), cap, nat.ptr(coeffs),
+                                             nat.ptr(times), nat.ptr(rows), nat.ptr(seg_table), nat.ptr(seg_yaw0), ctypes.byref(n_seg), tab_rows, status,
+                                             ctypes.byref(rounds), nat.stream_ptr(dev)), "uavb_plan_shared_f64")
+    if any(st == nat.SOLVE_TOO_MANY for st in status):
+        raise TooManySplines(f"obstacle correction needs more than {nat.MAX_SPLINES} splines in one table -- an obstacle probably contains a waypoint "
+                             "(the reference loops forever in this case)")
+    n = n_seg.value
+    total = sum(tab_rows)
+    plan = MissionPlan(coeffs[:n], rows[:n], seg_table[:n], seg_yaw0[:n], float(dt), times=times[:n], n_seg_shared=n)
+    plan.status = torch.tensor(list(status), dtype=torch.int32)             # host tensors: the C call already brought them back
+    plan.rows_per_mission = torch.tensor([total], dtype=torch.int32)
+    plan.correction_rounds = rounds.value
+    plan.targets = rollout_targets(plan, total)
+    return plan
+
+
+def _plan_shared(tables, dt: float, factor: float, table_rows: Optional[int], obstacles: Optional[torch.Tensor] = None) -> MissionPlan:
+    """One mission flown by every rollout: K1 per table straight into the packed segment arrays, one table-geometry launch,
+    the set-point table -- T + 5 kernel launches for T tables, no host synchronisation when ``table_rows`` is given.
+    With obstacles the T tables go through the correction loop as a batch of T missions (one extra synchronisation)."""
+    dev = tables[0][0].device
+    if obstacles is not None and obstacles.numel() > 0:
+        if obstacles.dim() != 2:
+            raise ValueError("a shared mission takes one obstacle set (n_obs, 6)")
+        return _plan_shared_corrected(tables, dt, factor, table_rows, obstacles)
     splines = tuple(int(wp.shape[1]) - 1 for wp, _ in tables)
     n_seg, T = sum(splines), len(splines)
     key = (dev, splines)

@@ -24,7 +24,6 @@ from .. import _native as nat, kernels
 class MinimumSnap:
     START_END_TIME_FACTOR = 1.5            # minimum_snap.py:10
     MIN_HORIZONTAL_SPEED_FOR_YAW = 1e-3    # minimum_snap.py:11
-    MAX_CORRECTION_ROUNDS = 32             # the reference loops forever when an obstacle contains a waypoint; this raises instead
 
     def __init__(self, path, obstacles, velocity=1.0, dt=0.01):
         """
@@ -77,6 +76,7 @@ class MinimumSnap:
         self.coeffs = None
         self.row_offsets = None
         self.status = None
+        self.correction_rounds = 0         # plan rounds of the last obstacle-correction run (1 = nothing was hit)
 
     def get_trajectory(self):
         self._generate_collision_free_trajectory()
@@ -97,6 +97,8 @@ class MinimumSnap:
     def _compute_spline_parameters(self, method="lstsq"):
         """Time allocation + coefficients for every mission (minimum_snap.py:138-153, 311-321), one K1 launch."""
         wp, wp_offs, splines = self._pack()
+        if int(splines.max()) > nat.MAX_SPLINES:
+            raise ValueError(f"too many splines ({int(splines.max())}; the solver accepts at most {nat.MAX_SPLINES} per mission)")
         B = len(self._paths)
         vel = self._velocity_tensor()
         if len(set(splines.tolist())) == 1:
@@ -121,6 +123,10 @@ class MinimumSnap:
     def _generate_trajectory(self, method="lstsq"):
         """Sampled (N, 11) table(s): rows at j*dt for j < ceil(T_i/dt) per spline, yaw hold/unwrap rules (minimum_snap.py:97-136)."""
         self._compute_spline_parameters(method)
+        return self._sample_tables()
+
+    def _sample_tables(self):
+        """Table geometry + K3 over the current coefficients."""
         B = len(self._paths)
         rows, yaw0, total = kernels.table_meta(self._coeffs_dev, self._times_dev, self._seg_offsets, self.dt)
         roff = torch.zeros(B + 1, dtype=torch.int32, device=self.device)
@@ -138,35 +144,38 @@ class MinimumSnap:
 
     def _generate_collision_free_trajectory(self):
         """Per obstacle: plan, mark the splines that own a sampled point inside the box, insert a midpoint waypoint in
-        each, re-plan until clean (minimum_snap.py:63-95).  The sweep over sampled points runs on the device for all
-        missions at once; only the (rare) waypoint insertion touches the host."""
+        each, re-plan until clean (minimum_snap.py:63-95).  The whole loop runs on the device for all missions at once
+        (kernels.minsnap_correct: every mission walks the obstacle list with its own cursor, only missions that were hit
+        are planned again); the host reads the final waypoints back, like the reference's ``self.waypoints`` after the loop."""
         if self.coord_obstacles is None:
             self._generate_trajectory()
             return
         obstacles = np.asarray(self.coord_obstacles, dtype=float).reshape(-1, 6)
-        B = len(self._paths)
-        for coord in obstacles:            # an empty obstacle array leaves full_trajectory = None, like the reference
-            paths = self._paths
-            self.reset()
-            self._paths = paths
-            self._generate_trajectory()
-            box = torch.tensor(coord, dtype=torch.float64, device=self.device)
-            for _ in range(self.MAX_CORRECTION_ROUNDS):
-                mask = torch.zeros(B, dtype=torch.int64, device=self.device)
-                kernels.table_hits(self._table_dev, self.row_offsets, box, mask)
-                mask = mask.cpu().numpy()
-                if not mask.any():
-                    break
-                for b in np.flatnonzero(mask):
-                    ids = {s + 1 for s in range(64) if (int(mask[b]) >> s) & 1}
-                    self._paths[b] = MinimumSnap.insert_midpoints_at_indexes(self._paths[b], ids)
-                paths = self._paths
-                self.reset()
-                self._paths = paths
-                self._generate_trajectory()
-            else:
-                raise RuntimeError("obstacle correction did not converge: an obstacle probably contains a waypoint "
-                                   "(the reference loops forever in this case)")
+        if len(obstacles) == 0:            # an empty obstacle array leaves full_trajectory = None, like the reference
+            return
+        paths = self._paths
+        self.reset()
+        self._paths = paths
+        obs = torch.tensor(obstacles, dtype=torch.float64, device=self.device)
+        try:
+            c, t, seg_off, status, wp, n_wp, self.correction_rounds = kernels.plan_collision_free(
+                self._paths, self._velocity_tensor(), self.dt, obs, self.START_END_TIME_FACTOR, device=self.device)
+        except kernels.TooManySplines as exc:
+            raise RuntimeError(f"obstacle correction did not converge: {exc}") from None
+        if bool((status != 0).any()):
+            bad = int((status != 0).nonzero()[0])
+            raise np.linalg.LinAlgError(f"mission {bad}: zero-length spline or non-positive velocity (singular minimum-snap system)")
+        wp_h, n_h = wp.cpu().numpy(), n_wp.cpu().numpy()
+        self._paths = [wp_h[b, :n_h[b]].copy() for b in range(len(n_h))]
+        self._coeffs_dev, self._times_dev, self._seg_offsets, self.status = c, t, seg_off, status
+        splines = (n_h - 1).tolist()
+        self.nb_splines = int(splines[0]) if self._single else splines
+        if self._single:
+            self.coeffs = c.reshape(-1, 3).cpu().numpy()
+            self.times = t.cpu().numpy().tolist()
+        else:
+            self.coeffs, self.times = c, t
+        self._sample_tables()
 
     def trajectories(self) -> List[np.ndarray]:
         """Per-mission (N_b, 11) NumPy tables of a batched plan."""
@@ -177,7 +186,7 @@ class MinimumSnap:
     @staticmethod
     def _calculate_yaws(velocities) -> np.ndarray:
         """Heading profile of a velocity sequence (minimum_snap.py:126-136), computed by the K3 yaw kernels."""
-        v = torch.tensor(np.asarray(velocities, dtype=float).reshape(-1, 3), dtype=torch.float64, device="cuda")
+        v = torch.tensor(np.asarray(velocities, dtype=float).reshape(-1, 3), dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
         n = v.shape[0]
         out = torch.empty(n, dtype=torch.float64, device=v.device)
         offs = torch.tensor([0, n], dtype=torch.int32, device=v.device)

@@ -103,14 +103,16 @@ class BatchedSimulation:
     # ------------------------------------------------------------------ fused path
     def rollout(self, velocity: float, frequency: int = 10, n_ticks: Optional[int] = None, *, gains: Optional[dict] = None,
                 log_stride: int = 0, want_state: bool = True):
-        """Plan the mission (take-off table + course table, main.py:73-84) and fly it for every drone in one launch of
+        """Plan the mission (take-off table + course table, each with the obstacle-correction loop, main.py:73-84) and fly it for every drone in one launch of
         the persistent rollout kernel.  ``gains`` maps gain names to (B,) tensors (Monte-Carlo); mass / inertia
         perturbations come from the Quad.  Returns ``kernels.RolloutResult`` (metrics (B, 8), final state, log)."""
         q = self.quad
         dev = self.device
         wp = torch.tensor(self.mission_waypoints, dtype=torch.float64, device=dev)
         vel = torch.tensor([float(velocity)], dtype=torch.float64, device=dev)
-        plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], q.dt * frequency, shared=True)
+        obs64 = torch.tensor(self.obstacles, dtype=torch.float64, device=dev) if len(self.obstacles) else None
+        plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], q.dt * frequency, shared=True,
+                                     obstacles=obs64)       # both tables through the correction loop, like _generate_mission_trajectory
         if n_ticks is None:
             n_ticks = frequency * int(plan.total_rows.item())
         veh, mc = q.vehicle_struct(self.batch, gains or {})
