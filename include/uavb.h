@@ -239,6 +239,8 @@ typedef struct uavb_rollout_args {
   float*        state_out;    /* [13][B] final X, SoA; may be NULL                                     */
   float*        metrics_out;  /* [B][UAVB_N_METRICS]; may be NULL                                      */
   float*        log_out;      /* [n_ticks / log_stride][13][B] SoA samples; required iff log_stride > 0 */
+  int           log_tma;      /* 0 = library policy: the fp32 log leaves through staged TMA tensor stores when B is a multiple of 4 and
+                                 log_out is 16-byte aligned, else through per-thread streaming stores; -1 = always the latter (same bits) */
 } uavb_rollout_args;
 
 /* Set-points of every table row of ONE mission (the rows MinimumSnap._generate_trajectory would sample, :97-124, plus the

@@ -408,3 +408,20 @@ def test_state_log_is_identical_across_slice_counts(cuda, monkeypatch):
         assert torch.equal(logs[0].log, logs[1].log) and torch.equal(logs[0].state, logs[1].state) and torch.equal(logs[0].metrics, logs[1].metrics)
         if n % stride == 0:
             assert torch.equal(logs[0].log[-1], logs[0].state)
+
+
+def test_state_log_through_tensor_stores_equals_per_thread_stores(cuda):
+    """The staged TMA log (uavb_rollout_args.log_tma = 0, batches that are a multiple of 4) against the per-thread streaming stores
+    (log_tma = -1): same samples, same places, same bits -- for whole and ragged last warps, strides that do and do not divide
+    the staging depth or the slice length, odd sample counts, and several slices; a batch that is not a multiple of 4 takes the
+    per-thread path by itself."""
+    import torch
+    plan = lab_course_plan(cuda, 3.0)
+    rng = np.random.default_rng(17)
+    for B, n, stride, slices in ((96, 1001, 1, 1), (700, 2350, 7, 9), (1028, 1500, 50, 3), (4, 333, 3, 2), (131072, 400, 1, 0), (98, 500, 1, 1)):
+        mc = mc_arrays(cuda, B, rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3)))
+        a = _fly(cuda, plan, B, n, log_stride=stride, n_slices=slices, **mc)
+        b = _fly(cuda, plan, B, n, log_stride=stride, n_slices=slices, log_tma=-1, **mc)
+        assert a.log.shape == (n // stride, 13, B)
+        assert torch.equal(a.log, b.log) and torch.equal(a.state, b.state) and torch.equal(a.metrics, b.metrics), (B, n, stride, slices)
+        assert bool(torch.isfinite(a.log).all())

@@ -17,7 +17,7 @@ for B, ticks, stride in [(16384, 4000, 1), (75776, 800, 1), (151552, 400, 1), (3
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         kernels.rollout(plan, B, ticks, start=torch.tensor(LAB_COURSE_START, **f64), goal=torch.tensor(LAB_COURSE_GOAL, **f64), obstacles=obs,
-                        want_state=False, want_metrics=False, log_stride=stride, out=res)
+                        want_state=False, want_metrics=False, log_stride=stride, out=res, log_tma=int(os.environ.get('LOG_TMA', '0')))
         b.record(); torch.cuda.synchronize()
         if i: ts.append(a.elapsed_time(b))
     t = statistics.mean(ts)

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <mutex>
 
+#include "tma.cuh"
 #include "uavb_common.cuh"
 
 namespace uavb {
@@ -53,6 +54,20 @@ cudaMemPool_t scratch_pool() {
     }
   });
   return pools[dev];
+}
+
+TensorMapEncodeTiledFn tensor_map_encoder() {
+  static TensorMapEncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
 }
 
 // SM count of the current device (one query per device and process, thread-safe).

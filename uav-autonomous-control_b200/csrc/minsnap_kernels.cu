@@ -8,6 +8,7 @@
 
 #include "minsnap_core.cuh"
 #include "rollout_core.cuh"
+#include "tma.cuh"
 #include "uavb_common.cuh"
 
 namespace uavb {
@@ -24,12 +25,18 @@ constexpr int kSolveThreads = 64;
 //   kStageMission the whole mission ([thread][24 S + 1]) is staged and leaves as one contiguous tile (49.7 KB at S = 4).
 //   kDirect       per-thread stores straight from registers (S > 8: work arrays in local memory anyway).
 // Threads past the end of the batch run the solve on the last mission (they must reach the barriers) and store nothing.
-enum { kDirect = 0, kStageMission = 1, kStageSpline = 2, kStagePair = 3 };
+//   kStageTma     two splines per flush like kStagePair, but the 64 x 48-double tile leaves the CTA as THREE 2-D tensor stores
+//                 (cp.async.bulk.tensor.2d, boxes of 64 missions x 16 doubles over the [B][24 S] coefficient matrix) issued by one
+//                 thread instead of a 48-iteration copy loop run by every thread; the tile is staged in the 128-byte swizzle
+//                 the tensor map declares (16-byte chunk c of row r at chunk c ^ (r & 7)), rows past the end of the batch and the
+//                 unused half of an odd last flush are clipped by the map.
+enum { kDirect = 0, kStageMission = 1, kStageSpline = 2, kStagePair = 3, kStageTma = 4 };
+constexpr int kTmaSubTileBytes = kSolveThreads * 128;     // 64 rows x 16 doubles
 
 template <int MAXS, int MODE, int MINB>
 __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_kernel(
     const double* __restrict__ waypoints, const double* __restrict__ velocity, int B, int S, double factor,
-    double* __restrict__ coeffs_out, double* __restrict__ times_out, int* __restrict__ status_out) {
+    double* __restrict__ coeffs_out, double* __restrict__ times_out, int* __restrict__ status_out, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ double s_out[];
   const int per = 24 * S;              // doubles per mission
   const long long base = (long long)blockIdx.x * kSolveThreads;
@@ -72,6 +79,30 @@ __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_kernel(
           }
           __syncthreads();
         });
+  } else if constexpr (MODE == kStageTma) {
+    char* tiles = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(s_out) + 1023) & ~(uintptr_t)1023);      // 128-byte swizzle: 1024-byte aligned
+    char* row = tiles + threadIdx.x * 128;
+    const unsigned sw = (threadIdx.x & 7u) << 4;
+    st = minsnap_solve_one<MAXS>(
+        S, velocity[bb], factor, loadw,
+        [row, sw](int seg, int j, int ax, double val) {
+          const int off = (seg & 1) * 24 + j * 3 + ax, q = off >> 4, d = off & 15;           // sub-tile, double within the 128-byte row
+          *reinterpret_cast<double*>(row + q * kTmaSubTileBytes + ((((unsigned)d >> 1) << 4) ^ sw) + (d & 1) * 8) = val;
+        },
+        storet,
+        [&](int seg) {
+          const bool last = seg == S - 1;
+          if (!(seg & 1) && !last) return;                 // uniform: S is the same for the whole launch
+          const int first = (seg & 1) ? seg - 1 : seg, n_sub = (seg & 1) ? 3 : 2;            // a lone last spline fills 24 of the 48 columns
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            for (int q = 0; q < n_sub; ++q) tensor_store_2d(&tmap, first * 24 + q * 16, (int)base, tiles + q * kTmaSubTileBytes);
+            bulk_commit();
+            bulk_wait_read<0>();                           // the tile may be overwritten (or the CTA may end) once it has been read
+          }
+          if (!last) __syncthreads();
+        });
   } else if constexpr (MODE == kStageMission) {
     const int pitch = per + 1;
     double* mine = s_out + (size_t)threadIdx.x * pitch;
@@ -92,6 +123,91 @@ __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_kernel(
                                  storet);
   }
   if (live && status_out) status_out[b] = st;
+}
+
+// K1, streaming form (S <= 8, tensor-map output): a persistent grid of CTAs walks the 64-mission tiles.  Every global access of
+// the tile is asynchronous: the NEXT tile's waypoints and velocities (64 x 24 (S+1) + 512 contiguous bytes) arrive by bulk copy
+// (cp.async.bulk, completion on an mbarrier) while the current tile is solved, and the coefficients leave by tensor stores as in
+// kStageTma.  The one-shot kernels above start every CTA with a dependent global load of its waypoints (ncu: 4.2 long-scoreboard
+// stall cycles per issued instruction at 11 warps per SM); here a CTA waits for memory once, at its first tile.
+#ifndef UAVB_K1_STREAM_CTAS
+#define UAVB_K1_STREAM_CTAS 4
+#endif
+constexpr int kStreamCtasPerSm = UAVB_K1_STREAM_CTAS;
+template <int MAXS, int MINB>
+__global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_stream_kernel(
+    const double* __restrict__ waypoints, const double* __restrict__ velocity, int B, int S, double factor, double* __restrict__ times_out,
+    int* __restrict__ status_out, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ double s_out[];
+  __shared__ uint64_t s_bar;
+  char* tiles = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(s_out) + 1023) & ~(uintptr_t)1023);
+  double* s_wp = reinterpret_cast<double*>(tiles + 3 * kTmaSubTileBytes);       // [64][3 (S+1)]
+  const int wpd = 3 * (S + 1);
+  double* s_vel = s_wp + kSolveThreads * wpd;                                   // [64]
+  char* row = tiles + threadIdx.x * 128;
+  const unsigned sw = (threadIdx.x & 7u) << 4;
+  const int n_tiles = (B + kSolveThreads - 1) / kSolveThreads;
+  // the input of tile t: one bulk copy per array when the tile is whole, a cooperative copy for the ragged last tile (a bulk copy
+  // needs a multiple of 16 bytes, 64 missions always are)
+  auto prefetch = [&](int tile) {                         // thread 0
+    if ((long long)(tile + 1) * kSolveThreads > B) return;
+    const uint32_t wp_bytes = (uint32_t)(kSolveThreads * wpd * 8), vel_bytes = kSolveThreads * 8;
+    mbar_expect_tx(&s_bar, wp_bytes + vel_bytes);
+    bulk_load_1d(s_wp, waypoints + (size_t)tile * kSolveThreads * wpd, wp_bytes, &s_bar);
+    bulk_load_1d(s_vel, velocity + (size_t)tile * kSolveThreads, vel_bytes, &s_bar);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x);
+  }
+  __syncthreads();
+  unsigned phase = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long base = (long long)tile * kSolveThreads;
+    const int n_here = (int)((B - base) < kSolveThreads ? (B - base) : kSolveThreads);
+    const bool live = (int)threadIdx.x < n_here;
+    if (n_here == kSolveThreads) {
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+    } else {                                              // ragged last tile (the last iteration of one CTA)
+      for (int e = threadIdx.x; e < n_here * wpd; e += kSolveThreads) s_wp[e] = __ldg(waypoints + (size_t)base * wpd + e);
+      if (live) s_vel[threadIdx.x] = __ldg(velocity + base + threadIdx.x);
+      __syncthreads();
+    }
+    // this thread's mission into registers (threads past the end of the batch solve the tile's first mission and store nothing)
+    const int src = live ? threadIdx.x : 0;
+    double wreg[3 * (MAXS + 1)];
+#pragma unroll
+    for (int k = 0; k < 3 * (MAXS + 1); ++k)
+      if (k < wpd) wreg[k] = s_wp[src * wpd + k];
+    const double vel = s_vel[src];
+    if (threadIdx.x == 0) bulk_wait_read<0>();            // ... and the previous tile's last tensor store has read the staging tile
+    __syncthreads();                                      // the input buffer is free: fetch the tile this CTA solves next
+    if (threadIdx.x == 0 && tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+    double* tout = times_out + (size_t)(base + src) * S;
+    const int st = minsnap_solve_one<MAXS>(
+        S, vel, factor, [&wreg](int i, int ax) { return wreg[3 * i + ax]; },
+        [row, sw](int seg, int j, int ax, double val) {
+          const int off = (seg & 1) * 24 + j * 3 + ax, q = off >> 4, d = off & 15;
+          *reinterpret_cast<double*>(row + q * kTmaSubTileBytes + ((((unsigned)d >> 1) << 4) ^ sw) + (d & 1) * 8) = val;
+        },
+        [tout, live](int seg, double t) { if (live) tout[seg] = t; },
+        [&](int seg) {
+          const bool last = seg == S - 1;
+          if (!(seg & 1) && !last) return;
+          const int first = (seg & 1) ? seg - 1 : seg, n_sub = (seg & 1) ? 3 : 2;
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            for (int q = 0; q < n_sub; ++q) tensor_store_2d(&tmap, first * 24 + q * 16, (int)base, tiles + q * kTmaSubTileBytes);
+            bulk_commit();
+            if (!last) bulk_wait_read<0>();               // the next pair of splines overwrites the tile right away; after the last
+          }                                               // flush the wait moves to the next tile's barrier (a whole solve later)
+          if (!last) __syncthreads();
+        });
+    if (live && status_out) status_out[base + threadIdx.x] = st;
+  }
+  if (threadIdx.x == 0) bulk_wait_read<0>();              // shared memory must outlive the last store's read
 }
 
 // K1, ragged S (obstacle-correction loop): per-thread direct stores, packed segments.
@@ -174,9 +290,12 @@ __global__ void __launch_bounds__(128) table_meta_kernel(const double* __restric
 // evaluate position / velocity / acceleration, and resolve the yaw column with warp scans that carry their state from
 // chunk to chunk: np.unwrap over the valid rows is raw + cumsum(correction) (a prefix sum), hold-last-valid is a
 // fill-forward from the nearest valid lane, and rows before the first valid row take the first valid yaw, found by a
-// short velocity-only pre-scan (minimum_snap.py:126-136).  Each 32 x 11 tile is staged in shared memory and leaves the
-// warp as one contiguous 2 816-byte block of fully coalesced 8-byte stores.
+// short velocity-only pre-scan (minimum_snap.py:126-136).  Each 32 x 11 tile is staged in shared memory (two buffers per warp) and
+// leaves as ONE bulk asynchronous copy (cp.async.bulk, 2 816 contiguous bytes) issued by lane 0 while the warp evaluates the next
+// 32 rows; a bulk copy needs 16-byte alignment at both ends and rows are 88 bytes, so a mission that starts on an odd table row
+// stages its tile 8 bytes up and writes its first row -- and a chunk with an odd row count its last row -- with plain stores.
 constexpr int kSampleWarps = 4;
+constexpr int kTileDoubles = 32 * 11 + 2;                  // + the 8-byte shift, rounded to 16 bytes
 
 struct RowEval {
   double p[3], v[3], a[3];
@@ -193,7 +312,7 @@ __device__ __forceinline__ void eval_table_row(const double* __restrict__ c, dou
 __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
                                                                          const int* __restrict__ seg_rows, const int* __restrict__ row_offsets,
                                                                          int B, double dt, double* __restrict__ table) {
-  __shared__ double s_tile[kSampleWarps][32 * 11];
+  __shared__ __align__(16) double s_tile[kSampleWarps][2][kTileDoubles];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -202,7 +321,8 @@ __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const d
   const int s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
   const long long row0 = row_offsets[b];
   const int N = (int)(row_offsets[b + 1] - row0);
-  double* tile = s_tile[wib];
+  const int head = (int)(row0 & 1);                        // rows before the first 16-byte aligned one (base is a multiple of 32)
+  int buf = 0;
 
   // segment cursor shared by the warp: segment `cs` starts at mission row `cf`
   auto locate = [&](int g, int& s, int& f) {           // advance (s, f) until row g lies in segment s
@@ -285,19 +405,34 @@ __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const d
       have_prev = true;
     }
     cum += __shfl_sync(full, incl, 31);
-    // ---- stage the tile and write it out contiguously
+    // ---- stage the tile and send it off
+    double* tile = s_tile[wib][buf] + head;
+    if (lane == 0) bulk_wait_read<1>();                    // the copy that last read this buffer (two chunks ago) is done with it
+    __syncwarp();
     if (active) {
       double* o = tile + lane * 11;
       o[0] = r.p[0]; o[1] = r.p[1]; o[2] = r.p[2]; o[3] = r.v[0]; o[4] = r.v[1]; o[5] = r.v[2];
       o[6] = r.a[0]; o[7] = r.a[1]; o[8] = r.a[2]; o[9] = yaw; o[10] = (double)(s - s0);
     }
+    fence_proxy_async_smem();                              // every lane: its staged row before the async-proxy read
     __syncwarp();
-    const int n_here = (N - base < 32 ? N - base : 32) * 11;
+    const int rows_here = N - base < 32 ? N - base : 32;
+    const int first = head < rows_here ? head : rows_here;                 // plain-store rows in front ...
+    const int bulk_rows = (rows_here - first) & ~1;                        // ... an even number of rows by the bulk copy ...
     double* out = table + (size_t)(row0 + base) * 11;
-    for (int e = lane; e < n_here; e += 32) out[e] = tile[e];
-    __syncwarp();
+    if (lane == 0 && bulk_rows > 0) {
+      bulk_store_1d(out + first * 11, tile + first * 11, (uint32_t)bulk_rows * 88u);
+      bulk_commit();
+    }
+    if (lane < 11) {
+      if (first) out[lane] = tile[lane];
+      const int last = first + bulk_rows;                                  // ... and at most one row behind
+      if (last < rows_here) out[last * 11 + lane] = tile[last * 11 + lane];
+    }
+    buf ^= 1;
     locate(base + 31 < N ? base + 31 : N - 1, cs, cf);
   }
+  if (lane == 0) bulk_wait_read<0>();                      // shared memory must outlive the copies that read it
 }
 
 // `col` points at the yaw entry of row 0 and consecutive rows are `stride` doubles apart (11 inside a table, 1 for a
@@ -367,15 +502,24 @@ __global__ void __launch_bounds__(128) table_hits_kernel(const double* __restric
 }
 
 template <int MAXS, int MODE, int MINB>
-static int launch_solve(const double* w, const double* vel, int B, int S, double factor, double* c, double* t, int* st, cudaStream_t stream) {
+static int launch_solve(const double* w, const double* vel, int B, int S, double factor, double* c, double* t, int* st, cudaStream_t stream,
+                        const CUtensorMap* tmap = nullptr) {
   const size_t smem = MODE == kStageMission ? sizeof(double) * (size_t)kSolveThreads * (24 * S + 1)
                                             : (MODE == kStageSpline ? sizeof(double) * (size_t)kSolveThreads * 25
-                                               : (MODE == kStagePair ? sizeof(double) * (size_t)kSolveThreads * 49 : 0));
+                                               : (MODE == kStagePair ? sizeof(double) * (size_t)kSolveThreads * 49
+                                                  : (MODE == kStageTma ? (size_t)3 * kTmaSubTileBytes + 1024 : 0)));
   if (smem > 48 * 1024)
     UAVB_CUDA_OK(cudaFuncSetAttribute(minsnap_solve_kernel<MAXS, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  minsnap_solve_kernel<MAXS, MODE, MINB><<<div_up(B, kSolveThreads), kSolveThreads, smem, stream>>>(w, vel, B, S, factor, c, t, st);
+  CUtensorMap none = {};
+  minsnap_solve_kernel<MAXS, MODE, MINB><<<div_up(B, kSolveThreads), kSolveThreads, smem, stream>>>(w, vel, B, S, factor, c, t, st, tmap ? *tmap : none);
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
+}
+
+// The [B][24 S] coefficient matrix as a tensor map with boxes of 64 missions x 16 doubles in the 128-byte swizzle (kStageTma).
+static bool coeff_tensor_map(CUtensorMap* tm, double* coeffs, int B, int S) {
+  return make_tensor_map_2d(tm, coeffs, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 24ull * S, (unsigned long long)B, 192ull * S, 16, kSolveThreads,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace uavb
@@ -404,6 +548,11 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
         case 6: return launch_solve<4, kDirect, 8>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
         case 7: return launch_solve<4, kStageSpline, 10>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
         case 8: return launch_solve<4, kStagePair, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+        case 9: {
+          CUtensorMap tmv;
+          if (coeff_tensor_map(&tmv, coeffs_out, B, S)) return launch_solve<4, kStageTma, 8>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st, &tmv);
+          break;
+        }
         default: break;
       }
     }
@@ -414,8 +563,33 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
   // S <= 4 (BASELINE configs[1]): 6 CTAs per SM (168 registers) measured fastest -- 0.216 ms per 10^6 solves against 0.250 ms
   // unconstrained (198 registers, 5 CTAs) and 0.238 ms at 8 CTAs (128 registers, spills); tools/k1_sweep.sh
   // ... and staging two splines at a time (384-byte chunks = whole 128-byte lines, 25 KB per CTA) 0.198 ms against 0.2026 ms
-  if (S <= 4) return launch_solve<4, kStagePair, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
-  if (S <= 8) return launch_solve<8, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  // ... and, where the driver gives a tensor map (16-byte aligned output), the tile leaves through the TMA unit instead of a copy loop
+  CUtensorMap tm;
+  const bool tma = S > 2 && S <= 8 && coeff_tensor_map(&tm, coeffs_out, B, S);
+  bool streaming = tma && S == 4 &&     // measured: S = 3 is 5 % faster one-shot (6 CTAs per SM), S = 4 14 % faster streaming
+                   (reinterpret_cast<uintptr_t>(waypoints) & 15u) == 0 && (reinterpret_cast<uintptr_t>(velocity) & 15u) == 0;
+#ifdef UAVB_DEV
+  if (getenv("UAVB_K1_ONESHOT")) streaming = false;           // development builds only: the one-shot tensor-store kernel for comparison
+#endif
+  if (streaming) {
+    int sms = 0;
+    rc = sm_count_cached(&sms);
+    if (rc) return rc;
+    const size_t smem = (size_t)3 * kTmaSubTileBytes + 1024 + sizeof(double) * kSolveThreads * (3 * (S + 1) + 1);
+    const int n_tiles = div_up(B, kSolveThreads);
+    const int grid = n_tiles < kStreamCtasPerSm * sms ? n_tiles : kStreamCtasPerSm * sms;
+    minsnap_solve_stream_kernel<4, kStreamCtasPerSm><<<grid, kSolveThreads, smem, st>>>(waypoints, velocity, B, S, factor, times_out, status_out, tm);
+    UAVB_CUDA_OK(cudaGetLastError());
+    return UAVB_OK;
+  }
+  if (S <= 4) {
+    if (tma) return launch_solve<4, kStageTma, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st, &tm);
+    return launch_solve<4, kStagePair, 6>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  }
+  if (S <= 8) {
+    if (tma) return launch_solve<8, kStageTma, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st, &tm);
+    return launch_solve<8, kStageSpline, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
+  }
   return launch_solve<UAVB_MAX_SPLINES, kDirect, 1>(waypoints, velocity, B, S, factor, coeffs_out, times_out, status_out, st);
 }
 

@@ -334,9 +334,10 @@ __device__ __forceinline__ void write_outputs(const uavb_rollout_args& a, long l
 
 // One PAIR of drones (2j, 2j+1), one slice of their mission: the production fp32 path (rollout_pair.cuh).  Arguments as
 // drone_slice.  When B is odd the last pair's second lane re-flies the first drone and writes nothing.
-template <bool LOG, bool MC, bool TABLE, bool LAG>
+// LOG: 0 = no state log, 1 = per-thread streaming stores (PairLog), 2 = staged tensor stores (PairLogTma, `maps` required).
+template <int LOG, bool MC, bool TABLE, bool LAG>
 __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long j, int n_ticks, bool from_carry, bool to_carry,
-                                           bool finish, int launch_tick0) {
+                                           bool finish, int launch_tick0, const LogTma* maps = nullptr) {
   const uavb_rollout_args& a = p.a;
   const long long B = a.B;
   const long long i0 = 2 * j;
@@ -388,7 +389,20 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
       if constexpr (MC) rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, v2, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg);
       else rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, p.vp, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg);
     };
-    if constexpr (LOG) {
+    if constexpr (LOG == 2) {
+      extern __shared__ __align__(128) float s_dyn_f32[];     // tensor stores read 128-byte aligned shared memory
+      PairLogTma lg;
+      lg.maps = maps;
+      lg.stage = s_dyn_f32 + maps->stage_offset / 4 + (threadIdx.x >> 5) * kLogTmaWarpFloats;
+      lg.mine = reinterpret_cast<float2*>(lg.stage) + (threadIdx.x & 31);
+      lg.mask = __activemask();
+      lg.col = (int)(2 * (j - (threadIdx.x & 31)));
+      lg.sample = launch_tick0 / a.log_stride;
+      lg.stride = a.log_stride; lg.left = a.log_stride - launch_tick0 % a.log_stride;
+      lg.filled = 0; lg.buf = 0;
+      with_log(lg);
+      lg.finish();
+    } else if constexpr (LOG == 1) {
       PairLog lg;
       lg.out = reinterpret_cast<float*>(a.log_out) + (size_t)(launch_tick0 / a.log_stride) * 13 * B + i0;
       lg.B = (unsigned)B; lg.stride = a.log_stride; lg.left = a.log_stride - launch_tick0 % a.log_stride;
@@ -416,7 +430,7 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
   if (second) {
     get_lane<1>(d, s);
     if (to_carry) Carry{a.carry + i1, B}.store(s, c[1], acc[1], tick0 + n_ticks);
-    if (finish) write_outputs(a, i1, s, c[1], acc[1], LOG);
+    if (finish) write_outputs(a, i1, s, c[1], acc[1], LOG != 0);
   }
 }
 
@@ -465,9 +479,9 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-template <bool MC, bool TABLE, bool LOG, bool LAG>
-__global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
-  extern __shared__ float s_boxes[];
+template <bool MC, bool TABLE, int LOG, bool LAG>
+__device__ __forceinline__ void sliced_body(const RolloutDev<float>& p, const SliceSched& sch, const LogTma* maps) {
+  extern __shared__ __align__(128) float s_boxes[];
   __shared__ int s_item;
   stage_shared_boxes(p.a, s_boxes);
   const int n_items = sch.n_groups * sch.n_chunks;
@@ -488,7 +502,7 @@ __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid
     if (2 * j < p.a.B) {
       const bool last = c == sch.n_chunks - 1;
       const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
-      pair_slice<LOG, MC, TABLE, LAG>(p, j, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
+      pair_slice<LOG, MC, TABLE, LAG>(p, j, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks, maps);
     }
     __threadfence();
     __syncthreads();
@@ -496,10 +510,23 @@ __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid
   }
 }
 
+template <bool MC, bool TABLE, bool LOG, bool LAG>
+__global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
+  sliced_body<MC, TABLE, LOG ? 1 : 0, LAG>(p, sch, nullptr);
+}
+
+// The state log through staged tensor stores (PairLogTma); `maps` lives in the kernel parameter space, where the TMA unit reads it.
+template <bool MC, bool TABLE, bool LAG>
+__global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_tma_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch,
+                                                                         const __grid_constant__ LogTma maps) {
+  sliced_body<MC, TABLE, 2, LAG>(p, sch, &maps);
+}
+
 
 // Host-side launchers, one per translation unit (kernel templates are instantiated where they are launched).
 void launch_rollout_sliced(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
-void launch_rollout_sliced_log(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
+void launch_rollout_sliced_log(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch,
+                               const LogTma* maps);      // maps != nullptr: staged tensor stores
 void launch_rollout_f64(bool log, bool mc, int grid, size_t smem, cudaStream_t st, const RolloutDev<double>& p);
 
 }  // namespace uavb

@@ -170,7 +170,24 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     sch.done = sch.counter + 1;
     sch.n_groups = grid; sch.n_chunks = n_chunks; sch.chunk_ticks = chunk;
     const int pgrid = slots < grid ? slots : grid;
-    if (log) launch_rollout_sliced_log(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
+    // state log: through the TMA unit when the [samples x 13][B] log is a legal tensor (rows a multiple of 16 bytes, 16-byte aligned)
+    LogTma maps;
+    bool tma_log = false;
+    if (log && a->log_tma >= 0) {
+      const unsigned long long n_samples = (unsigned long long)(a->n_ticks / a->log_stride);
+      if (a->B % 4 == 0 && n_samples > 0 && n_samples * 13ull < 2000000000ull) {
+        tma_log = make_tensor_map_2d(&maps.box_k, a->log_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (unsigned long long)a->B, n_samples * 13ull, 4ull * a->B, 64,
+                                     13 * kLogTmaSamples, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+                  make_tensor_map_2d(&maps.box_1, a->log_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (unsigned long long)a->B, n_samples * 13ull, 4ull * a->B, 64, 13,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
+      }
+      if (tma_log) {
+        smem = (smem + 127) / 128 * 128;
+        maps.stage_offset = (int)smem;
+        smem += sizeof(float) * kLogTmaWarpFloats * (kRolloutThreadsLog / 32);
+      }
+    }
+    if (log) launch_rollout_sliced_log(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch, tma_log ? &maps : nullptr);
     else launch_rollout_sliced(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
   }
   UAVB_CUDA_OK(cudaGetLastError());

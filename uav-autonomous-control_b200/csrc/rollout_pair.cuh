@@ -10,6 +10,7 @@
 
 #include "flight_pair.cuh"
 #include "rollout_core.cuh"
+#include "tma.cuh"
 
 namespace uavb {
 
@@ -39,6 +40,63 @@ struct PairLog {
     put(o + (size_t)(7u * b), d.vx); put(o + (size_t)(8u * b), d.vy); put(o + (size_t)(9u * b), d.vz);
     put(o + (size_t)(10u * b), d.wx); put(o + (size_t)(11u * b), d.wy); put(o + (size_t)(12u * b), d.wz);
     out = o + (size_t)(13u * b);
+  }
+};
+
+// The same log through the TMA unit: every warp stages kLogTmaSamples samples x 13 fields x 64 drones in shared memory (one
+// conflict-free 8-byte shared store per field and thread, 32-bit addressing) and its first lane sends the 13 kLogTmaSamples x 256-byte
+// box to the [samples x 13][B] log with ONE tensor store -- instead of 13 global stores with 64-bit address arithmetic per thread
+// and sample -- while the warp flies on into the second staging buffer.  Samples left over at the end of a slice leave through
+// the one-sample map.  Drones past the end of the batch are clipped by the map (B is a multiple of 4 on this path).
+constexpr int kLogTmaSamples = 2;
+constexpr int kLogTmaSampleFloats = 13 * 64;               // one sample of one warp
+constexpr int kLogTmaWarpFloats = 2 * kLogTmaSamples * kLogTmaSampleFloats;    // two buffers
+struct alignas(64) LogTma {
+  CUtensorMap box_k;       // boxes of (13 kLogTmaSamples) rows x 64 drones
+  CUtensorMap box_1;       // boxes of 13 rows x 64 drones
+  int stage_offset;        // byte offset of the staging area in dynamic shared memory (128-byte aligned)
+};
+struct PairLogTma {
+  static constexpr bool kNormEveryTick = true;
+  const LogTma* maps;
+  float* stage;            // this warp's staging area
+  float2* mine;            // ... + this lane's column pair in buffer 0, sample 0
+  unsigned mask;           // lanes of the warp that fly (the others are past the end of the batch)
+  int col, sample;         // tensor coordinates: first drone of the warp, index of the next sample to stage
+  int stride, left, filled, buf;
+  UAVB_DEV bool leader() const { return (threadIdx.x & 31u) == (unsigned)(__ffs(mask) - 1); }
+  UAVB_DEV void send(const CUtensorMap* map, const float* src, int first_sample) {
+    fence_proxy_async_smem();                              // every lane: its staged columns before the async-proxy read
+    __syncwarp(mask);
+    if (leader()) {
+      tensor_store_2d(map, col, first_sample * 13, src);
+      bulk_commit();
+      bulk_wait_read<1>();                                 // the OTHER buffer's store has finished reading: it may be refilled
+    }
+    __syncwarp(mask);
+  }
+  UAVB_DEV void tick(const Drone2& d) {
+    if (--left) return;
+    left = stride;
+    float2* o = mine + (buf * kLogTmaSamples + filled) * (kLogTmaSampleFloats / 2);
+    o[0 * 32] = make_float2((float)(d.px[0] + (double)d.dx.x), (float)(d.px[1] + (double)d.dx.y));
+    o[1 * 32] = make_float2((float)(d.py[0] + (double)d.dy.x), (float)(d.py[1] + (double)d.dy.y));
+    o[2 * 32] = make_float2((float)(d.pz[0] + (double)d.dz.x), (float)(d.pz[1] + (double)d.dz.y));
+    o[3 * 32] = d.q0; o[4 * 32] = d.q1; o[5 * 32] = d.q2; o[6 * 32] = d.q3;
+    o[7 * 32] = d.vx; o[8 * 32] = d.vy; o[9 * 32] = d.vz;
+    o[10 * 32] = d.wx; o[11 * 32] = d.wy; o[12 * 32] = d.wz;
+    ++sample;
+    if (++filled == kLogTmaSamples) {
+      send(&maps->box_k, stage + buf * kLogTmaSamples * kLogTmaSampleFloats, sample - kLogTmaSamples);
+      buf ^= 1; filled = 0;
+    }
+  }
+  // end of the slice: the samples still staged, one box each; then the staging area is free for the CTA's next work item
+  UAVB_DEV void finish() {
+    for (int k = 0; k < filled; ++k) send(&maps->box_1, stage + (buf * kLogTmaSamples + k) * kLogTmaSampleFloats, sample - filled + k);
+    filled = 0;
+    if (leader()) bulk_wait_read<0>();
+    __syncwarp(mask);
   }
 };
 

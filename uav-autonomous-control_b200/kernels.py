@@ -429,7 +429,7 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
             obstacles: Optional[torch.Tensor] = None, obstacle_set: Optional[torch.Tensor] = None, thrust_frame_lag: int = 1,
             log_stride: int = 0, carry: Optional[torch.Tensor] = None, resume: bool = False, want_state: bool = True,
             want_metrics: bool = True, want_carry: bool = False, dtype: torch.dtype = torch.float32, index_base: int = 0, use_targets: bool = True,
-            out: Optional[RolloutResult] = None, n_slices: int = 0) -> RolloutResult:
+            out: Optional[RolloutResult] = None, n_slices: int = 0, log_tma: int = 0) -> RolloutResult:
     """n_ticks ticks of `trajectory_controller.step(); simulation.step()` for B drones
     (tests/integration/test_mujoco_trajectory_tracking.py:27-31) in one persistent kernel launch.
 
@@ -437,6 +437,7 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     obstacles: [n_obs, 6] (shared) or [n_sets, n_obs, 6] f32 with obstacle_set [B] i32.
     dtype float64 selects the validation kernel (outputs f64, no carry).
     n_slices > 0 forces the number of time slices of the fp32 launch (uavb.h; results do not depend on it).
+    log_tma = -1 writes the state log with per-thread stores instead of staged TMA tensor stores (uavb.h; same bits).
     """
     dev = plan.seg_coeffs.device
     f64 = dtype == torch.float64
@@ -446,6 +447,7 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     a.thrust_frame_lag, a.resume, a.log_stride = int(thrust_frame_lag), int(bool(resume)), int(log_stride)
     a.index_base = int(index_base)
     a.n_slices = int(n_slices)
+    a.log_tma = int(log_tma)
     a.veh = vehicle if vehicle is not None else nat.default_vehicle()
     a.mc_mass = nat.ptr(mc_mass, torch.float32, "mc_mass")
     a.mc_inertia = nat.ptr(mc_inertia, torch.float32, "mc_inertia")
