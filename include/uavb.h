@@ -239,6 +239,20 @@ typedef struct uavb_rollout_args {
   float*        state_out;    /* [13][B] final X, SoA; may be NULL                                     */
   float*        metrics_out;  /* [B][UAVB_N_METRICS]; may be NULL                                      */
   float*        log_out;      /* [n_ticks / log_stride][13][B] SoA samples; required iff log_stride > 0 */
+  /* D5, the viewer's flown-path list (MujocoSimulation._record_actual_trajectory, mujoco_sim.py:201-218), per rollout: after every
+     tick the simulation time advances by veh.dt (mj_step); the position is appended when z <= traj_gate_z (NED: at or above the
+     take-off altitude, mission_waypoints[1][2]) and time >= next sample time, which then becomes time + traj_interval.
+     fp32 rollouts only; not together with log_out.  Rollout i's k-th sample is traj_out[k][0..2][i]. */
+  float*        traj_out;         /* [traj_max_samples][3][B] or NULL                                                     */
+  int*          traj_count_out;   /* [B] samples the reference would hold (may exceed traj_max_samples; the rest is dropped) */
+  int           traj_max_samples;
+  double        traj_gate_z;
+  double        traj_interval;    /* ACTUAL_TRAJECTORY_SAMPLE_INTERVAL = 0.05 s (mujoco_sim.py:16)                       */
+  /* Optional unilateral floor (the reference's drone rests on MuJoCo's ground plane until the rotors carry it; a free body
+     sags ~1.5 cm through it during the first 50 ms).  ground_on = 1: after every tick, z > ground_z (NED, below the floor) is set
+     back to ground_z and a downward velocity to zero.  Default 0: free body, as in round 1. */
+  int           ground_on;
+  double        ground_z;
   int           log_tma;      /* 0 = library policy: the fp32 log leaves through staged TMA tensor stores when B is a multiple of 4 and
                                  log_out is 16-byte aligned, else through per-thread streaming stores; -1 = always the latter (same bits) */
 } uavb_rollout_args;

@@ -22,7 +22,7 @@ class CVehicle(C.Structure):
                 ("kf", C.c_double), ("kappa", C.c_double), ("min_thrust", C.c_double), ("max_thrust", C.c_double),
                 ("tau_rise", C.c_double), ("tau_fall", C.c_double), ("max_ascent", C.c_double), ("max_descent", C.c_double),
                 ("max_speed_xy", C.c_double), ("max_horiz_accel", C.c_double), ("max_tilt", C.c_double), ("gains", C.c_double * 11),
-                ("integral_limit", C.c_double)]
+                ("integral_limit", C.c_double), ("ground_on", C.c_double), ("ground_z", C.c_double)]
 
 
 def lib():
@@ -48,10 +48,12 @@ def _dp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def c_vehicle(v: Vehicle) -> CVehicle:
+def c_vehicle(v: Vehicle, ground_z=None) -> CVehicle:
     c = CVehicle(g=v.g, dt=v.dt, mass=v.mass, arm=v.arm, kf=v.kf, kappa=v.kappa, min_thrust=v.min_thrust, max_thrust=v.max_thrust,
                  tau_rise=v.tau_rise, tau_fall=v.tau_fall, max_ascent=v.max_ascent, max_descent=v.max_descent, max_speed_xy=v.max_speed_xy,
                  max_horiz_accel=v.max_horiz_accel, max_tilt=v.max_tilt, integral_limit=10.0)
+    if ground_z is not None:
+        c.ground_on, c.ground_z = 1.0, float(ground_z)
     c.inertia[:] = list(np.asarray(v.inertia, dtype=float))
     c.gains[:] = [getattr(v, n) for n in Vehicle.GAIN_NAMES]
     return c
@@ -90,7 +92,8 @@ def mission_table(waypoints, velocity, dt):
     return np.vstack([sample_table(*solve_coeffs(p, velocity), dt) for p in (w[:2], w[1:])])
 
 
-def closed_loop(veh: Vehicle, table, start, *, freq=10, n_ticks=None, obstacles=None, goal=None, wind=None, thrust_frame_lag=1, log_stride=0):
+def closed_loop(veh: Vehicle, table, start, *, freq=10, n_ticks=None, obstacles=None, goal=None, wind=None, thrust_frame_lag=1, log_stride=0,
+                ground_z=None):
     table = np.ascontiguousarray(table, dtype=float)
     n_ticks = freq * len(table) if n_ticks is None else int(n_ticks)
     obs = None if obstacles is None else np.ascontiguousarray(obstacles, dtype=float).reshape(-1, 6)
@@ -99,20 +102,21 @@ def closed_loop(veh: Vehicle, table, start, *, freq=10, n_ticks=None, obstacles=
     wind_a = None if wind is None else np.ascontiguousarray(wind, dtype=float)
     m, X, om = np.empty(8), np.empty(13), np.empty(4)
     log = np.empty((n_ticks // log_stride, 13)) if log_stride else None
-    cv = c_vehicle(veh)
+    cv = c_vehicle(veh, ground_z)
     lib().oracle_closed_loop(C.byref(cv), _dp(table), len(table), _dp(start), freq, n_ticks, _dp(obs), 0 if obs is None else len(obs), _dp(goal_a),
                              _dp(wind_a), int(thrust_frame_lag), _dp(m), _dp(X), _dp(om), int(log_stride), _dp(log))
     return dict(X=X, omega=om, final_dist=m[0], collision=bool(m[1]), rmse=m[2], mean_err=m[3], max_err=m[4], first_collision_tick=int(m[6]),
                 periods=int(m[7]), log=log)
 
 
-def closed_loop_batch(vehicles, table, start, *, freq=10, n_ticks=None, obstacles=None, goal=None, wind=None, thrust_frame_lag=1, threads=1):
+def closed_loop_batch(vehicles, table, start, *, freq=10, n_ticks=None, obstacles=None, goal=None, wind=None, thrust_frame_lag=1, threads=1,
+                      ground_z=None):
     """B drones (list of Vehicle, or one Vehicle with ``wind`` (B, 3)) on one table; returns metrics (B, 8), X (B, 13)."""
     table = np.ascontiguousarray(table, dtype=float)
     n_ticks = freq * len(table) if n_ticks is None else int(n_ticks)
     single = isinstance(vehicles, Vehicle)
     B = len(wind) if single else len(vehicles)
-    arr = (CVehicle * (1 if single else B))(*([c_vehicle(vehicles)] if single else [c_vehicle(v) for v in vehicles]))
+    arr = (CVehicle * (1 if single else B))(*([c_vehicle(vehicles, ground_z)] if single else [c_vehicle(v, ground_z) for v in vehicles]))
     obs = None if obstacles is None else np.ascontiguousarray(obstacles, dtype=float).reshape(-1, 6)
     start = np.ascontiguousarray(start, dtype=float)
     goal_a = None if goal is None else np.ascontiguousarray(goal, dtype=float)

@@ -184,7 +184,8 @@ def motor_lag(veh: Vehicle, omega, forces):
 
 # ----------------------------------------------------------------------------- closed loop
 def closed_loop(veh: Vehicle, table: np.ndarray, start, *, freq: int = 10, n_ticks: int | None = None,
-                obstacles=None, goal=None, wind=None, thrust_frame_lag: int = 1, log_stride: int = 0):
+                obstacles=None, goal=None, wind=None, thrust_frame_lag: int = 1, log_stride: int = 0, ground_z=None,
+                traj_gate_z=None, traj_interval: float = 0.05):
     """Headless mission (integration test :26-31 + main:37-61) on the free-body model.
 
     Tick k: (1) if k % freq == 0 outer loop on X_k with table row ``idx`` then idx=min(idx+1,N-1);
@@ -195,6 +196,10 @@ def closed_loop(veh: Vehicle, table: np.ndarray, start, *, freq: int = 10, n_tic
     Returns a dict: X (13,), omega (4,), integral, errors (per period), collision (bool),
     first_collision_tick, final_dist, mean_err, rmse, max_err, and ``log`` (n_log, 13) every
     ``log_stride`` ticks (state after the tick) when log_stride > 0.
+    ``ground_z`` (optional): unilateral floor -- after the free-body step a position below it (NED: z > ground_z) is put
+    back onto it and a downward velocity set to zero.  ``traj_gate_z``: also return ``traj_ticks`` / ``traj`` -- the flown-path list
+    of MujocoSimulation._record_actual_trajectory (ms:201-218): data.time += dt per tick, a sample when z <= gate and
+    time >= next, next = time + traj_interval.
     """
     N = len(table)
     if n_ticks is None:
@@ -214,6 +219,7 @@ def closed_loop(veh: Vehicle, table: np.ndarray, start, *, freq: int = 10, n_tic
     first_hit = -1
     log = []
     row = table[0]
+    sim_time, traj_next, traj_ticks, traj = 0.0, 0.0, [], []
     for k in range(n_ticks):
         if k % freq == 0:
             row = table[idx]
@@ -232,6 +238,15 @@ def closed_loop(veh: Vehicle, table: np.ndarray, start, *, freq: int = 10, n_tic
         X = freebody_step(X, omega, R_use, g=veh.g, dt=veh.dt, mass=veh.mass, inertia=veh.inertia, kf=veh.kf,
                           arm=veh.arm, kappa=veh.kappa, wind=wind)
         R_stale = R_now
+        if ground_z is not None and X[2] > ground_z:
+            X[2] = ground_z
+            X[9] = min(X[9], 0.0)
+        if traj_gate_z is not None:
+            sim_time += veh.dt
+            if not (X[2] > traj_gate_z) and not (sim_time < traj_next):
+                traj_ticks.append(k)
+                traj.append(X[0:3].copy())
+                traj_next = sim_time + traj_interval
         if obstacles is not None and not collided:
             for box in obstacles:
                 if box[0] <= X[0] <= box[1] and box[2] <= X[1] <= box[3] and box[4] <= X[2] <= box[5]:
@@ -247,6 +262,8 @@ def closed_loop(veh: Vehicle, table: np.ndarray, start, *, freq: int = 10, n_tic
                rmse=float(math.sqrt(np.mean(errors ** 2))) if len(errors) else 0.0,
                max_err=float(errors.max()) if len(errors) else 0.0,
                log=np.asarray(log) if log_stride else None)
+    if traj_gate_z is not None:
+        out["traj_ticks"], out["traj"] = np.asarray(traj_ticks, dtype=int), np.asarray(traj).reshape(-1, 3)
     if goal is not None:
         out["final_dist"] = float(math.sqrt(np.sum((X[0:3] - np.asarray(goal, dtype=float)) ** 2)))
     return out

@@ -189,6 +189,7 @@ typedef struct oracle_vehicle {  /* same field order as struct uavb_vehicle (inc
   double max_ascent, max_descent, max_speed_xy, max_horiz_accel, max_tilt;
   double gains[11]; /* kp_xy kd_xy kp_z kd_z ki_z kp_roll kp_pitch kp_yaw kp_p kp_q kp_r */
   double integral_limit;
+  double ground_on, ground_z; /* optional unilateral floor (not in uavb_vehicle: uavb_rollout_args.ground_on / ground_z); 0 = free body */
 } oracle_vehicle;
 
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
@@ -323,6 +324,10 @@ void oracle_closed_loop(const oracle_vehicle* v, const double* table, int n_rows
     quat_to_rot(X + 3, R_now);
     freebody_step(v, X, omega, thrust_frame_lag ? R_stale : R_now, wind);
     memcpy(R_stale, R_now, sizeof(R_now));
+    if (v->ground_on != 0.0 && X[2] > v->ground_z) { /* below the floor (NED): back onto it, no downward velocity */
+      X[2] = v->ground_z;
+      if (X[9] > 0.0) X[9] = 0.0;
+    }
     if (!collided)
       for (int b = 0; b < n_obs; ++b) {
         const double* q = obstacles + 6 * b;

@@ -17,7 +17,7 @@ def golden():
     import numpy as np
     gd = os.path.join(ROOT, "tests", "golden")
     return {name: np.load(os.path.join(gd, name + ".npz")) for name in
-            ("planning", "stages", "closed_loop_v2", "closed_loop_v3", "closed_loop_variants", "rrt")}
+            ("planning", "stages", "closed_loop_v2", "closed_loop_v3", "closed_loop_variants", "actual_trajectory", "rrt")}
 
 
 @pytest.fixture(scope="session")

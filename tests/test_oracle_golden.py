@@ -296,3 +296,33 @@ def test_closed_loop_variants_match_reference_objects(golden):
     out = flight_np.closed_loop(flight_np.Vehicle(), tab, g["waypoints"][0], obstacles=ref["obstacles"], goal=GOAL)
     _compare_closed_loop(ref, out, len(tab))
     assert out["collision"] and out["first_collision_tick"] == 4086
+
+
+def test_actual_trajectory_list_matches_the_reference_recorder(golden):
+    """D5: the viewer's flown-path list.  tests/golden/actual_trajectory.npz was recorded by the reference's OWN
+    MujocoSimulation._record_actual_trajectory (mujoco_sim.py:201-218) called after every tick of the reference objects' closed loop;
+    the oracle's restatement of its two tests (take-off gate on z, 0.05 s of accumulated data.time) must pick the same ticks."""
+    g, ref = golden["planning"], golden["actual_trajectory"]
+    out = flight_np.closed_loop(flight_np.Vehicle(), g["v3_table"], g["waypoints"][0], goal=GOAL, traj_gate_z=float(ref["takeoff_z"]),
+                                traj_interval=float(ref["interval"]))
+    np.testing.assert_array_equal(out["traj_ticks"], ref["ticks"])
+    np.testing.assert_allclose(out["traj"], ref["positions"], rtol=0, atol=1e-9)
+    assert set(np.diff(ref["ticks"]).tolist()) >= {50, 51}                        # accumulated fp64 time: not a fixed 50-tick stride
+    assert ref["ticks"][0] > 400 and (np.diff(ref["ticks"]) > 51).any()            # gated during take-off and again where the course dips below it
+
+
+def test_ground_floor_switch(golden):
+    """SURVEY 7.3's documented choice as a switch: ground_z puts a unilateral floor under the free body.  Off (default) the drone
+    sags through its start height while the rotors spin up (<= 1.5 cm); on, it never goes below it and the rest of
+    the flight is unchanged to a few millimetres.  NumPy and C oracles agree."""
+    from oracle import c_port
+    g = golden["planning"]
+    tab, start = g["v3_table"][:120], g["waypoints"][0]
+    free = flight_np.closed_loop(flight_np.Vehicle(), tab, start, goal=GOAL, log_stride=1)
+    held = flight_np.closed_loop(flight_np.Vehicle(), tab, start, goal=GOAL, log_stride=1, ground_z=float(start[2]))
+    sag = float((free["log"][:, 2] - start[2]).max())
+    assert 0.002 < sag < 0.016
+    assert float((held["log"][:, 2] - start[2]).max()) <= 0.0
+    assert np.abs(held["log"][-1, :3] - free["log"][-1, :3]).max() < 0.02
+    c = c_port.closed_loop(flight_np.Vehicle(), tab, start, goal=GOAL, ground_z=float(start[2]))
+    np.testing.assert_allclose(c["X"], held["X"], rtol=0, atol=1e-10)

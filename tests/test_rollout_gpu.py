@@ -425,3 +425,66 @@ def test_state_log_through_tensor_stores_equals_per_thread_stores(cuda):
         assert a.log.shape == (n // stride, 13, B)
         assert torch.equal(a.log, b.log) and torch.equal(a.state, b.state) and torch.equal(a.metrics, b.metrics), (B, n, stride, slices)
         assert bool(torch.isfinite(a.log).all())
+
+
+def test_actual_trajectory_list_matches_the_reference_recorder(cuda, golden):
+    """D5 (mujoco_sim.py:201-218) in the persistent rollout: the gated 20 Hz position list of every drone against the list the
+    reference's own _record_actual_trajectory produced (tests/golden/actual_trajectory.npz: 191 samples, first after tick 509,
+    50 / 51 ticks apart, a 671-tick gap where the course dips below the take-off altitude).  A sample taken one tick off would
+    sit ~3 mm away, so count + 1e-4 m pin the ticks.  The list does not depend on the slice count, and recording it leaves
+    the flight that of the metrics-only rollout (same numerics, another compiled kernel: equal to a few ulps)."""
+    import torch
+    ref = golden["actual_trajectory"]
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * int(plan.total_rows.item())
+    B = 70
+    kw = dict(traj_max_samples=256, traj_gate_z=float(ref["takeoff_z"]), traj_interval=float(ref["interval"]))
+    a = _fly(cuda, plan, B, n, **kw)
+    assert a.traj_count.tolist() == [len(ref["ticks"])] * B
+    got = a.traj[:len(ref["ticks"]), :, 0].double().cpu().numpy()
+    assert np.abs(got - ref["positions"]).max() < 1e-4
+    assert bool((a.traj == a.traj[:, :, :1]).all()) and float(a.traj[len(ref["ticks"]):].abs().max()) == 0.0
+    b = _fly(cuda, plan, B, n, n_slices=9, **kw)
+    assert torch.equal(a.traj, b.traj) and torch.equal(a.traj_count, b.traj_count)
+    plain = _fly(cuda, plan, B, n)
+    assert float((a.state - plain.state).abs().max()) < 1e-5 and float((a.metrics - plain.metrics).abs().max()) < 1e-5
+    # a list shorter than the flight keeps its first samples and still counts them all; per-rollout vehicles differ
+    rng = np.random.default_rng(3)
+    mc = mc_arrays(cuda, B, rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3)))
+    c = _fly(cuda, plan, B, n, traj_max_samples=16, traj_gate_z=float(ref["takeoff_z"]), **mc)
+    assert int(c.traj_count.min()) > 150 and len(set(c.traj_count.tolist())) > 1
+    # through the simulation object
+    from uav_ac_b200.simulation.batched_sim import BatchedSimulation
+    r = BatchedSimulation(3).rollout(3.0, record_actual_trajectory=True)
+    assert r.traj_count.tolist() == [len(ref["ticks"])] * 3 and np.abs(r.traj[:len(ref["ticks"]), :, 1].double().cpu().numpy() - ref["positions"]).max() < 1e-4
+
+
+def test_ground_floor_switch_matches_the_oracle(cuda, golden):
+    """uavb_rollout_args.ground_on: the unilateral floor in the fp32 pair kernel and the fp64 kernel against the C
+    oracle with the same switch -- with and without obstacles (the floor rides on the obstacle culling), Monte-Carlo vehicles."""
+    import torch
+    from oracle import c_port, flight_np
+    g = golden["planning"]
+    tab, start = g["v3_table"], g["waypoints"][0]
+    plan = lab_course_plan(cuda, 3.0)
+    n = 10 * len(tab)
+    B = 130
+    rng = np.random.default_rng(21)
+    gs, ms_, is_ = rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3))
+    mc = mc_arrays(cuda, B, gs, ms_, is_)
+    vehs = [flight_np.Vehicle().with_values(mc["mc_gains"][:, i].double().cpu().numpy(), float(mc["mc_mass"][i]), mc["mc_inertia"][:, i].double().cpu().numpy())
+            for i in range(B)]
+    gz = float(start[2])
+    m_ref, X_ref = c_port.closed_loop_batch(vehs, tab, start, obstacles=g["obstacles"], goal=GOAL, threads=8, ground_z=gz)
+    obs = torch.tensor(g["obstacles"], dtype=torch.float32, device=cuda)
+    for kw in (dict(obstacles=obs), dict()):
+        r = _fly(cuda, plan, B, n, ground_z=gz, **kw, **mc)
+        X = r.state.double().cpu().numpy().T
+        assert np.abs(X[:, :3] - X_ref[:, :3]).max() < 1e-4 and rotation_angle(X[:, 3:7], X_ref[:, 3:7]).max() < 1e-4
+    r64 = _fly(cuda, plan, 4, n, dtype=torch.float64, ground_z=gz, obstacles=obs)
+    ref0 = c_port.closed_loop(flight_np.Vehicle(), tab, start, obstacles=g["obstacles"], goal=GOAL, ground_z=gz)
+    assert np.abs(r64.state[:, 0].cpu().numpy() - ref0["X"]).max() < 1e-7
+    # the floor holds: the logged altitude never goes below the start height; without it the drone sags while the rotors spin up
+    held = _fly(cuda, plan, 8, 400, log_stride=1, ground_z=gz)
+    free = _fly(cuda, plan, 8, 400, log_stride=1)
+    assert float((held.log[:, 2] - gz).max()) <= 1e-6 and 0.002 < float((free.log[:, 2] - gz).max()) < 0.016

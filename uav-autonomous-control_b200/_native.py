@@ -65,7 +65,9 @@ class RolloutArgs(Structure):
         ("shared_targets", c_void_p), ("n_target_rows", c_int), ("n_slices", c_int),
         ("start", c_void_p), ("start_stride", c_int), ("goal", c_void_p), ("goal_stride", c_int),
         ("aabbs", c_void_p), ("aabb_set", c_void_p),
-        ("carry", c_void_p), ("state_out", c_void_p), ("metrics_out", c_void_p), ("log_out", c_void_p), ("log_tma", c_int),
+        ("carry", c_void_p), ("state_out", c_void_p), ("metrics_out", c_void_p), ("log_out", c_void_p),
+        ("traj_out", c_void_p), ("traj_count_out", c_void_p), ("traj_max_samples", c_int), ("traj_gate_z", c_double), ("traj_interval", c_double),
+        ("ground_on", c_int), ("ground_z", c_double), ("log_tma", c_int),
     ]
 
 

@@ -73,6 +73,13 @@ struct NoLog {
   template <class R> UAVB_HD void tick(const Drone<R>&) {}
 };
 
+// Optional unilateral floor (uavb_rollout_args.ground_on / ground_z): NED, z <= ground z.  The floor takes part in the obstacle
+// culling below like one more box -- a drone that cannot reach it during a stretch is not tested against it.
+struct Ground {
+  int on;
+  double z;
+};
+
 struct NoObstacles {
   static constexpr bool kAny = false;
   template <class R> UAVB_HD R gap(R, R, R) const { return R(3.0e38); }
@@ -157,7 +164,7 @@ template <class R> UAVB_HD void table_target(const TargetRow* rows, int row, Tar
 // A compile-time switch, so the table-driven instantiation carries none of the fp64 evaluation code or its registers.
 template <class R, bool TABLE, class OBST, class LOG>
 UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& u, const VehP<R>& v, const MissionView& m,
-                         int tick0, int n_ticks, int freq, int lag, const OBST& obst, LOG& logger) {
+                         int tick0, int n_ticks, int freq, int lag, const OBST& obst, LOG& logger, const Ground gr = Ground{0, 0.0}) {
   typedef Math<R> M;
   int k = 0;
   R clear = R(0);                                            // not part of the carry: every launch / slice measures first
@@ -176,11 +183,17 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
     }
     const int n = (freq - c.phase < n_ticks - k) ? (freq - c.phase) : (n_ticks - k);
     bool watch = false;
-    if (OBST::kAny && !a.collided) {
+    if (OBST::kAny && (!a.collided || gr.on)) {
       const R T = (R)n * u.dt;
       const R speed = M::sqrt_fast(d.vx * d.vx + d.vy * d.vy + d.vz * d.vz);
       const R reach = R(1.01) * (speed + v.acc_max * T) * T + R(1e-4);
-      if (!(clear > reach)) clear = obst.gap((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz));
+      if (!(clear > reach)) {
+        clear = a.collided ? R(3.0e38) : obst.gap((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz));
+        if (gr.on) {
+          const R gg = (R)(gr.z - (d.pz + (double)d.dz));  // room above the floor
+          clear = (gg < clear || gg != gg) ? gg : clear;
+        }
+      }
       watch = !(clear > reach);                              // NaN positions keep measuring and watching
       clear -= reach;
     }
@@ -199,6 +212,10 @@ UAVB_HD void rollout_run(Drone<R>& d, Cursor<R>& c, Accum<R>& a, const VehU<R>& 
       for (int j = 0; j < n; ++j) {
         inner_tick<R, LOG::kNormEveryTick>(d, u, v, kLag);
         if constexpr (kWatch) {
+          if (gr.on && d.pz + (double)d.dz > gr.z) {         // below the floor: back onto it, no downward velocity
+            d.dz = (R)(gr.z - d.pz);
+            d.vz = M::fmin(d.vz, R(0));
+          }
           if (!a.collided && obst.hit((R)(d.px + (double)d.dx), (R)(d.py + (double)d.dy), (R)(d.pz + (double)d.dz))) {
             a.collided = 1; a.first_hit = tick0 + k + j;
           }

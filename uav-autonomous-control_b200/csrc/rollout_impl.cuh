@@ -216,10 +216,10 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
       GlobalLog<R> lg;
       lg.out = reinterpret_cast<R*>(a.log_out) + (size_t)(launch_tick0 / a.log_stride) * 13 * B + i;
       lg.B = (unsigned)B; lg.stride = a.log_stride; lg.left = a.log_stride - launch_tick0 % a.log_stride;
-      rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+      rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg, Ground{a.ground_on, a.ground_z});
     } else {
       NoLog lg;
-      rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg);
+      rollout_run<R, TABLE>(d, c, acc, u, v, m, tick0, n_ticks, a.inner_per_outer, a.thrust_frame_lag, obst, lg, Ground{a.ground_on, a.ground_z});
     }
   };
   if (a.n_obs > 0) {
@@ -228,6 +228,8 @@ __device__ __forceinline__ void drone_slice(const RolloutDev<R>& p, const float*
     } else {
       fly(BoxesT<false>{a.aabbs + (size_t)a.aabb_set[i] * a.n_obs * 6, a.n_obs});
     }
+  } else if (a.ground_on) {
+    fly(BoxesT<true>{nullptr, 0});                           // no boxes, but the floor rides on the obstacle culling
   } else {
     fly(NoObstacles{});
   }
@@ -334,7 +336,8 @@ __device__ __forceinline__ void write_outputs(const uavb_rollout_args& a, long l
 
 // One PAIR of drones (2j, 2j+1), one slice of their mission: the production fp32 path (rollout_pair.cuh).  Arguments as
 // drone_slice.  When B is odd the last pair's second lane re-flies the first drone and writes nothing.
-// LOG: 0 = no state log, 1 = per-thread streaming stores (PairLog), 2 = staged tensor stores (PairLogTma, `maps` required).
+// LOG: 0 = no state log, 1 = per-thread streaming stores (PairLog), 2 = staged tensor stores (PairLogTma, `maps` required),
+// 3 = the gated position list of the viewer (PairTrajLog; its state rides in the carry block between slices).
 template <int LOG, bool MC, bool TABLE, bool LAG>
 __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long j, int n_ticks, bool from_carry, bool to_carry,
                                            bool finish, int launch_tick0, const LogTma* maps = nullptr) {
@@ -384,12 +387,29 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
     accum_init<float>(acc[0]); accum_init<float>(acc[1]);
   }
 
+  double traj_time = 0.0, traj_next[2] = {0.0, 0.0};
+  int traj_count[2] = {0, 0};
   auto fly = [&](const auto& oa, const auto& ob) {
     auto with_log = [&](auto& lg) {
-      if constexpr (MC) rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, v2, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg);
-      else rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, p.vp, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg);
+      const Ground gr{a.ground_on, a.ground_z};
+      if constexpr (MC) rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, v2, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg, gr);
+      else rollout_run_pair<TABLE, LAG>(d, c, acc, u, va, vb, p.vp, vo, ma, mb, tick0, n_ticks, a.inner_per_outer, oa, ob, lg, gr);
     };
-    if constexpr (LOG == 2) {
+    if constexpr (LOG == 3) {
+      PairTrajLog lg;
+      lg.out = a.traj_out + i0; lg.B = B;
+      lg.dt = a.veh.dt; lg.interval = a.traj_interval; lg.gate_z = a.traj_gate_z; lg.max_samples = a.traj_max_samples; lg.second = second;
+      const Carry cb0{a.carry + i0, B}, cb1{a.carry + i1, B};
+      if (from_carry) {                                    // words 35..37 / 50..51 of the carry block: next sample time, count / data.time
+        lg.time = cb0.get64(50);
+        lg.next[0] = cb0.get64(35); lg.count[0] = f2i(cb0.w(37));
+        lg.next[1] = cb1.get64(35); lg.count[1] = f2i(cb1.w(37));
+      } else {
+        lg.time = 0.0; lg.next[0] = lg.next[1] = 0.0; lg.count[0] = lg.count[1] = 0;     // mujoco_sim.py:190-199
+      }
+      with_log(lg);
+      traj_time = lg.time; traj_next[0] = lg.next[0]; traj_next[1] = lg.next[1]; traj_count[0] = lg.count[0]; traj_count[1] = lg.count[1];
+    } else if constexpr (LOG == 2) {
       extern __shared__ __align__(128) float s_dyn_f32[];     // tensor stores read 128-byte aligned shared memory
       PairLogTma lg;
       lg.maps = maps;
@@ -419,18 +439,35 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
     } else {
       fly(BoxesT<false>{a.aabbs + (size_t)a.aabb_set[i0] * a.n_obs * 6, a.n_obs}, BoxesT<false>{a.aabbs + (size_t)a.aabb_set[i1] * a.n_obs * 6, a.n_obs});
     }
+  } else if (a.ground_on) {
+    fly(BoxesT<true>{nullptr, 0}, BoxesT<true>{nullptr, 0});     // no boxes, but the floor rides on the obstacle culling
   } else {
     fly(NoObstacles{}, NoObstacles{});
   }
 
+  constexpr bool kStateLog = LOG == 1 || LOG == 2;          // per-tick quaternion normalisation
   Drone<float> s;
   get_lane<0>(d, s);
   if (to_carry) Carry{a.carry + i0, B}.store(s, c[0], acc[0], tick0 + n_ticks);
-  if (finish) write_outputs(a, i0, s, c[0], acc[0], LOG);
+  if (finish) write_outputs(a, i0, s, c[0], acc[0], kStateLog);
   if (second) {
     get_lane<1>(d, s);
     if (to_carry) Carry{a.carry + i1, B}.store(s, c[1], acc[1], tick0 + n_ticks);
-    if (finish) write_outputs(a, i1, s, c[1], acc[1], LOG != 0);
+    if (finish) write_outputs(a, i1, s, c[1], acc[1], kStateLog);
+  }
+  if constexpr (LOG == 3) {
+    if (to_carry) {
+      const Carry cb0{a.carry + i0, B};
+      cb0.put64(50, traj_time); cb0.put64(35, traj_next[0]); cb0.w(37) = i2f(traj_count[0]);
+      if (second) {
+        const Carry cb1{a.carry + i1, B};
+        cb1.put64(50, traj_time); cb1.put64(35, traj_next[1]); cb1.w(37) = i2f(traj_count[1]);
+      }
+    }
+    if (finish && a.traj_count_out) {
+      a.traj_count_out[i0] = traj_count[0];
+      if (second) a.traj_count_out[i1] = traj_count[1];
+    }
   }
 }
 
@@ -515,6 +552,12 @@ __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid
   sliced_body<MC, TABLE, LOG ? 1 : 0, LAG>(p, sch, nullptr);
 }
 
+// Metrics + the gated position list of the viewer (PairTrajLog); one-warp CTAs like the metrics-only kernel.
+template <bool MC, bool TABLE, bool LAG>
+__global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_traj_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
+  sliced_body<MC, TABLE, 3, LAG>(p, sch, nullptr);
+}
+
 // The state log through staged tensor stores (PairLogTma); `maps` lives in the kernel parameter space, where the TMA unit reads it.
 template <bool MC, bool TABLE, bool LAG>
 __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_tma_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch,
@@ -527,6 +570,7 @@ __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_tma_kernel(const __
 void launch_rollout_sliced(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
 void launch_rollout_sliced_log(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch,
                                const LogTma* maps);      // maps != nullptr: staged tensor stores
+void launch_rollout_sliced_traj(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
 void launch_rollout_f64(bool log, bool mc, int grid, size_t smem, cudaStream_t st, const RolloutDev<double>& p);
 
 }  // namespace uavb

@@ -79,6 +79,8 @@ static int check_args(const uavb_rollout_args* a, bool f64) {
   UAVB_REQUIRE(a->n_slices >= 0, "rollout: n_slices must be >= 0");
   UAVB_REQUIRE(a->log_stride == 0 || a->log_out != nullptr, "rollout: log_stride > 0 needs log_out");
   UAVB_REQUIRE(a->log_stride == 0 || a->B <= 300000000LL, "rollout: a state log supports at most 3e8 rollouts per launch");
+  UAVB_REQUIRE(a->traj_out == nullptr || (!f64 && a->log_stride == 0), "rollout: traj_out is for fp32 rollouts without a state log");
+  UAVB_REQUIRE(a->traj_out == nullptr || (a->traj_max_samples >= 1 && a->traj_interval >= 0.0), "rollout: traj_out needs traj_max_samples >= 1 and traj_interval >= 0");
   UAVB_REQUIRE(a->n_obs >= 0 && a->n_obs <= 1024, "rollout: n_obs out of range");
   UAVB_REQUIRE(a->n_obs == 0 || (a->aabbs != nullptr && a->n_obs_sets >= 1), "rollout: n_obs > 0 needs aabbs and n_obs_sets >= 1");
   UAVB_REQUIRE(a->dt_outer > 0.0 && a->veh.dt > 0.0 && a->veh.mass > 0.0, "rollout: dt_outer, veh.dt and veh.mass must be positive");
@@ -188,6 +190,7 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
       }
     }
     if (log) launch_rollout_sliced_log(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch, tma_log ? &maps : nullptr);
+    else if (a->traj_out) launch_rollout_sliced_traj(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
     else launch_rollout_sliced(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
   }
   UAVB_CUDA_OK(cudaGetLastError());

@@ -100,6 +100,38 @@ struct PairLogTma {
   }
 };
 
+// D5, the viewer's flown-path list (MujocoSimulation._record_actual_trajectory, mujoco_sim.py:201-218) for the pair: `time` is
+// data.time -- mj_step adds the time step once per tick, so it is accumulated the same way, one fp64 addition per tick, and the
+// sample ticks come out as the reference's (50 or 51 ticks apart at 20 Hz) -- the gate is quad.z > takeoff z => skip, the
+// sample time rule time < next => skip, next = time + interval.  Positions are stored as fp32 triples [sample][3][B].
+// Quaternion handling is the metrics-only one (kNormEveryTick = false): a rollout that records its path flies the metrics-only
+// rollout to a few ulps (another compiled kernel; measured 2e-7 after 10 760 ticks).
+struct PairTrajLog {
+  static constexpr bool kNormEveryTick = false;
+  float* out;              // element (sample 0, field 0, drone 2j)
+  long long B;
+  double time, dt, interval, gate_z;
+  double next[2];
+  int count[2];
+  int max_samples;
+  bool second;             // the pair's second drone exists
+  template <int L> UAVB_DEV void lane_tick(const Drone2& d) {
+    const double z = d.pz[L] + (double)lane<L>(d.dz);
+    if (z > gate_z || time < next[L]) return;             // comparisons with NaN are false, as in the reference's two tests
+    if (count[L] < max_samples && (L == 0 || second)) {
+      float* o = out + (size_t)count[L] * 3 * B + L;
+      o[0] = (float)(d.px[L] + (double)lane<L>(d.dx)); o[B] = (float)(d.py[L] + (double)lane<L>(d.dy)); o[2 * B] = (float)z;
+    }
+    ++count[L];
+    next[L] = time + interval;
+  }
+  UAVB_DEV void tick(const Drone2& d) {
+    time += dt;
+    lane_tick<0>(d);
+    lane_tick<1>(d);
+  }
+};
+
 struct NoPairLog {
   static constexpr bool kNormEveryTick = false;
   UAVB_DEV void tick(const Drone2&) {}
@@ -144,19 +176,37 @@ template <> struct PairTarget<false> {
 
 // Obstacle culling for the coming stretch of n ticks (rollout_run, "clearance budget"): true when either drone could reach a
 // box before the next check, i.e. the per-tick inclusive test must run.  `clear` = lower bounds of the Chebyshev gaps.
+// With a floor (Ground) the gap also counts the room above it, and a drone keeps being watched after its collision flag is set.
+template <int L, class OBST> UAVB_DEV float pair_gap(const Drone2& d, const Accum<float>& a, const OBST& o, const Ground& gr) {
+  const double z = d.pz[L] + (double)lane<L>(d.dz);
+  float g = a.collided ? 3.0e38f : o.gap((float)(d.px[L] + (double)lane<L>(d.dx)), (float)(d.py[L] + (double)lane<L>(d.dy)), (float)z);
+  if (gr.on) {
+    const float gg = (float)(gr.z - z);
+    g = (gg < g || gg != gg) ? gg : g;
+  }
+  return g;
+}
 template <class OBST> UAVB_DEV bool pair_watch(const Drone2& d, const Accum<float> (&a)[2], const VehU<float>& u, V2 acc_max,
-                                               const OBST& oa, const OBST& ob, int n, V2& clear) {
+                                               const OBST& oa, const OBST& ob, int n, V2& clear, const Ground& gr) {
   const float T = __fmul_rn((float)n, u.dt);
   const V2 speed = sqrt2(fma2(d.vx, d.vx, fma2(d.vy, d.vy, mul2(d.vz, d.vz))));
   const V2 reach = fma2(mul2(fma2(acc_max, T, speed), T), 1.01f, 1e-4f);
-  const bool live_a = !a[0].collided, live_b = !a[1].collided;
+  const bool live_a = !a[0].collided || gr.on, live_b = !a[1].collided || gr.on;
   if ((live_a && !(clear.x > reach.x)) || (live_b && !(clear.y > reach.y))) {      // measure (rare): NaN positions keep measuring
-    if (live_a && !(clear.x > reach.x)) clear.x = oa.gap((float)(d.px[0] + (double)d.dx.x), (float)(d.py[0] + (double)d.dy.x), (float)(d.pz[0] + (double)d.dz.x));
-    if (live_b && !(clear.y > reach.y)) clear.y = ob.gap((float)(d.px[1] + (double)d.dx.y), (float)(d.py[1] + (double)d.dy.y), (float)(d.pz[1] + (double)d.dz.y));
+    if (live_a && !(clear.x > reach.x)) clear.x = pair_gap<0>(d, a[0], oa, gr);
+    if (live_b && !(clear.y > reach.y)) clear.y = pair_gap<1>(d, a[1], ob, gr);
   }
   const bool watch = (live_a && !(clear.x > reach.x)) || (live_b && !(clear.y > reach.y));
   clear = sub2(clear, reach);
   return watch;
+}
+
+// The floor for lane L after a tick: below it => back onto it, no downward velocity (NED: +z is down).
+template <int L> UAVB_DEV void pair_floor(Drone2& d, const Ground& gr) {
+  if (d.pz[L] + (double)lane<L>(d.dz) > gr.z) {
+    lane<L>(d.dz) = (float)(gr.z - d.pz[L]);
+    lane<L>(d.vz) = fminf(lane<L>(d.vz), 0.f);
+  }
 }
 
 template <int L, class OBST> UAVB_DEV void pair_hit(const Drone2& d, Accum<float>& a, const OBST& obst, int tick) {
@@ -173,7 +223,7 @@ template <int L, class OBST> UAVB_DEV void pair_hit(const Drone2& d, Accum<float
 template <bool TABLE, bool LAG, class VP2, class OBST, class LOG>
 UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&a)[2], const VehU<float>& u, const VehP<float>& va,
                                const VehP<float>& vb, const VP2& v2, const VehO2& vo, const MissionView& ma, const MissionView& mb, int tick0,
-                               int n_ticks, int freq, const OBST& oa, const OBST& ob, LOG& logger) {
+                               int n_ticks, int freq, const OBST& oa, const OBST& ob, LOG& logger, const Ground gr = Ground{0, 0.0}) {
   int k = 0;
   V2 clear = make_float2(0.f, 0.f);                          // not part of the carry: every launch / slice measures first
   const V2 acc_max = make_float2(va.acc_max, vb.acc_max);
@@ -187,7 +237,7 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
     }
     const int n = (freq - c[0].phase < n_ticks - k) ? (freq - c[0].phase) : (n_ticks - k);
     bool watch = false;
-    if (OBST::kAny) watch = __any_sync(__activemask(), pair_watch(d, a, u, acc_max, oa, ob, n, clear));   // one decision per warp; watching is always correct
+    if (OBST::kAny) watch = __any_sync(__activemask(), pair_watch(d, a, u, acc_max, oa, ob, n, clear, gr));   // one decision per warp; watching is always correct
     auto stretch = [&](auto watch_c) {
       constexpr bool kWatch = decltype(watch_c)::value;
       // two ticks per iteration (the tail of one tick overlaps the head of the next: +2 % on the table-driven headline workload)
@@ -198,6 +248,7 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
       for (int j = 0; j < n; ++j) {
         inner_tick_pair<LOG::kNormEveryTick, LAG>(d, u, v2);
         if constexpr (kWatch) {
+          if (gr.on) { pair_floor<0>(d, gr); pair_floor<1>(d, gr); }
           pair_hit<0>(d, a[0], oa, tick0 + k + j);
           pair_hit<1>(d, a[1], ob, tick0 + k + j);
         }

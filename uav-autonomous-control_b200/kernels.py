@@ -421,6 +421,8 @@ class RolloutResult:
     log: Optional[torch.Tensor]        # [n_samples, 13, B]
     carry: Optional[torch.Tensor]      # [48, B] resumable block
     n_ticks: int = 0
+    traj: Optional[torch.Tensor] = None        # [traj_max_samples, 3, B] gated 20 Hz positions (mujoco_sim.py:201-218)
+    traj_count: Optional[torch.Tensor] = None  # [B] i32 samples the reference would hold
 
 
 def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goal: Optional[torch.Tensor] = None,
@@ -429,7 +431,8 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
             obstacles: Optional[torch.Tensor] = None, obstacle_set: Optional[torch.Tensor] = None, thrust_frame_lag: int = 1,
             log_stride: int = 0, carry: Optional[torch.Tensor] = None, resume: bool = False, want_state: bool = True,
             want_metrics: bool = True, want_carry: bool = False, dtype: torch.dtype = torch.float32, index_base: int = 0, use_targets: bool = True,
-            out: Optional[RolloutResult] = None, n_slices: int = 0, log_tma: int = 0) -> RolloutResult:
+            out: Optional[RolloutResult] = None, n_slices: int = 0, log_tma: int = 0, ground_z: Optional[float] = None,
+            traj_max_samples: int = 0, traj_gate_z: float = 0.0, traj_interval: float = 0.05) -> RolloutResult:
     """n_ticks ticks of `trajectory_controller.step(); simulation.step()` for B drones
     (tests/integration/test_mujoco_trajectory_tracking.py:27-31) in one persistent kernel launch.
 
@@ -438,6 +441,9 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     dtype float64 selects the validation kernel (outputs f64, no carry).
     n_slices > 0 forces the number of time slices of the fp32 launch (uavb.h; results do not depend on it).
     log_tma = -1 writes the state log with per-thread stores instead of staged TMA tensor stores (uavb.h; same bits).
+    ground_z: optional unilateral floor (NED; uavb.h ground_on / ground_z).  traj_max_samples > 0 also records the viewer's
+    flown-path list (MujocoSimulation._record_actual_trajectory, mujoco_sim.py:201-218): positions every traj_interval seconds
+    of simulation time while z <= traj_gate_z, into result.traj [traj_max_samples, 3, B] / result.traj_count [B].
     """
     dev = plan.seg_coeffs.device
     f64 = dtype == torch.float64
@@ -448,6 +454,8 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     a.index_base = int(index_base)
     a.n_slices = int(n_slices)
     a.log_tma = int(log_tma)
+    if ground_z is not None:
+        a.ground_on, a.ground_z = 1, float(ground_z)
     a.veh = vehicle if vehicle is not None else nat.default_vehicle()
     a.mc_mass = nat.ptr(mc_mass, torch.float32, "mc_mass")
     a.mc_inertia = nat.ptr(mc_inertia, torch.float32, "mc_inertia")
@@ -504,6 +512,12 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     a.state_out = nat.ptr(res.state if want_state else None)
     a.metrics_out = nat.ptr(res.metrics if want_metrics else None)
     a.log_out = nat.ptr(res.log if log_stride > 0 else None)
+    if traj_max_samples > 0:
+        if res.traj is None:
+            res.traj = torch.zeros((int(traj_max_samples), 3, B), dtype=torch.float32, device=dev)
+            res.traj_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+        a.traj_out, a.traj_count_out = nat.ptr(res.traj, torch.float32, "traj"), nat.ptr(res.traj_count, torch.int32, "traj_count")
+        a.traj_max_samples, a.traj_gate_z, a.traj_interval = int(res.traj.shape[0]), float(traj_gate_z), float(traj_interval)
     fn = nat.lib().uavb_rollout_f64 if f64 else nat.lib().uavb_rollout_f32
     nat.check(fn(ctypes.byref(a), nat.stream_ptr(dev)), "uavb_rollout_f64" if f64 else "uavb_rollout_f32")
     return res

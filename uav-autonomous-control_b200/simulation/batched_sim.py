@@ -24,6 +24,8 @@ from . import scene
 
 class BatchedSimulation:
     TAKEOFF_HEIGHT = 0.1   # mujoco_sim.py:17 (ground-contact amnesty; unused by the free-body model)
+    ACTUAL_TRAJECTORY_SAMPLE_INTERVAL = 0.05   # mujoco_sim.py:16
+    ACTUAL_TRAJECTORY_SEGMENT_COUNT = 200      # mujoco_sim.py:14 (capsules the viewer can draw; the list itself is unbounded)
 
     def __init__(self, batch: int = 1, device=None, *, model_path=None, waypoints=None, obstacles=None, thrust_frame_lag: int = 1,
                  mass=None, inertia=None):
@@ -102,10 +104,15 @@ class BatchedSimulation:
 
     # ------------------------------------------------------------------ fused path
     def rollout(self, velocity: float, frequency: int = 10, n_ticks: Optional[int] = None, *, gains: Optional[dict] = None,
-                log_stride: int = 0, want_state: bool = True):
+                log_stride: int = 0, want_state: bool = True, record_actual_trajectory: bool = False, ground: bool = False):
         """Plan the mission (take-off table + course table, each with the obstacle-correction loop, main.py:73-84) and fly it for every drone in one launch of
         the persistent rollout kernel.  ``gains`` maps gain names to (B,) tensors (Monte-Carlo); mass / inertia
-        perturbations come from the Quad.  Returns ``kernels.RolloutResult`` (metrics (B, 8), final state, log)."""
+        perturbations come from the Quad.  Returns ``kernels.RolloutResult`` (metrics (B, 8), final state, log).
+        ``record_actual_trajectory``: also keep every drone's flown-path list exactly as the viewer records it
+        (``_record_actual_trajectory``, mujoco_sim.py:201-218: one position per 0.05 s of simulation time while the drone is at or
+        above the take-off altitude ``mission_waypoints[1][2]``) in ``result.traj`` / ``result.traj_count``.
+        ``ground``: unilateral floor at the start height (the reference's drone rests on MuJoCo's ground plane until its rotors
+        carry it; the default free body sags ~1.5 cm through it in the first 50 ms)."""
         q = self.quad
         dev = self.device
         wp = torch.tensor(self.mission_waypoints, dtype=torch.float64, device=dev)
@@ -120,4 +127,6 @@ class BatchedSimulation:
                                mc_mass=mc.get("mc_mass"), mc_inertia=mc.get("mc_inertia"), mc_gains=mc.get("mc_gains"),
                                mc_wind=st.soa(self.wind) if self.wind is not None else None,
                                obstacles=self._obs if len(self.obstacles) else None, thrust_frame_lag=self.thrust_frame_lag,
-                               log_stride=log_stride, want_state=want_state)
+                               log_stride=log_stride, want_state=want_state, ground_z=float(self.mission_waypoints[0][2]) if ground else None,
+                               traj_max_samples=(n_ticks // int(round(self.ACTUAL_TRAJECTORY_SAMPLE_INTERVAL / q.dt)) + 1) if record_actual_trajectory else 0,
+                               traj_gate_z=float(self.mission_waypoints[1][2]), traj_interval=self.ACTUAL_TRAJECTORY_SAMPLE_INTERVAL)
