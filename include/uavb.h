@@ -106,6 +106,14 @@ int uavb_minsnap_solve_ragged_f64(const double* waypoints, const int* wp_offsets
                                   int B, double start_end_time_factor, double* coeffs_out,
                                   double* times_out, int* status_out, void* stream);
 
+/* The reference's constraint system, MinimumSnap.A and MinimumSnap.b after _create_polynom_matrices (minimum_snap.py:171-255),
+ * in the reference's row order: 2S position rows, 6 boundary rows, 4 (S-1) continuity rows.  K1 does not use it (it solves the
+ * reduced problem); it serves the attribute surface of the reference class and its KKT-optimality test
+ * (tests/unit/planning/test_minimum_snap.py:154-168).
+ *   waypoints [B][S+1][3], times [B][S] (MinimumSnap.times)  ->  A_out [B][6S+2][8S], b_out [B][6S+2][3] */
+int uavb_minsnap_constraints_f64(const double* waypoints, const double* times, int B, int S, double* A_out, double* b_out,
+                                 void* stream);
+
 /* Table geometry of MinimumSnap._generate_trajectory (minimum_snap.py:97-124) without sampling it:
  *   rows_out  [n_seg]  len(np.arange(0, T_i, dt)) of every packed segment (:104)
  *   yaw0_out  [B]      yaw taken by the rows that precede the first row with horizontal speed

@@ -341,3 +341,32 @@ def test_main_reports_the_batch(cuda, capsys):
     app.main(batch=2000)
     out = capsys.readouterr().out
     assert "2000 flights finished" in out and "% reached" in out
+
+
+def test_constraint_system_attributes_and_argument_only_controller_method(cuda, golden):
+    """VERDICT r1 API gaps.  MinimumSnap.A / .b: None before a plan, afterwards the reference's constraint system in its row order
+    (minimum_snap.py:171-255; goldens written by the reference itself), usable for the reference's own KKT check
+    (tests/unit/planning/test_minimum_snap.py:154-168).  roll_pitch_controller reads only its arguments, like the reference's."""
+    import torch
+    from uav_ac_b200.control.controller import CascadedController
+    from uav_ac_b200.planning.minimum_snap import MinimumSnap
+    g = golden["planning"]
+    ms = MinimumSnap(g["waypoints"][1:], None, 3.0, 0.01)
+    assert ms.A is None and ms.b is None
+    ms.get_trajectory()
+    np.testing.assert_allclose(ms.A, g["v3_course_A"], rtol=1e-14, atol=0)
+    np.testing.assert_array_equal(ms.b, g["v3_course_b"])
+    assert ms.A.shape == (6 * ms.nb_splines + 2, 8 * ms.nb_splines) and np.abs(ms.A @ ms.coeffs - ms.b).max() < 1e-9
+    batch = MinimumSnap([g["waypoints"][1:], g["waypoints"][:2], g["waypoints"][1:] + 1.0], None, 3.0, 0.01)
+    batch.get_trajectory()
+    assert isinstance(batch.A, list) and tuple(batch.A[1].shape) == (8, 8)
+    np.testing.assert_allclose(batch.A[0].cpu().numpy(), g["v3_course_A"], rtol=1e-14, atol=0)
+    np.testing.assert_allclose(batch.A[1].cpu().numpy(), g["v3_takeoff_A"], rtol=1e-14, atol=0)
+    # controller.py:132-154 with nothing but its arguments (reference unit test: identity attitude, commanded tilt)
+    ctrl = CascadedController(9.81, 0.01)
+    pq = ctrl.roll_pitch_controller(np.array([0.1, -0.2]), np.eye(3), 2.0, 4.0)
+    assert tuple(pq.shape) == (1, 2) and np.allclose(pq.cpu().numpy(), [[0.8, 0.2]], atol=1e-6)     # p = -kp_pitch b_y, q = kp_roll b_x at R = I
+    B = 5
+    rot = torch.eye(3, device=cuda).expand(B, 3, 3).contiguous()
+    pqB = ctrl.roll_pitch_controller(torch.tensor([[0.1, -0.2]], device=cuda).expand(B, 2), rot, 2.0, 4.0)
+    assert tuple(pqB.shape) == (B, 2) and np.allclose(pqB.cpu().numpy(), [[0.8, 0.2]] * B, atol=1e-6)

@@ -32,7 +32,7 @@ M_FINAL_DIST, M_COLLISION, M_RMSE, M_MEAN_ERR, M_MAX_ERR, M_STATUS, M_FIRST_HIT,
 SYMBOLS = (
     "uavb_version", "uavb_last_error", "uavb_device_count", "uavb_device_info", "uavb_minsnap_solve_f64",
     "uavb_minsnap_solve_ragged_f64", "uavb_minsnap_table_meta_f64", "uavb_minsnap_sample_f64", "uavb_minsnap_yaw_profile_f64",
-    "uavb_minsnap_table_hits_f64", "uavb_minsnap_correct_f64", "uavb_minsnap_pack_f64", "uavb_plan_shared_f64",
+    "uavb_minsnap_table_hits_f64", "uavb_minsnap_correct_f64", "uavb_minsnap_pack_f64", "uavb_plan_shared_f64", "uavb_minsnap_constraints_f64",
     "uavb_rollout_targets_f64", "uavb_rollout_f32", "uavb_rollout_f64", "uavb_vehicle_defaults", "uavb_stage_f32", "uavb_mc_uniform_f32",
     "uavb_mc_missions_f64", "uavb_measure_fma_peak", "uavb_measure_fma_rates", "uavb_minsnap_solve_f64_host", "uavb_fly_mission_host", "uavb_rrt_workspace_bytes", "uavb_rrt_star_f64", "uavb_segments_hit_aabbs_f64",
 )
@@ -119,6 +119,7 @@ def lib() -> ctypes.CDLL:
     L.uavb_minsnap_correct_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_int, c_longlong, c_void_p, c_void_p,
                                            c_void_p, POINTER(c_int), c_void_p]
     L.uavb_minsnap_pack_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.uavb_minsnap_constraints_f64.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.uavb_plan_shared_f64.argtypes = [c_int, POINTER(c_void_p), POINTER(c_int), c_void_p, c_double, c_double, c_void_p, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]
     L.uavb_rollout_targets_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_int, c_void_p]

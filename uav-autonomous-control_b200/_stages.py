@@ -41,7 +41,8 @@ def soa(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def run(stage: int, quad, dt_outer: float, B: int, *, gains: Optional[dict] = None, **arrays) -> None:
-    """Launch one stage.  ``arrays`` are SoA float32 device tensors keyed by the struct field names;
+    """Launch one stage.  ``dt_outer`` is CascadedController.dt (the integrator step of the ALTITUDE / OUTER stages; the vehicle
+    stages never read it and pass their own dt).  ``arrays`` are SoA float32 device tensors keyed by the struct field names;
     ``gains`` overrides vehicle gains by name with floats or (B,) tensors (the reference passes gains
     as method arguments)."""
     a = nat.StageArgs()
@@ -62,4 +63,5 @@ def run(stage: int, quad, dt_outer: float, B: int, *, gains: Optional[dict] = No
         setattr(a, name, nat.ptr(t, _F32, name))
         dev = t.device
         keep.append(t)
-    nat.check(nat.lib().uavb_stage_f32(ctypes.byref(a), nat.stream_ptr(dev)), "uavb_stage_f32")
+    with torch.cuda.device(dev):                      # the library works on the CURRENT device: make it the tensors' device
+        nat.check(nat.lib().uavb_stage_f32(ctypes.byref(a), nat.stream_ptr(dev)), "uavb_stage_f32")

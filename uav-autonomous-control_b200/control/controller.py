@@ -11,6 +11,25 @@ import torch
 from .. import _native as nat, _stages as st
 
 
+class _ArgumentsOnly:
+    """Stand-in vehicle for controller methods that read nothing but their arguments (roll_pitch_controller): the lab_course
+    constants with the gains the caller passed."""
+
+    def __init__(self, batch: int, device):
+        self.batch, self.device = int(batch), device
+
+    def vehicle_struct(self, B: int, gain_overrides: dict):
+        v = nat.default_vehicle()
+        mc = {}
+        gains = [gain_overrides.get(n, v.gains[k]) for k, n in enumerate(nat.GAIN_NAMES)]
+        if any(isinstance(gv, torch.Tensor) for gv in gains):
+            mc["mc_gains"] = torch.stack([st.as_batch(gv, B, None, self.device) for gv in gains]).contiguous()
+            v.gains[:] = [float(torch.as_tensor(gv).double().mean()) for gv in gains]
+        else:
+            v.gains[:] = [float(gv) for gv in gains]
+        return v, mc
+
+
 class CascadedController:
     """Cascaded controller (Lupashin et al.) for B drones."""
 
@@ -88,12 +107,17 @@ class CascadedController:
 
     def roll_pitch_controller(self, bxy_cmd, rot_mat, kp_roll, kp_pitch, quad=None) -> torch.Tensor:
         """[p_cmd, q_cmd] (B, 2) from the commanded and actual [R02, R12] (controller.py:132-154).
-        The reference method is static in its inputs; ``quad`` only supplies batch size and device."""
+        The reference method takes no vehicle: it reads only its arguments.  So does this one -- the batch size and the device
+        come from ``bxy_cmd`` / ``rot_mat`` ((B, 2) / (B, 3, 3); plain (2,) / (3, 3) inputs are one drone, as in the reference) --
+        and ``quad`` is an optional hint for them (reduced_attitude passes it)."""
         if quad is None:
-            raise TypeError("the batched roll_pitch_controller needs quad=... for the batch size and the device")
+            bt, rt = torch.as_tensor(bxy_cmd), torch.as_tensor(rot_mat)
+            B = bt.shape[0] if bt.dim() == 2 else (rt.shape[0] if rt.dim() == 3 else 1)
+            device = next((t.device for t in (bt, rt) if t.is_cuda), torch.device("cuda", torch.cuda.current_device()))
+            quad = _ArgumentsOnly(B, device)
         B = quad.batch
         pqr = torch.zeros((3, B), dtype=torch.float32, device=quad.device)
-        st.run(nat.STAGE_ROLL_PITCH, quad, self.dt, B, gains=dict(kp_roll=kp_roll, kp_pitch=kp_pitch), X=st.soa(quad.X),
+        st.run(nat.STAGE_ROLL_PITCH, quad, self.dt, B, gains=dict(kp_roll=kp_roll, kp_pitch=kp_pitch), X=st.soa(getattr(quad, "X", None)),
                bxy=st.soa(st.as_batch(bxy_cmd, B, 2, quad.device)), rot=self._rot(quad, rot_mat), pqr_cmd=pqr)
         return pqr[:2].t().contiguous()
 

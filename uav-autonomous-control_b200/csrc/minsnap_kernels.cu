@@ -501,6 +501,56 @@ __global__ void __launch_bounds__(128) table_hits_kernel(const double* __restric
   if (lane == 0) hit_mask[b] |= m;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The reference's constraint system A c = b (minimum_snap.py:171-255) in its own row order, one thread per (mission, row):
+//   rows [0, S)        position of spline i at t = 0        = waypoint i          (:233-239)
+//   rows [S, 2S)       position of spline i at t = T_i      = waypoint i+1        (:241-248)
+//   rows 2S .. 2S+2    derivatives 1..3 of the first spline at t = 0   = 0        (:215-219)
+//   rows 2S+3 .. 2S+5  derivatives 1..3 of the last spline at t = T    = 0        (:221-225)
+//   then, for every interior waypoint s = 1 .. S-1 and k = 1..4: polynom(k, T_{s-1}) on spline s-1 minus polynom(k, 0) on spline s (:196-204)
+// polynom(n, k, t)[i] = i! / (i-k)! t^(i-k) (:258-286).  K1 never forms this system (it solves the reduced problem); the kernel
+// exists for the MinimumSnap.A / .b attributes of the reference API.
+__device__ __forceinline__ double basis_entry(int i, int k, double t) {
+  if (i < k) return 0.0;
+  double f = 1.0;
+  for (int m = 0; m < k; ++m) f *= (double)(i - m);
+  double p = 1.0;
+  for (int m = 0; m < i - k; ++m) p *= t;
+  return f * p;
+}
+
+__global__ void __launch_bounds__(128) constraint_rows_kernel(const double* __restrict__ waypoints, const double* __restrict__ times, int B, int S,
+                                                              double* __restrict__ A, double* __restrict__ b) {
+  const int n_rows = 6 * S + 2, n_cols = 8 * S;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)B * n_rows) return;
+  const int m = (int)(g / n_rows), r = (int)(g - (long long)m * n_rows);
+  const double* w = waypoints + (size_t)m * (S + 1) * 3;
+  const double* T = times + (size_t)m * S;
+  double* row = A + (size_t)g * n_cols;
+  double* rhs = b + (size_t)g * 3;
+  for (int c = 0; c < n_cols; ++c) row[c] = 0.0;
+  rhs[0] = rhs[1] = rhs[2] = 0.0;
+  if (r < 2 * S) {
+    const int i = r < S ? r : r - S;
+    const double t = r < S ? 0.0 : T[i];
+    for (int c = 0; c < 8; ++c) row[8 * i + c] = basis_entry(c, 0, t);
+    const double* p = w + 3 * (r < S ? i : i + 1);
+    rhs[0] = p[0]; rhs[1] = p[1]; rhs[2] = p[2];
+  } else if (r < 2 * S + 6) {
+    const int q = r - 2 * S, k = q % 3 + 1;
+    const int i = q < 3 ? 0 : S - 1;
+    const double t = q < 3 ? 0.0 : T[S - 1];
+    for (int c = 0; c < 8; ++c) row[8 * i + c] = basis_entry(c, k, t);
+  } else {
+    const int q = r - 2 * S - 6, s = q / 4 + 1, k = q % 4 + 1;
+    for (int c = 0; c < 8; ++c) {
+      row[8 * (s - 1) + c] = basis_entry(c, k, T[s - 1]);
+      row[8 * s + c] = -1.0 * basis_entry(c, k, 0.0);
+    }
+  }
+}
+
 template <int MAXS, int MODE, int MINB>
 static int launch_solve(const double* w, const double* vel, int B, int S, double factor, double* c, double* t, int* st, cudaStream_t stream,
                         const CUtensorMap* tmap = nullptr) {
@@ -659,6 +709,18 @@ extern "C" int uavb_minsnap_table_hits_f64(const double* table, const int* row_o
   if (B == 0) return UAVB_OK;
   table_hits_kernel<<<div_up((long long)B * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(table, row_offsets, B, cuboid,
                                                                                                  cuboid_stride, hit_mask_out);
+  UAVB_CUDA_OK(cudaGetLastError());
+  return UAVB_OK;
+}
+
+extern "C" int uavb_minsnap_constraints_f64(const double* waypoints, const double* times, int B, int S, double* A_out, double* b_out, void* stream) {
+  UAVB_REQUIRE(waypoints && times && A_out && b_out, "minsnap_constraints: NULL pointer");
+  UAVB_REQUIRE(B >= 0 && S >= 1 && S <= UAVB_MAX_SPLINES, "minsnap_constraints: B >= 0 and 1 <= S <= UAVB_MAX_SPLINES required");
+  int rc = require_device();
+  if (rc) return rc;
+  if (B == 0) return UAVB_OK;
+  const long long n = (long long)B * (6 * S + 2);
+  constraint_rows_kernel<<<div_up(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(waypoints, times, B, S, A_out, b_out);
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }

@@ -61,6 +61,17 @@ def minsnap_solve_ragged(waypoints: torch.Tensor, wp_offsets: torch.Tensor, velo
     return coeffs, times, status
 
 
+def minsnap_constraints(waypoints: torch.Tensor, times: torch.Tensor):
+    """MinimumSnap.A / MinimumSnap.b of the reference (minimum_snap.py:171-255, same row order) for B missions of S splines:
+    waypoints [B, S+1, 3], times [B, S] -> A [B, 6S+2, 8S], b [B, 6S+2, 3]."""
+    B, S = waypoints.shape[0], waypoints.shape[1] - 1
+    A = torch.empty((B, 6 * S + 2, 8 * S), dtype=torch.float64, device=waypoints.device)
+    b = torch.empty((B, 6 * S + 2, 3), dtype=torch.float64, device=waypoints.device)
+    nat.check(nat.lib().uavb_minsnap_constraints_f64(nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(times, torch.float64, "times"), B, S,
+                                                     nat.ptr(A), nat.ptr(b), nat.stream_ptr(waypoints.device)), "uavb_minsnap_constraints_f64")
+    return A, b
+
+
 def table_meta(coeffs: torch.Tensor, times: torch.Tensor, seg_offsets: torch.Tensor, dt: float):
     """Rows per segment, look-ahead yaw and total rows per table (minimum_snap.py:104, 126-136).
 
@@ -519,7 +530,8 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
         a.traj_out, a.traj_count_out = nat.ptr(res.traj, torch.float32, "traj"), nat.ptr(res.traj_count, torch.int32, "traj_count")
         a.traj_max_samples, a.traj_gate_z, a.traj_interval = int(res.traj.shape[0]), float(traj_gate_z), float(traj_interval)
     fn = nat.lib().uavb_rollout_f64 if f64 else nat.lib().uavb_rollout_f32
-    nat.check(fn(ctypes.byref(a), nat.stream_ptr(dev)), "uavb_rollout_f64" if f64 else "uavb_rollout_f32")
+    with torch.cuda.device(dev):                      # the library works on the CURRENT device: make it the tensors' device
+        nat.check(fn(ctypes.byref(a), nat.stream_ptr(dev)), "uavb_rollout_f64" if f64 else "uavb_rollout_f32")
     return res
 
 

@@ -4,6 +4,11 @@
 (main.py:10-61) and drives B drones per call through the stage kernels; ``main()`` flies the
 laboratory course for a Monte-Carlo batch in one launch of the persistent rollout kernel and prints
 the mission report of main.py:115-120 as fractions over the batch.
+
+Precision of the method-level path: ``quad.X`` and the table handed to ``TrajectoryController`` are float32 tensors (the stage
+kernels' interface), so positions round at ~1e-6 m near |p| = 20 m every tick and the path holds ~1e-3 m over a mission -- it
+exists for method-by-method parity with the reference classes.  The fused rollout (``BatchedSimulation.rollout`` /
+``kernels.rollout``) keeps fp64 set-points and an fp64 position fold and is the one that meets the 1e-4 m budget.
 """
 from __future__ import annotations
 

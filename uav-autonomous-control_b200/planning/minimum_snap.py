@@ -9,7 +9,8 @@ then returns the packed (rows, 11) CUDA tensor and ``row_offsets`` delimits the 
 
 The coefficients are the unique minimiser the reference obtains from its KKT system (K1 computes it
 from the reduced block-tridiagonal form), so ``method`` ("lstsq" / "solve") is accepted for
-signature compatibility and does not change the result.  ``A`` and ``b`` are never formed and stay None.
+signature compatibility and does not change the result.  The solver never forms the reference's constraint system; the
+``A`` and ``b`` attributes are materialised on first access (on the device, in the reference's row order) once a plan exists.
 """
 from __future__ import annotations
 
@@ -71,8 +72,8 @@ class MinimumSnap:
         self.snap = []
         self.full_trajectory = None
         self.row_counter = 0
-        self.A = None
-        self.b = None
+        self._A = None
+        self._b = None
         self.coeffs = None
         self.row_offsets = None
         self.status = None
@@ -81,6 +82,39 @@ class MinimumSnap:
     def get_trajectory(self):
         self._generate_collision_free_trajectory()
         return self.full_trajectory
+
+    def _constraint_system(self):
+        """A and b of the reference (minimum_snap.py:171-255) for the current waypoints and times; None before a plan exists
+        (the reference allocates them in _setup, :288-293, during _compute_spline_parameters).  Single mission: NumPy
+        (6S+2, 8S) / (6S+2, 3); batch: one tensor per mission (a stacked tensor when every mission has the same S)."""
+        if self._A is None and self.coeffs is not None:
+            times = self._times_dev
+            off = self._seg_offsets.cpu().numpy()
+            groups = {}
+            for b_, p_ in enumerate(self._paths):
+                groups.setdefault(len(p_) - 1, []).append(b_)
+            A_list, b_list = [None] * len(self._paths), [None] * len(self._paths)
+            for S, members in groups.items():
+                wp = torch.tensor(np.stack([self._paths[m] for m in members]), dtype=torch.float64, device=self.device)
+                tt = torch.stack([times[off[m]:off[m] + S] for m in members]).contiguous()
+                A, b = kernels.minsnap_constraints(wp, tt)
+                for k, m in enumerate(members):
+                    A_list[m], b_list[m] = A[k], b[k]
+            if self._single:
+                self._A, self._b = A_list[0].cpu().numpy(), b_list[0].cpu().numpy()
+            elif len(groups) == 1:
+                self._A, self._b = torch.stack(A_list), torch.stack(b_list)
+            else:
+                self._A, self._b = A_list, b_list
+        return self._A, self._b
+
+    @property
+    def A(self):
+        return self._constraint_system()[0]
+
+    @property
+    def b(self):
+        return self._constraint_system()[1]
 
     # ------------------------------------------------------------------ planning on the device
     def _velocity_tensor(self) -> torch.Tensor:

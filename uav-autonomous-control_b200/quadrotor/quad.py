@@ -103,14 +103,14 @@ class Quad:
         thrust = st.as_batch(thrust_cmd, B, None, self.device)
         moment = st.soa(st.as_batch(moment_cmd, B, 3, self.device))
         omega, cmd = st.soa(self.omega), torch.empty((4, B), dtype=torch.float32, device=self.device)
-        st.run(nat.STAGE_PROPELLER, self, self.dt * 10, B, thrust=thrust, moment=moment, omega=omega, omega_cmd=cmd)
+        st.run(nat.STAGE_PROPELLER, self, self.dt, B, thrust=thrust, moment=moment, omega=omega, omega_cmd=cmd)
         self.omega, self.omega_command = omega.t().contiguous(), cmd.t().contiguous()
 
     def _allocate_rotor_forces(self, thrust_cmd, moment_cmd) -> torch.Tensor:
         """Rotor forces (B, 4) that keep the feasible collective and scale the moments into the limits (quad.py:105-122)."""
         B = self.batch
         forces = torch.empty((4, B), dtype=torch.float32, device=self.device)
-        st.run(nat.STAGE_ALLOCATE, self, self.dt * 10, B, thrust=st.as_batch(thrust_cmd, B, None, self.device),
+        st.run(nat.STAGE_ALLOCATE, self, self.dt, B, thrust=st.as_batch(thrust_cmd, B, None, self.device),
                moment=st.soa(st.as_batch(moment_cmd, B, 3, self.device)), forces=forces)
         return forces.t().contiguous()
 
@@ -124,7 +124,7 @@ class Quad:
         B = self.batch
         rot = torch.empty((9, B), dtype=torch.float32, device=self.device) if want_rot else None
         eul = torch.empty((3, B), dtype=torch.float32, device=self.device) if want_euler else None
-        st.run(nat.STAGE_ATTITUDE, self, self.dt * 10, B, X=st.soa(self.X), rot_out=rot, euler_out=eul)
+        st.run(nat.STAGE_ATTITUDE, self, self.dt, B, X=st.soa(self.X), rot_out=rot, euler_out=eul)
         return (rot.t().reshape(B, 3, 3).contiguous() if want_rot else None), (eul.t().contiguous() if want_euler else None)
 
     def R(self) -> torch.Tensor:

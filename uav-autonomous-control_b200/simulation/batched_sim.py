@@ -94,7 +94,7 @@ class BatchedSimulation:
         B = self.batch
         X = st.soa(q.X)
         zb_next = torch.empty_like(self._zb)
-        st.run(nat.STAGE_PHYSICS, q, q.dt * 10, B, X=X, omega=st.soa(q.omega), zb=self._zb if self.thrust_frame_lag else None,
+        st.run(nat.STAGE_PHYSICS, q, q.dt, B, X=X, omega=st.soa(q.omega), zb=self._zb if self.thrust_frame_lag else None,
                zb_out=zb_next, wind=st.soa(self.wind) if self.wind is not None else None,
                aabbs=self._obs if len(self.obstacles) else None, n_obs=len(self.obstacles), collided=self._collided)
         self._zb = zb_next
