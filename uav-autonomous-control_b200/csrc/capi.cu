@@ -56,6 +56,24 @@ cudaMemPool_t scratch_pool() {
   return pools[dev];
 }
 
+void* pinned_scratch(int slot, size_t bytes) {
+  thread_local void* buf[2] = {nullptr, nullptr};
+  thread_local size_t cap[2] = {0, 0};
+  if (slot < 0 || slot > 1) return nullptr;
+  if (bytes > cap[slot]) {
+    if (buf[slot]) cudaFreeHost(buf[slot]);
+    buf[slot] = nullptr; cap[slot] = 0;
+    const size_t want = bytes < 4096 ? 4096 : bytes;
+    if (cudaHostAlloc(&buf[slot], want, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      buf[slot] = nullptr;
+      return nullptr;
+    }
+    cap[slot] = want;
+  }
+  return buf[slot];
+}
+
 TensorMapEncodeTiledFn tensor_map_encoder() {
   static TensorMapEncodeTiledFn fn = nullptr;
   static std::once_flag once;

@@ -151,13 +151,31 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
     // sampled point lies inside a box, minimum_snap.py:63-95; nothing is inserted on lab_course) and are packed into the
     // segment arrays of a shared-mission rollout -- one synchronisation when nothing is hit (plan_shared_tables)
     const bool correct = m->n_obs > 0 && !m->no_correction;
-    std::vector<double> boxes;
-    if (correct) {
-      boxes.resize((size_t)m->n_obs * 6);
-      for (size_t k = 0; k < boxes.size(); ++k) boxes[k] = m->plan_aabbs ? m->plan_aabbs[k] : (double)m->aabbs[k];
+    // the small inputs travel as ONE pinned block: waypoints, planner boxes (fp64), velocities, start, goal | collision boxes (fp32)
+    const size_t n_wpd = (size_t)m->n_waypoints * 3, n_boxd = correct ? (size_t)m->n_obs * 6 : 0, n_aabb = (size_t)m->n_obs * 6;
+    const size_t n_dbl = n_wpd + n_boxd + 2 + 3 + 3, blob_bytes = sizeof(double) * n_dbl + sizeof(float) * n_aabb;
+    double* h_blob = static_cast<double*>(pinned_scratch(1, blob_bytes));
+    char* d_blob = pool.alloc<char>(blob_bytes);
+    if (h_blob == nullptr || pool.err != cudaSuccess) result = set_error(UAVB_ENOMEM, "fly_mission_host: scratch allocation failed");
+    double* d_wp = reinterpret_cast<double*>(d_blob);
+    double* d_boxes = correct ? d_wp + n_wpd : nullptr;
+    double* d_vel = d_wp + n_wpd + n_boxd;
+    double* d_start = d_vel + 2;
+    double* d_goal = d_start + 3;
+    float* d_aabbs = m->n_obs > 0 ? reinterpret_cast<float*>(d_goal + 3) : nullptr;
+    if (!result) {
+      for (size_t k = 0; k < n_wpd; ++k) h_blob[k] = m->waypoints[k];
+      for (size_t k = 0; k < n_boxd; ++k) h_blob[n_wpd + k] = m->plan_aabbs ? m->plan_aabbs[k] : (double)m->aabbs[k];
+      double* hv = h_blob + n_wpd + n_boxd;
+      hv[0] = hv[1] = m->velocity;
+      const double* s3 = m->start ? m->start : m->waypoints;
+      const double* g3 = m->goal ? m->goal : m->waypoints + 3 * (size_t)(m->n_waypoints - 1);
+      for (int k = 0; k < 3; ++k) { hv[2 + k] = s3[k]; hv[5 + k] = g3[k]; }
+      float* ha = reinterpret_cast<float*>(hv + 8);
+      for (size_t k = 0; k < n_aabb; ++k) ha[k] = m->aabbs[k];
+      const cudaError_t e = cudaMemcpyAsync(d_blob, h_blob, blob_bytes, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) result = set_error(UAVB_ECUDA, "fly_mission_host: %s", cudaGetErrorString(e));
     }
-    double* d_wp = pool.upload(m->waypoints, (size_t)m->n_waypoints * 3);
-    double* d_boxes = correct ? pool.upload(boxes.data(), boxes.size()) : nullptr;
     constexpr int kCapSeg = 2 * UAVB_MAX_SPLINES;
     double* d_coeffs = pool.alloc<double>((size_t)kCapSeg * 24);
     double* d_times = pool.alloc<double>(kCapSeg);
@@ -167,9 +185,6 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
     if (pool.err != cudaSuccess) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
     const double* tab_wp[2] = {d_wp, d_wp + 3 * (size_t)(m->n_takeoff_waypoints ? m->n_takeoff_waypoints - 1 : 0)};
     const int tab_n[2] = {S0 + 1, S1 + 1};
-    const double vel2[2] = {m->velocity, m->velocity};
-    double* d_vel = pool.upload(vel2, 2);
-    if (pool.err != cudaSuccess && !result) result = set_error(UAVB_ENOMEM, "fly_mission_host: %s", cudaGetErrorString(pool.err));
     int status[2] = {0, 0}, tab_rows[2] = {0, 0}, n_seg = 0;
     if (!result)
       result = plan_shared_tables(n_tab, tab_wp, tab_n, d_vel, m->start_end_time_factor, dt_outer, d_boxes, correct ? m->n_obs : 0, kCapSeg, d_coeffs,
@@ -201,9 +216,9 @@ extern "C" int uavb_fly_mission_host(const uavb_mission_host* m, float* metrics_
         a.shared_targets = d_targets;
         a.n_target_rows = (int)total_rows;
       }
-      a.start = pool.upload(m->start ? m->start : m->waypoints, 3);
-      a.goal = pool.upload(m->goal ? m->goal : m->waypoints + 3 * (size_t)(m->n_waypoints - 1), 3);
-      a.aabbs = m->n_obs > 0 ? pool.upload(m->aabbs, (size_t)m->n_obs * 6) : nullptr;
+      a.start = d_start;
+      a.goal = d_goal;
+      a.aabbs = d_aabbs;
       float* d_metrics = pool.alloc<float>(B * UAVB_N_METRICS);
       float* d_state = state_out ? pool.alloc<float>(B * UAVB_STATE_DIM) : nullptr;
       a.metrics_out = d_metrics; a.state_out = d_state;

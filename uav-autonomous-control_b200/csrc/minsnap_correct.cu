@@ -199,23 +199,24 @@ static int launch_solve_list(int bucket, const double* wp, const int* n_wp, cons
 
 // The loop behind uavb_minsnap_correct_f64 (arguments as there).  The first round is launched blind -- every bucket's kernels over a
 // grid sized for B, each reading its list length from device memory -- so a batch in which nothing is hit costs ONE host
-// synchronisation; later rounds are sized from the counters read back.  n_wp_host / status_host (optional, [B] host ints) receive
-// n_waypoints / status with the final read-back; after_first_round (optional) enqueues the caller's follow-up work between round 1
+// synchronisation; later rounds are sized from the counters read back.  ctrl (optional): a zeroed device block of ints whose first
+// 2 x 4 words serve as the counters and whose other words belong to the caller (who may place n_waypoints / status in it); every
+// round's read-back copies the whole block to ctrl->host (pinned) in ONE transfer.  after_first_round (optional) enqueues the caller's follow-up work between round 1
 // and its read-back, so that a plan in which nothing is hit is complete after that one synchronisation (plan_shared_tables);
 // n_wp_known (optional, [B] host ints): the initial n_waypoints when the host has them, to launch only the buckets in use.
 int correct_missions(double* waypoints, int* n_waypoints, const double* velocity, int B, int max_wp, double factor, double dt, const double* cuboids,
-                     int n_obs, long long cuboid_stride, double* coeffs_out, double* times_out, int* status_out, int* rounds_out, int* n_wp_host,
-                     int* status_host, cudaStream_t st, const std::function<int()>* after_first_round, const int* n_wp_known) {
+                     int n_obs, long long cuboid_stride, double* coeffs_out, double* times_out, int* status_out, int* rounds_out, cudaStream_t st,
+                     const std::function<int()>* after_first_round, const int* n_wp_known, const CtrlBlock* ctrl) {
   int result = UAVB_OK;
   cudaError_t e = cudaSuccess;
   {
     DevPool pool(st);
     int* obs_idx = pool.alloc<int>(B);
     int* lists = pool.alloc<int>((size_t)2 * kBuckets * B);
-    int* counts = pool.alloc<int>(2 * kBuckets);
+    int* counts = ctrl ? ctrl->dev : pool.alloc<int>(2 * kBuckets);
     if (pool.err != cudaSuccess) return set_error(UAVB_ENOMEM, "minsnap_correct: %s", cudaGetErrorString(pool.err));
     WorkLists wl[2] = {{lists, counts}, {lists + (size_t)kBuckets * B, counts + kBuckets}};
-    UAVB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * 2 * kBuckets, st));
+    if (!ctrl) UAVB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * 2 * kBuckets, st));      // a control block arrives zeroed
     correct_classify_kernel<<<div_up(B, 256), 256, 0, st>>>(n_waypoints, B, max_wp, obs_idx, status_out, wl[0]);
     e = cudaGetLastError();
     int host_counts[kBuckets] = {B, B, B, B};             // round 1: upper bounds, the kernels read the real lengths
@@ -245,10 +246,16 @@ int correct_missions(double* waypoints, int* n_waypoints, const double* velocity
       }
       // work the caller wants behind round 1 and in front of its read-back (valid if nothing was hit: rounds_out == 1)
       if (e == cudaSuccess && !result && rounds == 1 && after_first_round) result = (*after_first_round)();
-      if (e == cudaSuccess && !result) e = cudaMemcpyAsync(host_counts, out.count, sizeof(host_counts), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess && !result && n_wp_host) e = cudaMemcpyAsync(n_wp_host, n_waypoints, sizeof(int) * B, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess && !result && status_host) e = cudaMemcpyAsync(status_host, status_out, sizeof(int) * B, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess && !result) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess && !result) {
+        if (ctrl) {                                       // the whole control block (counters + the caller's words) in one copy
+          e = cudaMemcpyAsync(ctrl->host, ctrl->dev, sizeof(int) * ctrl->ints, cudaMemcpyDeviceToHost, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+          for (int k = 0; k < kBuckets; ++k) host_counts[k] = ctrl->host[(cur ^ 1) * kBuckets + k];
+        } else {
+          e = cudaMemcpyAsync(host_counts, out.count, sizeof(host_counts), cudaMemcpyDeviceToHost, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+      }
       cur ^= 1;
     }
     if (rounds_out) *rounds_out = rounds;
@@ -288,43 +295,56 @@ int plan_shared_tables(int T, const double* const* d_waypoints, const int* n_wp_
   UAVB_REQUIRE(n_seg0 <= cap_seg, "plan_shared: cap_seg is smaller than the mission");
   int result = UAVB_OK;
   {
+    // ONE scratch allocation, ONE upload and ONE read-back per round.  Control block (ints): [0, 8) the loop's counters,
+    // then n_waypoints [T], status [T], table rows [T], segment offsets [T + 1]; its host mirror is pinned.
+    const int o_nwp = 2 * kBuckets, o_status = o_nwp + T, o_total = o_status + T, o_offs = o_total + T, n_ints = o_offs + T + 1;
+    const size_t b_ints = ((size_t)n_ints * sizeof(int) + 15) / 16 * 16;
+    const size_t b_fixed = sizeof(double) * (size_t)T * kMaxWp * 3, b_cf = sizeof(double) * (size_t)T * UAVB_MAX_SPLINES * 24;
+    const size_t b_tf = sizeof(double) * (size_t)T * UAVB_MAX_SPLINES, b_yaw = sizeof(double) * (size_t)T;
     DevPool pool(st);
-    double* d_fixed = pool.alloc<double>((size_t)T * kMaxWp * 3);
-    int* d_n_wp = pool.upload(n_wp_in, T);
-    double* d_cf = pool.alloc<double>((size_t)T * UAVB_MAX_SPLINES * 24);
-    double* d_tf = pool.alloc<double>((size_t)T * UAVB_MAX_SPLINES);
-    int* d_status = pool.alloc<int>(T);
-    int* d_offs = pool.alloc<int>(T + 1);
-    double* d_yaw0 = pool.alloc<double>(T);
-    int* d_total = pool.alloc<int>(T);
-    if (pool.err != cudaSuccess) return set_error(UAVB_ENOMEM, "plan_shared: %s", cudaGetErrorString(pool.err));
+    char* blob = pool.alloc<char>(b_fixed + b_cf + b_tf + b_yaw + b_ints);
+    int* host = static_cast<int*>(pinned_scratch(0, sizeof(int) * 2 * n_ints));   // [0, n_ints) read-back mirror, [n_ints, 2 n_ints) upload image
+    if (pool.err != cudaSuccess || host == nullptr) return set_error(UAVB_ENOMEM, "plan_shared: scratch allocation failed");
+    double* d_fixed = reinterpret_cast<double*>(blob);
+    double* d_cf = reinterpret_cast<double*>(blob + b_fixed);
+    double* d_tf = reinterpret_cast<double*>(blob + b_fixed + b_cf);
+    double* d_yaw0 = reinterpret_cast<double*>(blob + b_fixed + b_cf + b_tf);
+    int* d_ctrl = reinterpret_cast<int*>(blob + b_fixed + b_cf + b_tf + b_yaw);
+    int* d_n_wp = d_ctrl + o_nwp; int* d_status = d_ctrl + o_status; int* d_total = d_ctrl + o_total; int* d_offs = d_ctrl + o_offs;
+    int* up = host + n_ints;
+    for (int i = 0; i < n_ints; ++i) up[i] = 0;
+    up[o_offs] = 0;
+    for (int k = 0; k < T; ++k) { up[o_nwp + k] = n_wp_in[k]; up[o_offs + k + 1] = up[o_offs + k] + n_wp_in[k] - 1; }
+    UAVB_CUDA_OK(cudaMemcpyAsync(d_ctrl, up, sizeof(int) * n_ints, cudaMemcpyHostToDevice, st));       // zeroed counters, n_waypoints, offsets
     for (int k = 0; k < T; ++k)
       UAVB_CUDA_OK(cudaMemcpyAsync(d_fixed + (size_t)k * kMaxWp * 3, d_waypoints[k], sizeof(double) * 3 * n_wp_in[k], cudaMemcpyDeviceToDevice, st));
-    int n_wp[kMaxSharedTables], status[kMaxSharedTables], offs[kMaxSharedTables + 1];
-    // pack + table geometry + segment flags + read-back of the rows per table, for the spline counts in `counts`
-    auto tail = [&](const int* counts) -> int {
-      offs[0] = 0;
-      for (int k = 0; k < T; ++k) offs[k + 1] = offs[k] + counts[k] - 1;
-      if (offs[T] > cap_seg) return set_error(UAVB_EINVAL, "plan_shared: the corrected mission has %d splines, cap_seg is %d", offs[T], cap_seg);
-      UAVB_CUDA_OK(cudaMemcpyAsync(d_offs, offs, sizeof(int) * (T + 1), cudaMemcpyHostToDevice, st));
+    // pack + table geometry + segment flags for the segment offsets now in d_offs
+    auto tail = [&](int n_seg) -> int {
       int rc = uavb_minsnap_pack_f64(d_cf, d_tf, d_n_wp, T, kMaxWp, d_offs, seg_coeffs, seg_times, st);
       if (!rc) rc = uavb_minsnap_table_meta_f64(seg_coeffs, seg_times, d_offs, T, dt, seg_rows, d_yaw0, d_total, st);
       if (rc) return rc;
-      shared_seg_flags_kernel<<<div_up(offs[T], 128), 128, 0, st>>>(d_offs, d_yaw0, T, offs[T], seg_table, seg_yaw0);
+      shared_seg_flags_kernel<<<div_up(n_seg, 128), 128, 0, st>>>(d_offs, d_yaw0, T, n_seg, seg_table, seg_yaw0);
       UAVB_CUDA_OK(cudaGetLastError());
-      UAVB_CUDA_OK(cudaMemcpyAsync(rows_out, d_total, sizeof(int) * T, cudaMemcpyDeviceToHost, st));
       return UAVB_OK;
     };
-    const std::function<int()> speculative = [&]() { return tail(n_wp_in); };
-    int rounds = 0;
-    result = correct_missions(d_fixed, d_n_wp, d_velocity, T, kMaxWp, factor, dt, d_cuboids, n_obs, 0, d_cf, d_tf, d_status, &rounds, n_wp, status, st, &speculative, n_wp_in);
+    const std::function<int()> speculative = [&]() { return tail(n_seg0); };
+    const CtrlBlock ctrl{d_ctrl, host, n_ints};
+    int rounds = 0, n_seg = n_seg0;
+    result = correct_missions(d_fixed, d_n_wp, d_velocity, T, kMaxWp, factor, dt, d_cuboids, n_obs, 0, d_cf, d_tf, d_status, &rounds, st, &speculative, n_wp_in,
+                              &ctrl);
     if (!result && rounds > 1) {                            // midpoints were inserted: lay the mission out again
-      result = tail(n_wp);
+      n_seg = 0;
+      for (int k = 0; k < T; ++k) { up[o_offs + k] = n_seg; n_seg += host[o_nwp + k] - 1; }
+      up[o_offs + T] = n_seg;
+      if (n_seg > cap_seg) return set_error(UAVB_EINVAL, "plan_shared: the corrected mission has %d splines, cap_seg is %d", n_seg, cap_seg);
+      UAVB_CUDA_OK(cudaMemcpyAsync(d_offs, up + o_offs, sizeof(int) * (T + 1), cudaMemcpyHostToDevice, st));
+      result = tail(n_seg);
+      if (!result) UAVB_CUDA_OK(cudaMemcpyAsync(host, d_ctrl, sizeof(int) * n_ints, cudaMemcpyDeviceToHost, st));
       if (!result) UAVB_CUDA_OK(cudaStreamSynchronize(st));
     }
     if (!result) {
-      for (int k = 0; k < T; ++k) status_out[k] = status[k];
-      *n_seg_out = offs[T];
+      for (int k = 0; k < T; ++k) { status_out[k] = host[o_status + k]; rows_out[k] = host[o_total + k]; }
+      *n_seg_out = n_seg;
       if (rounds_out) *rounds_out = rounds;
     }
   }
@@ -348,7 +368,7 @@ extern "C" int uavb_minsnap_correct_f64(double* waypoints, int* n_waypoints, con
   if (rounds_out) *rounds_out = 0;
   if (B == 0) return UAVB_OK;
   return correct_missions(waypoints, n_waypoints, velocity, B, max_wp, factor, dt, cuboids, n_obs, cuboid_stride, coeffs_out, times_out, status_out,
-                          rounds_out, nullptr, nullptr, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+                          rounds_out, static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr);
 }
 
 extern "C" int uavb_minsnap_pack_f64(const double* coeffs, const double* times, const int* n_waypoints, int B, int max_wp, const int* seg_offsets,

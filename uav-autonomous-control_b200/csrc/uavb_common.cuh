@@ -64,12 +64,22 @@ struct DevPool {
   }
 };
 
-// The obstacle-correction loop behind uavb_minsnap_correct_f64 (minsnap_correct.cu) with an optional host copy of the final
-// n_waypoints / status in the same read-back as the loop's counters, and an optional hook that enqueues follow-up work behind
-// round 1 (complete after that round's synchronisation when nothing was hit).
+// Thread-local pinned (portable) host scratch of at least `bytes` bytes, grown on demand and kept for the life of the thread;
+// two independent slots (0: the planner's control block, 1: the host-buffer mission call's small inputs).  nullptr on failure.
+void* pinned_scratch(int slot, size_t bytes);
+
+// The obstacle-correction loop behind uavb_minsnap_correct_f64 (minsnap_correct.cu).  after_first_round (optional) enqueues
+// follow-up work behind round 1 (complete after that round's synchronisation when nothing was hit); n_wp_known (optional): the
+// initial n_waypoints on the host; ctrl (optional): a zeroed device block whose first 8 ints are the loop's counters, copied whole
+// to ctrl->host (pinned) at every round's read-back.
+struct CtrlBlock {
+  int* dev;
+  int* host;
+  int ints;
+};
 int correct_missions(double* waypoints, int* n_waypoints, const double* velocity, int B, int max_wp, double factor, double dt, const double* cuboids,
-                     int n_obs, long long cuboid_stride, double* coeffs_out, double* times_out, int* status_out, int* rounds_out, int* n_wp_host,
-                     int* status_host, cudaStream_t st, const std::function<int()>* after_first_round, const int* n_wp_known);
+                     int n_obs, long long cuboid_stride, double* coeffs_out, double* times_out, int* status_out, int* rounds_out, cudaStream_t st,
+                     const std::function<int()>* after_first_round, const int* n_wp_known, const CtrlBlock* ctrl);
 
 // One mission of T consecutive tables planned with the correction loop into shared-mission segment arrays (uavb_plan_shared_f64).
 constexpr int kMaxSharedTables = 8;
