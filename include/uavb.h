@@ -261,6 +261,9 @@ typedef struct uavb_rollout_args {
      back to ground_z and a downward velocity to zero.  Default 0: free body, as in round 1. */
   int           ground_on;
   double        ground_z;
+  int           pair_kernel_only; /* 0 = library policy: metrics-only fp32 rollouts with per-rollout missions fly one drone per thread
+                                     (the round-1 kernel, faster on such divergent batches), everything else two per thread;
+                                     1 = always two per thread.  Both meet the 1e-4 budget; their bits differ.                  */
   int           log_tma;      /* 0 = library policy: the fp32 log leaves through staged TMA tensor stores when B is a multiple of 4 and
                                  log_out is 16-byte aligned, else through per-thread streaming stores; -1 = always the latter (same bits) */
 } uavb_rollout_args;

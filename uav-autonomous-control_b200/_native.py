@@ -67,7 +67,7 @@ class RolloutArgs(Structure):
         ("aabbs", c_void_p), ("aabb_set", c_void_p),
         ("carry", c_void_p), ("state_out", c_void_p), ("metrics_out", c_void_p), ("log_out", c_void_p),
         ("traj_out", c_void_p), ("traj_count_out", c_void_p), ("traj_max_samples", c_int), ("traj_gate_z", c_double), ("traj_interval", c_double),
-        ("ground_on", c_int), ("ground_z", c_double), ("log_tma", c_int),
+        ("ground_on", c_int), ("ground_z", c_double), ("pair_kernel_only", c_int), ("log_tma", c_int),
     ]
 
 

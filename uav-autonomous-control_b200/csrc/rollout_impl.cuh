@@ -548,6 +548,43 @@ __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_kernel(const __grid
   sliced_body<MC, TABLE, LOG ? 1 : 0, LAG>(p, sch, nullptr);
 }
 
+// One drone per thread at 128 registers, 16 one-warp CTAs per SM: the round-1 kernel, kept for metrics-only rollouts with PER-ROLLOUT
+// missions.  There the warps of an SM sit at different phases (own splines, own obstacle sets, rotor limits in most ticks), the
+// fp64 set-point evaluation is inlined once instead of twice, and four warps per scheduler hide what two cannot: measured 98 ms
+// against 108 ms for the pair kernel on BASELINE configs[3].
+constexpr int kScalarThreads = 32;
+constexpr int kScalarCtasPerSm = 16;
+template <bool MC>
+__global__ void __maxnreg__(kRolloutRegs) rollout_sliced_scalar_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
+  extern __shared__ __align__(128) float s_boxes[];
+  __shared__ int s_item;
+  stage_shared_boxes(p.a, s_boxes);
+  const int n_items = sch.n_groups * sch.n_chunks;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const int it = atomicAdd(sch.counter, 1);
+      if (it < n_items) {
+        const int c = it / sch.n_groups, g = it - c * sch.n_groups;
+        while (ld_acquire_gpu(sch.done + g) < c) __nanosleep(200);
+      }
+      s_item = it;
+    }
+    __syncthreads();
+    const int it = s_item;
+    if (it >= n_items) return;
+    const int c = it / sch.n_groups, g = it - c * sch.n_groups;
+    const long long i = (long long)g * blockDim.x + threadIdx.x;
+    if (i < p.a.B) {
+      const bool last = c == sch.n_chunks - 1;
+      const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
+      drone_slice<float, false, MC, false>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(sch.done + g, c + 1);
+  }
+}
+
 // Metrics + the gated position list of the viewer (PairTrajLog); one-warp CTAs like the metrics-only kernel.
 template <bool MC, bool TABLE, bool LAG>
 __global__ void __maxnreg__(kRolloutPairRegs) rollout_sliced_traj_kernel(const __grid_constant__ RolloutDev<float> p, const SliceSched sch) {
@@ -567,6 +604,7 @@ void launch_rollout_sliced(bool mc, bool table, int grid, size_t smem, cudaStrea
 void launch_rollout_sliced_log(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch,
                                const LogTma* maps);      // maps != nullptr: staged tensor stores
 void launch_rollout_sliced_traj(bool mc, bool table, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
+void launch_rollout_sliced_scalar(bool mc, int grid, size_t smem, cudaStream_t st, const RolloutDev<float>& p, const SliceSched& sch);
 void launch_rollout_f64(bool log, bool mc, int grid, size_t smem, cudaStream_t st, const RolloutDev<double>& p);
 
 }  // namespace uavb

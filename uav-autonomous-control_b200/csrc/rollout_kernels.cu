@@ -114,9 +114,11 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   mc_from_vehicle(mc, a->veh);
   make_vehp<R>(p.vp, a->veh, mc);
   const bool log = a->log_stride > 0;
-  const int threads = sizeof(R) == 8 ? kRolloutThreadsF64 : (log ? kRolloutThreadsLog : kRolloutThreads);
+  // fp32 metrics-only rollouts with per-rollout missions fly one drone per thread (rollout_sliced_scalar_kernel), everything else in fp32 a pair
+  const bool scalar32 = sizeof(R) == 4 && !log && a->traj_out == nullptr && a->mission_seg_begin != nullptr && a->pair_kernel_only == 0;
+  const int threads = sizeof(R) == 8 ? kRolloutThreadsF64 : (log ? kRolloutThreadsLog : (scalar32 ? kScalarThreads : kRolloutThreads));
   // fp32: a thread flies a PAIR of drones (rollout_pair.cuh), so a CTA (= one work group of the slice scheduler) covers 2 x threads
-  const int per_cta = sizeof(R) == 8 ? threads : 2 * threads;
+  const int per_cta = (sizeof(R) == 8 || scalar32) ? threads : 2 * threads;
   const int grid = div_up(a->B, per_cta);
   size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
   p.coeff_cache_offset = -1;
@@ -138,7 +140,7 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     // slice when slicing has nothing to gain; a state log is written slice by slice into its place.  One compiled body for every batch size keeps
     // per-rollout results independent of how a job is sharded (ptxas fuses mul+add differently under different register
     // caps, so differently compiled variants are NOT bit-identical to each other).
-    const int slots = sms * (log ? kRolloutCtasPerSmLog : kRolloutCtasPerSm);
+    const int slots = sms * (log ? kRolloutCtasPerSmLog : (scalar32 ? kScalarCtasPerSm : kRolloutCtasPerSm));
     // ~32 items per resident CTA keep the tail near 3 % of the launch; slices are whole outer periods of >= 100 ticks
     constexpr int kMinChunkTicks = 100;
     long long want = grid > slots ? (32LL * slots + grid - 1) / grid : 1;
@@ -190,6 +192,7 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
       }
     }
     if (log) launch_rollout_sliced_log(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch, tma_log ? &maps : nullptr);
+    else if (scalar32) launch_rollout_sliced_scalar(mc_any, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
     else if (a->traj_out) launch_rollout_sliced_traj(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
     else launch_rollout_sliced(mc_any, from_table, pgrid, smem, st, *reinterpret_cast<RolloutDev<float>*>(&p), sch);
   }

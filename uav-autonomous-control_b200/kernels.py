@@ -443,7 +443,7 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
             log_stride: int = 0, carry: Optional[torch.Tensor] = None, resume: bool = False, want_state: bool = True,
             want_metrics: bool = True, want_carry: bool = False, dtype: torch.dtype = torch.float32, index_base: int = 0, use_targets: bool = True,
             out: Optional[RolloutResult] = None, n_slices: int = 0, log_tma: int = 0, ground_z: Optional[float] = None,
-            traj_max_samples: int = 0, traj_gate_z: float = 0.0, traj_interval: float = 0.05) -> RolloutResult:
+            traj_max_samples: int = 0, traj_gate_z: float = 0.0, traj_interval: float = 0.05, pair_kernel_only: bool = False) -> RolloutResult:
     """n_ticks ticks of `trajectory_controller.step(); simulation.step()` for B drones
     (tests/integration/test_mujoco_trajectory_tracking.py:27-31) in one persistent kernel launch.
 
@@ -465,6 +465,7 @@ def rollout(plan: MissionPlan, B: int, n_ticks: int, *, start: torch.Tensor, goa
     a.index_base = int(index_base)
     a.n_slices = int(n_slices)
     a.log_tma = int(log_tma)
+    a.pair_kernel_only = int(bool(pair_kernel_only))
     if ground_z is not None:
         a.ground_on, a.ground_z = 1, float(ground_z)
     a.veh = vehicle if vehicle is not None else nat.default_vehicle()
