@@ -248,6 +248,15 @@ def test_random_missions_wind_and_obstacle_sets_match_numpy_oracle(cuda):
         checked += 1
     print(f"collision flags: {checked} exact, {ambiguous} inside the {POS_TOL} m ambiguity band")
     assert checked >= 5
+    # the library flew these per-rollout missions one drone per thread; the two-drones-per-thread kernel (pair_kernel_only) flies the
+    # same batch to the same answers (other bits: another formulation of the quaternion map), flags included
+    pair = _fly(cuda, plan, B, n_ticks, start=ground.contiguous(), goal=wp[:, -1].contiguous(), mc_wind=wind,
+                obstacles=torch.tensor(boxes, device=cuda), obstacle_set=sets, pair_kernel_only=True)
+    sane = (res.metrics[:, 5] == 0) & (res.metrics[:, 4] < 5.0) & (pair.metrics[:, 5] == 0)
+    dp = (pair.state[:3] - res.state[:3]).abs().max(dim=0).values[sane]
+    print(f"pair kernel vs one-drone-per-thread kernel: max |dpos| {float(dp.max()):.2e} m over {int(sane.sum())} sane rollouts")
+    assert float(dp.max()) < POS_TOL
+    assert float((pair.metrics[sane, 1] != res.metrics[sane, 1]).float().mean()) < 2e-3      # a flag may flip only within rounding of a box face
 
 
 def test_state_log_layout_and_stride(cuda):
