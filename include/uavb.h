@@ -177,11 +177,20 @@ int uavb_minsnap_pack_f64(const double* coeffs, const double* times, const int* 
  *   seg_coeffs [cap_seg][8][3], seg_times / seg_rows / seg_table / seg_yaw0 [cap_seg]   DEVICE outputs; cap_seg >= the splines
  *                      of the corrected mission (n_tables * UAVB_MAX_SPLINES always suffices)
  *   n_seg_out, rows_out [n_tables] (table rows of every table), status_out [n_tables] (UAVB_SOLVE_*), rounds_out (may be NULL)  HOST
- * SYNCHRONISES `stream`.  n_tables <= 8. */
+ * SYNCHRONISES `stream`, n_tables <= 8 -- unless async_report is given.
+ *
+ * async_report (PINNED host memory, UAVB_PLAN_REPORT_INTS ints, or NULL): the SPECULATIVE form for a caller that plans the same
+ * mission again and again (a Monte-Carlo job) and does not want a host round trip per plan.  The call enqueues the plan as it is
+ * when nothing is hit and returns at once (n_seg_out = the uncorrected spline count, rows_out / status_out untouched); `stream`
+ * later delivers the loop's control block into async_report.  After synchronising with that copy the caller MUST check it:
+ *   async_report[4..7] all zero  (no mission was hit: the plan stands),
+ *   async_report[8 + n_tables + k] == UAVB_SOLVE_OK and async_report[8 + 2 n_tables + k] = table rows of table k.
+ * If a counter is non-zero the segment arrays hold the plan BEFORE correction: plan again without async_report. */
+#define UAVB_PLAN_REPORT_INTS 128     /* the first half is the report, the second half the call's upload image */
 int uavb_plan_shared_f64(int n_tables, const double* const* table_waypoints, const int* table_n_waypoints, const double* table_velocity,
                          double start_end_time_factor, double dt, const double* cuboids, int n_obs, int cap_seg, double* seg_coeffs,
                          double* seg_times, int* seg_rows, int* seg_table, double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out,
-                         int* rounds_out, void* stream);
+                         int* rounds_out, int* async_report, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2  persistent closed-loop rollout, fp32 state in registers, one thread per drone.

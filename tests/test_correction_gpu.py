@@ -157,3 +157,32 @@ def test_fused_planners_fly_the_corrected_mission(cuda, golden):
     r_pr = kernels.rollout(per, B, n_ticks, **kw)
     assert float((r_pr.state[:3].double() - torch.tensor(ref["X"][:3], device=cuda)[:, None]).abs().max()) < 1e-4
     assert torch.equal(r_pr.metrics[:, 1], r_sh.metrics[:1, 1].expand(B))
+
+
+def test_speculative_shared_plan_is_verified_after_the_fact(cuda, golden):
+    """plan_missions(shared=True, obstacles=..., table_rows=N): no host round trip while planning; plan.verify() accepts the plan when
+    the correction loop had nothing to do and the table has N rows, and refuses it otherwise."""
+    import torch
+    from uav_ac_b200 import kernels
+    from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES, LAB_COURSE_WAYPOINTS
+    f64 = dict(dtype=torch.float64, device=cuda)
+    wp, vel, obs = torch.tensor(LAB_COURSE_WAYPOINTS, **f64), torch.tensor([3.0], **f64), torch.tensor(LAB_COURSE_OBSTACLES, **f64)
+    tables = [(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)]
+    sure = kernels.plan_missions(tables, 0.01, shared=True, obstacles=obs)
+    n_rows = int(sure.total_rows.item())
+    assert sure.correction_rounds == 1 and sure.report is None
+    spec = kernels.plan_missions(tables, 0.01, shared=True, obstacles=obs, table_rows=n_rows)
+    assert spec.report is not None
+    spec.verify()
+    assert spec.report is None and spec.status.tolist() == [0, 0]
+    for name in ("seg_coeffs", "seg_rows", "seg_table", "seg_yaw0", "times", "targets"):
+        assert torch.equal(getattr(spec, name), getattr(sure, name)), name
+    with pytest.raises(RuntimeError, match="table rows"):
+        kernels.plan_missions(tables, 0.01, shared=True, obstacles=obs, table_rows=n_rows + 1).verify()
+    # the reference's corrected scenario: the loop inserts midpoints, so a speculative plan must be refused
+    g = golden["planning"]
+    course = torch.tensor(g["fix_waypoints_in"], **f64)
+    boxes = torch.tensor(g["fix_obstacles"], **f64)
+    v15 = torch.tensor([1.5], **f64)
+    with pytest.raises(RuntimeError, match="inside a box"):
+        kernels.plan_missions([(course[None].contiguous(), v15)], 0.01, shared=True, obstacles=boxes, table_rows=500).verify()

@@ -23,6 +23,7 @@ STATE_DIM = 13
 MAX_SPLINES = 64
 SOLVE_OK, SOLVE_DEGENERATE, SOLVE_NONFINITE, SOLVE_TOO_MANY = range(4)
 TARGET_ROW_BYTES = 56
+PLAN_REPORT_INTS = 128
 GAIN_NAMES = ("kp_xy", "kd_xy", "kp_z", "kd_z", "ki_z", "kp_roll", "kp_pitch", "kp_yaw", "kp_p", "kp_q", "kp_r")
 M_FINAL_DIST, M_COLLISION, M_RMSE, M_MEAN_ERR, M_MAX_ERR, M_STATUS, M_FIRST_HIT, M_PERIODS = range(8)
 (STAGE_OUTER, STAGE_INNER, STAGE_PHYSICS, STAGE_ALTITUDE, STAGE_LATERAL, STAGE_ROLL_PITCH, STAGE_YAW, STAGE_BODY_RATE, STAGE_ALLOCATE,
@@ -121,7 +122,7 @@ def lib() -> ctypes.CDLL:
     L.uavb_minsnap_pack_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.uavb_minsnap_constraints_f64.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.uavb_plan_shared_f64.argtypes = [c_int, POINTER(c_void_p), POINTER(c_int), c_void_p, c_double, c_double, c_void_p, c_int, c_int, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p]
+                                       c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_void_p, c_void_p]
     L.uavb_rollout_targets_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_void_p, c_int, c_void_p]
     L.uavb_rollout_f32.argtypes = [POINTER(RolloutArgs), c_void_p]
     L.uavb_rollout_f64.argtypes = [POINTER(RolloutArgs), c_void_p]

@@ -249,6 +249,7 @@ int correct_missions(double* waypoints, int* n_waypoints, const double* velocity
       if (e == cudaSuccess && !result) {
         if (ctrl) {                                       // the whole control block (counters + the caller's words) in one copy
           e = cudaMemcpyAsync(ctrl->host, ctrl->dev, sizeof(int) * ctrl->ints, cudaMemcpyDeviceToHost, st);
+          if (ctrl->no_wait) break;                       // the caller reads the block later (speculative plan: round 1 only)
           if (e == cudaSuccess) e = cudaStreamSynchronize(st);
           for (int k = 0; k < kBuckets; ++k) host_counts[k] = ctrl->host[(cur ^ 1) * kBuckets + k];
         } else {
@@ -285,7 +286,7 @@ __global__ void shared_seg_flags_kernel(const int* __restrict__ offs, const doub
 // loop, packed into the segment arrays of a shared-mission rollout.  ONE host synchronisation when nothing is hit.
 int plan_shared_tables(int T, const double* const* d_waypoints, const int* n_wp_in, const double* d_velocity, double factor, double dt,
                        const double* d_cuboids, int n_obs, int cap_seg, double* seg_coeffs, double* seg_times, int* seg_rows, int* seg_table,
-                       double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out, int* rounds_out, cudaStream_t st) {
+                       double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out, int* rounds_out, cudaStream_t st, int* async_report) {
   constexpr int kMaxWp = UAVB_MAX_SPLINES + 1;
   int n_seg0 = 0;
   for (int k = 0; k < T; ++k) {
@@ -311,7 +312,8 @@ int plan_shared_tables(int T, const double* const* d_waypoints, const int* n_wp_
     double* d_yaw0 = reinterpret_cast<double*>(blob + b_fixed + b_cf + b_tf);
     int* d_ctrl = reinterpret_cast<int*>(blob + b_fixed + b_cf + b_tf + b_yaw);
     int* d_n_wp = d_ctrl + o_nwp; int* d_status = d_ctrl + o_status; int* d_total = d_ctrl + o_total; int* d_offs = d_ctrl + o_offs;
-    int* up = host + n_ints;
+    // the upload image must outlive the asynchronous copy that reads it: in the speculative form it lives in the caller's block
+    int* up = async_report ? async_report + UAVB_PLAN_REPORT_INTS / 2 : host + n_ints;
     for (int i = 0; i < n_ints; ++i) up[i] = 0;
     up[o_offs] = 0;
     for (int k = 0; k < T; ++k) { up[o_nwp + k] = n_wp_in[k]; up[o_offs + k + 1] = up[o_offs + k] + n_wp_in[k] - 1; }
@@ -328,10 +330,15 @@ int plan_shared_tables(int T, const double* const* d_waypoints, const int* n_wp_
       return UAVB_OK;
     };
     const std::function<int()> speculative = [&]() { return tail(n_seg0); };
-    const CtrlBlock ctrl{d_ctrl, host, n_ints};
+    const CtrlBlock ctrl{d_ctrl, async_report ? async_report : host, n_ints, async_report != nullptr};
     int rounds = 0, n_seg = n_seg0;
     result = correct_missions(d_fixed, d_n_wp, d_velocity, T, kMaxWp, factor, dt, d_cuboids, n_obs, 0, d_cf, d_tf, d_status, &rounds, st, &speculative, n_wp_in,
                               &ctrl);
+    if (async_report) {                                     // speculative: nothing was waited for; the caller checks the report later
+      *n_seg_out = n_seg0;
+      if (rounds_out) *rounds_out = 1;
+      return result;
+    }
     if (!result && rounds > 1) {                            // midpoints were inserted: lay the mission out again
       n_seg = 0;
       for (int k = 0; k < T; ++k) { up[o_offs + k] = n_seg; n_seg += host[o_nwp + k] - 1; }
@@ -388,13 +395,14 @@ extern "C" int uavb_minsnap_pack_f64(const double* coeffs, const double* times, 
 extern "C" int uavb_plan_shared_f64(int n_tables, const double* const* table_waypoints, const int* table_n_waypoints, const double* table_velocity,
                                     double factor, double dt, const double* cuboids, int n_obs, int cap_seg, double* seg_coeffs, double* seg_times,
                                     int* seg_rows, int* seg_table, double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out, int* rounds_out,
-                                    void* stream) {
-  UAVB_REQUIRE(table_waypoints && table_n_waypoints && table_velocity && seg_coeffs && seg_times && seg_rows && seg_table && seg_yaw0 && n_seg_out &&
-                   rows_out && status_out, "plan_shared: NULL pointer");
+                                    int* async_report, void* stream) {
+  UAVB_REQUIRE(table_waypoints && table_n_waypoints && table_velocity && seg_coeffs && seg_times && seg_rows && seg_table && seg_yaw0 && n_seg_out,
+               "plan_shared: NULL pointer");
+  UAVB_REQUIRE(async_report != nullptr || (rows_out && status_out), "plan_shared: rows_out and status_out are required unless async_report is given");
   UAVB_REQUIRE(n_tables >= 1 && n_tables <= kMaxSharedTables, "plan_shared: 1 .. 8 tables");
   UAVB_REQUIRE(dt > 0.0 && n_obs >= 0 && (n_obs == 0 || cuboids != nullptr), "plan_shared: dt > 0; n_obs > 0 needs cuboids");
   int rc = require_device();
   if (rc) return rc;
   return plan_shared_tables(n_tables, table_waypoints, table_n_waypoints, table_velocity, factor, dt, cuboids, n_obs, cap_seg, seg_coeffs, seg_times,
-                            seg_rows, seg_table, seg_yaw0, n_seg_out, rows_out, status_out, rounds_out, static_cast<cudaStream_t>(stream));
+                            seg_rows, seg_table, seg_yaw0, n_seg_out, rows_out, status_out, rounds_out, static_cast<cudaStream_t>(stream), async_report);
 }

@@ -76,6 +76,7 @@ struct CtrlBlock {
   int* dev;
   int* host;
   int ints;
+  bool no_wait;       // enqueue round 1 and the copy of the block, do not synchronise (speculative plan)
 };
 int correct_missions(double* waypoints, int* n_waypoints, const double* velocity, int B, int max_wp, double factor, double dt, const double* cuboids,
                      int n_obs, long long cuboid_stride, double* coeffs_out, double* times_out, int* status_out, int* rounds_out, cudaStream_t st,
@@ -85,7 +86,7 @@ int correct_missions(double* waypoints, int* n_waypoints, const double* velocity
 constexpr int kMaxSharedTables = 8;
 int plan_shared_tables(int T, const double* const* d_waypoints, const int* n_wp_in, const double* d_velocity, double factor, double dt,
                        const double* d_cuboids, int n_obs, int cap_seg, double* seg_coeffs, double* seg_times, int* seg_rows, int* seg_table,
-                       double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out, int* rounds_out, cudaStream_t st);
+                       double* seg_yaw0, int* n_seg_out, int* rows_out, int* status_out, int* rounds_out, cudaStream_t st, int* async_report = nullptr);
 
 // SM count of the current device, cached per device (thread-safe).
 int sm_count_cached(int* sms);

@@ -232,6 +232,26 @@ class MissionPlan:
     targets: Optional[torch.Tensor] = None     # shared missions: [n_rows, 56] u8 per-row set-points (uavb_rollout_targets_f64)
     status: Optional[torch.Tensor] = None      # shared missions: [n_tables] i32 UAVB_SOLVE_* of each table
     correction_rounds: int = 0                 # plan rounds of the obstacle-correction loop (1 = nothing was hit; 0 = not run)
+    report: Optional[torch.Tensor] = None      # speculative shared plan: the pinned control block the correction loop reports into
+    report_tables: int = 0
+    report_event: Optional[object] = None
+
+    def verify(self) -> None:
+        """Speculative shared plans (plan_missions(..., shared=True, obstacles=..., table_rows=...)): wait for the loop's report and
+        raise if the plan that was flown is not the one the reference would have produced.  A no-op for every other plan."""
+        if self.report is None:
+            return
+        self.report_event.synchronize()
+        r, T = self.report.tolist(), self.report_tables
+        if any(r[4:8]):
+            raise RuntimeError("speculative plan: the obstacle-correction loop found a sampled point inside a box; plan again without table_rows")
+        status, rows = r[8 + T:8 + 2 * T], r[8 + 2 * T:8 + 3 * T]
+        if any(status):
+            raise RuntimeError(f"speculative plan: solver status {status}")
+        if sum(rows) != int(self.rows_per_mission.sum()):
+            raise RuntimeError(f"speculative plan: the mission has {sum(rows)} table rows, table_rows said {int(self.rows_per_mission.sum())}")
+        self.status = torch.tensor(status, dtype=torch.int32)
+        self.report = None
 
     @property
     def shared(self) -> bool:
@@ -337,9 +357,27 @@ def _plan_corrected(tables, dt: float, factor: float, obstacles: torch.Tensor) -
     return plan
 
 
+_REPORTS: dict = {}
+
+
+def _report_block(dev) -> torch.Tensor:
+    """One [PLAN_REPORT_INTS] row of a pinned ring (1024 rows per device) for a speculative plan's report."""
+    ring = _REPORTS.get(dev)
+    if ring is None:
+        ring = _REPORTS[dev] = [torch.zeros((1024, nat.PLAN_REPORT_INTS), dtype=torch.int32).pin_memory(), 0]
+    row = ring[0][ring[1] % 1024]
+    ring[1] += 1
+    return row
+
+
 def _plan_shared_corrected(tables, dt: float, factor: float, table_rows: Optional[int], obstacles: torch.Tensor) -> MissionPlan:
     """uavb_plan_shared_f64: the tables of one mission through the correction loop into the packed segment arrays, one C call
-    (a handful of launches, one synchronisation when nothing is hit), then the set-point table."""
+    (a handful of launches, one synchronisation when nothing is hit), then the set-point table.
+
+    With ``table_rows`` (the caller has planned this mission before and knows its table length) the plan is SPECULATIVE: nothing is
+    waited for, the kernels of the uncorrected plan are enqueued and the loop's report arrives in pinned memory behind them.
+    ``plan.verify()`` -- after the results of the flight have been synchronised -- raises if the correction loop would have inserted
+    a midpoint or the table length differs; a Monte-Carlo job that plans the same mission for every batch pays no host round trip."""
     dev = tables[0][0].device
     T = len(tables)
     for wp, vel in tables:
@@ -357,18 +395,29 @@ def _plan_shared_corrected(tables, dt: float, factor: float, table_rows: Optiona
     vels = torch.cat([vel for _, vel in tables]).contiguous() if T > 1 else tables[0][1]
     n_seg, rounds = ctypes.c_int(0), ctypes.c_int(0)
     tab_rows, status = (ctypes.c_int * T)(), (ctypes.c_int * T)()
-    nat.check(nat.lib().uavb_plan_shared_f64(T, ptrs, n_wp, nat.ptr(vels, torch.float64, "velocity"), float(factor), float(dt), nat.ptr(obs), int(obs.shape[0]), cap, nat.ptr(coeffs),
-                                             nat.ptr(times), nat.ptr(rows), nat.ptr(seg_table), nat.ptr(seg_yaw0), ctypes.byref(n_seg), tab_rows, status,
-                                             ctypes.byref(rounds), nat.stream_ptr(dev)), "uavb_plan_shared_f64")
-    if any(st == nat.SOLVE_TOO_MANY for st in status):
-        raise TooManySplines(f"obstacle correction needs more than {nat.MAX_SPLINES} splines in one table -- an obstacle probably contains a waypoint "
-                             "(the reference loops forever in this case)")
+    report = _report_block(dev) if table_rows is not None else None
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().uavb_plan_shared_f64(T, ptrs, n_wp, nat.ptr(vels, torch.float64, "velocity"), float(factor), float(dt), nat.ptr(obs),
+                                                 int(obs.shape[0]), cap, nat.ptr(coeffs), nat.ptr(times), nat.ptr(rows), nat.ptr(seg_table),
+                                                 nat.ptr(seg_yaw0), ctypes.byref(n_seg), tab_rows, status, ctypes.byref(rounds),
+                                                 ctypes.c_void_p(report.data_ptr()) if report is not None else None, nat.stream_ptr(dev)),
+                  "uavb_plan_shared_f64")
     n = n_seg.value
-    total = sum(tab_rows)
     plan = MissionPlan(coeffs[:n], rows[:n], seg_table[:n], seg_yaw0[:n], float(dt), times=times[:n], n_seg_shared=n)
-    plan.status = torch.tensor(list(status), dtype=torch.int32)             # host tensors: the C call already brought them back
+    if report is not None:
+        total = int(table_rows)
+        plan.report, plan.report_tables = report, T
+        plan.report_event = torch.cuda.Event()
+        plan.report_event.record(torch.cuda.current_stream(dev))
+        plan.correction_rounds = 1
+    else:
+        if any(st == nat.SOLVE_TOO_MANY for st in status):
+            raise TooManySplines(f"obstacle correction needs more than {nat.MAX_SPLINES} splines in one table -- an obstacle probably contains a "
+                                 "waypoint (the reference loops forever in this case)")
+        total = sum(tab_rows)
+        plan.status = torch.tensor(list(status), dtype=torch.int32)             # host tensors: the C call already brought them back
+        plan.correction_rounds = rounds.value
     plan.rows_per_mission = torch.tensor([total], dtype=torch.int32)
-    plan.correction_rounds = rounds.value
     plan.targets = rollout_targets(plan, total)
     return plan
 
