@@ -100,6 +100,22 @@ def test_argument_validation_and_no_cpu_path(nat):
     s = nat.StageArgs()
     s.B, s.stage = 1, 99
     assert L.uavb_stage_f32(ctypes.byref(s), null) == -1
+    # round-2 entry points: the correction loop, the shared planner, the constraint system
+    assert L.uavb_minsnap_correct_f64(one, one, one, 1, 66, 1.5, 0.01, null, 0, 0, one, one, one, None, null) == -1      # max_wp > UAVB_MAX_SPLINES + 1
+    assert b"max_wp" in L.uavb_last_error()
+    assert L.uavb_minsnap_correct_f64(one, one, one, 1, 6, 1.5, 0.01, null, 2, 0, one, one, one, None, null) == -1       # n_obs > 0 without cuboids
+    assert L.uavb_minsnap_correct_f64(one, one, one, 1, 6, 1.5, 0.0, null, 0, 0, one, one, one, None, null) == -1        # dt <= 0
+    assert L.uavb_minsnap_correct_f64(one, one, one, 1, 6, 1.5, 0.01, one, 2, 6, one, one, one, None, null) == -1        # cuboid_stride < 6 n_obs
+    assert L.uavb_minsnap_constraints_f64(one, one, 1, 0, one, one, null) == -1
+    n_seg = ctypes.c_int()
+    assert L.uavb_plan_shared_f64(0, None, None, one, 1.5, 0.01, null, 0, 8, one, one, one, one, one, ctypes.byref(n_seg), None, None, None, None, null) == -1
+    a = nat.RolloutArgs()
+    a.B, a.n_ticks, a.inner_per_outer, a.n_seg_shared, a.dt_outer, a.log_stride = 4, 10, 10, 1, 0.01, 1
+    a.veh = nat.default_vehicle()
+    for f in ("seg_coeffs", "seg_rows", "seg_table", "seg_yaw0", "start", "log_out", "traj_out"):
+        setattr(a, f, one)
+    a.traj_max_samples = 4
+    assert L.uavb_rollout_f32(ctypes.byref(a), null) == -1 and b"traj_out" in L.uavb_last_error()                # flown-path list together with a state log
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is visible: the ENODEVICE leg only applies to GPU-less hosts")
     assert L.uavb_device_count() == 0
