@@ -133,28 +133,33 @@ __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_kernel(
 #ifndef UAVB_K1_STREAM_CTAS
 #define UAVB_K1_STREAM_CTAS 4
 #endif
+#ifndef UAVB_K1_STREAM_THREADS
+#define UAVB_K1_STREAM_THREADS 64
+#endif
 constexpr int kStreamCtasPerSm = UAVB_K1_STREAM_CTAS;
+constexpr int kStreamThreads = UAVB_K1_STREAM_THREADS;       // missions per tile
+constexpr int kStreamSubTileBytes = kStreamThreads * 128;
 template <int MAXS, int MINB>
-__global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_stream_kernel(
+__global__ void __launch_bounds__(kStreamThreads, MINB) minsnap_solve_stream_kernel(
     const double* __restrict__ waypoints, const double* __restrict__ velocity, int B, int S, double factor, double* __restrict__ times_out,
     int* __restrict__ status_out, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ double s_out[];
   __shared__ uint64_t s_bar;
   char* tiles = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(s_out) + 1023) & ~(uintptr_t)1023);
-  double* s_wp = reinterpret_cast<double*>(tiles + 3 * kTmaSubTileBytes);       // [64][3 (S+1)]
+  double* s_wp = reinterpret_cast<double*>(tiles + 3 * kStreamSubTileBytes);       // [64][3 (S+1)]
   const int wpd = 3 * (S + 1);
-  double* s_vel = s_wp + kSolveThreads * wpd;                                   // [64]
+  double* s_vel = s_wp + kStreamThreads * wpd;                                   // [64]
   char* row = tiles + threadIdx.x * 128;
   const unsigned sw = (threadIdx.x & 7u) << 4;
-  const int n_tiles = (B + kSolveThreads - 1) / kSolveThreads;
+  const int n_tiles = (B + kStreamThreads - 1) / kStreamThreads;
   // the input of tile t: one bulk copy per array when the tile is whole, a cooperative copy for the ragged last tile (a bulk copy
   // needs a multiple of 16 bytes, 64 missions always are)
   auto prefetch = [&](int tile) {                         // thread 0
-    if ((long long)(tile + 1) * kSolveThreads > B) return;
-    const uint32_t wp_bytes = (uint32_t)(kSolveThreads * wpd * 8), vel_bytes = kSolveThreads * 8;
+    if ((long long)(tile + 1) * kStreamThreads > B) return;
+    const uint32_t wp_bytes = (uint32_t)(kStreamThreads * wpd * 8), vel_bytes = kStreamThreads * 8;
     mbar_expect_tx(&s_bar, wp_bytes + vel_bytes);
-    bulk_load_1d(s_wp, waypoints + (size_t)tile * kSolveThreads * wpd, wp_bytes, &s_bar);
-    bulk_load_1d(s_vel, velocity + (size_t)tile * kSolveThreads, vel_bytes, &s_bar);
+    bulk_load_1d(s_wp, waypoints + (size_t)tile * kStreamThreads * wpd, wp_bytes, &s_bar);
+    bulk_load_1d(s_vel, velocity + (size_t)tile * kStreamThreads, vel_bytes, &s_bar);
   };
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
@@ -163,14 +168,14 @@ __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_stream_kern
   __syncthreads();
   unsigned phase = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long base = (long long)tile * kSolveThreads;
-    const int n_here = (int)((B - base) < kSolveThreads ? (B - base) : kSolveThreads);
+    const long long base = (long long)tile * kStreamThreads;
+    const int n_here = (int)((B - base) < kStreamThreads ? (B - base) : kStreamThreads);
     const bool live = (int)threadIdx.x < n_here;
-    if (n_here == kSolveThreads) {
+    if (n_here == kStreamThreads) {
       mbar_wait(&s_bar, phase);
       phase ^= 1u;
     } else {                                              // ragged last tile (the last iteration of one CTA)
-      for (int e = threadIdx.x; e < n_here * wpd; e += kSolveThreads) s_wp[e] = __ldg(waypoints + (size_t)base * wpd + e);
+      for (int e = threadIdx.x; e < n_here * wpd; e += kStreamThreads) s_wp[e] = __ldg(waypoints + (size_t)base * wpd + e);
       if (live) s_vel[threadIdx.x] = __ldg(velocity + base + threadIdx.x);
       __syncthreads();
     }
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_stream_kern
         S, vel, factor, [&wreg](int i, int ax) { return wreg[3 * i + ax]; },
         [row, sw](int seg, int j, int ax, double val) {
           const int off = (seg & 1) * 24 + j * 3 + ax, q = off >> 4, d = off & 15;
-          *reinterpret_cast<double*>(row + q * kTmaSubTileBytes + ((((unsigned)d >> 1) << 4) ^ sw) + (d & 1) * 8) = val;
+          *reinterpret_cast<double*>(row + q * kStreamSubTileBytes + ((((unsigned)d >> 1) << 4) ^ sw) + (d & 1) * 8) = val;
         },
         [tout, live](int seg, double t) { if (live) tout[seg] = t; },
         [&](int seg) {
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(kSolveThreads, MINB) minsnap_solve_stream_kern
           fence_proxy_async_smem();
           __syncthreads();
           if (threadIdx.x == 0) {
-            for (int q = 0; q < n_sub; ++q) tensor_store_2d(&tmap, first * 24 + q * 16, (int)base, tiles + q * kTmaSubTileBytes);
+            for (int q = 0; q < n_sub; ++q) tensor_store_2d(&tmap, first * 24 + q * 16, (int)base, tiles + q * kStreamSubTileBytes);
             bulk_commit();
             if (!last) bulk_wait_read<0>();               // the next pair of splines overwrites the tile right away; after the last
           }                                               // flush the wait moves to the next tile's barrier (a whole solve later)
@@ -625,10 +630,17 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
     int sms = 0;
     rc = sm_count_cached(&sms);
     if (rc) return rc;
-    const size_t smem = (size_t)3 * kTmaSubTileBytes + 1024 + sizeof(double) * kSolveThreads * (3 * (S + 1) + 1);
-    const int n_tiles = div_up(B, kSolveThreads);
+    const size_t smem = (size_t)3 * kStreamSubTileBytes + 1024 + sizeof(double) * kStreamThreads * (3 * (S + 1) + 1);
+    const int n_tiles = div_up(B, kStreamThreads);
+    CUtensorMap tms;
+    if (kStreamThreads != kSolveThreads) {                 // the streaming kernel's tile has its own box height
+      if (!make_tensor_map_2d(&tms, coeffs_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 24ull * S, (unsigned long long)B, 192ull * S, 16, kStreamThreads,
+                              CU_TENSOR_MAP_SWIZZLE_128B))
+        return set_error(UAVB_ECUDA, "minsnap_solve: tensor map");
+      tm = tms;
+    }
     const int grid = n_tiles < kStreamCtasPerSm * sms ? n_tiles : kStreamCtasPerSm * sms;
-    minsnap_solve_stream_kernel<4, kStreamCtasPerSm><<<grid, kSolveThreads, smem, st>>>(waypoints, velocity, B, S, factor, times_out, status_out, tm);
+    minsnap_solve_stream_kernel<4, kStreamCtasPerSm><<<grid, kStreamThreads, smem, st>>>(waypoints, velocity, B, S, factor, times_out, status_out, tm);
     UAVB_CUDA_OK(cudaGetLastError());
     return UAVB_OK;
   }
