@@ -41,7 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_TICK = 269          # algorithmic flop per drone tick with 4 AABBs: 239 in the 1 kHz body + 298/10 from the 100 Hz loop (DESIGN.md "K2 work per tick")
-K2_DRAM_BYTES_PER_LAUNCH = 9.8e6    # ncu: 6.2 MB read + 3.6 MB written per launch of the bench workload (metrics-only: ~0 B per tick; profiles/r02_ncu_rollout_v13.md)
+K2_DRAM_BYTES_PER_LAUNCH = 9.3e6    # ncu: 6.2 MB read + 3.0 MB written per launch of the bench workload (metrics-only: ~0 B per tick; profiles/r02_ncu_rollout_final.md)
 LOG_BYTES_PER_TICK = 52      # 13 fp32 state words
 ROLLOUTS_PER_GPU = 100_000   # BASELINE configs[2]
 VELOCITY = 3.0               # config.ini:7
@@ -487,7 +487,7 @@ def run_b200(args):
                     "call": "uavb_fly_mission_host (C ABI, pinned host buffers, synchronous); host wall-clock, max over ranks"},
             "gpu_launches": 6 * args.steps,        # own kernels per step: 2x minsnap_solve, table_meta, target_rows + target_heading, rollout_sliced (torch glue not counted)
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                         "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_rollout_v13.md)",
+                         "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_rollout_final.md)",
                          "kernel": "rollout_sliced_kernel<MC,TABLE> (two drones per thread, packed fp32x2)", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,
                          "peak_source": "uavb_measure_fma_rates in this run (MEASURED_PEAKS.json carries no fp32 figure)",
                          "peak_three_operand": fp32_peak3, "frac_of_three_operand_peak": achieved / fp32_peak3 if fp32_peak3 else None,
