@@ -12,7 +12,13 @@
 #include "rollout_core.cuh"
 #include "tma.cuh"
 
+#ifndef UAVB_TICK_UNROLL
+#define UAVB_TICK_UNROLL 2
+#endif
+
 namespace uavb {
+
+constexpr int kTickUnroll = UAVB_TICK_UNROLL;
 
 // [sample][13][B] state log of a pair: drones 2j, 2j+1 are neighbours in every field row, so a field leaves as ONE 8-byte
 // streaming store per thread when the rows are 8-byte aligned (B even) -- a warp writes 256 contiguous bytes per field.
@@ -244,7 +250,7 @@ UAVB_DEV void rollout_run_pair(Drone2& d, Cursor<float> (&c)[2], Accum<float> (&
       // only where the instruction footprint allows it: the watching bodies carry the per-tick box tests, and kernels that
       // evaluate the set-points on the fly carry two inlined fp64 evaluations per period -- unrolled, BASELINE configs[3]
       // waits for instruction fetches and runs 10 % slower (measured)
-#pragma unroll((kWatch || !TABLE) ? 1 : 2)
+#pragma unroll((kWatch || !TABLE) ? 1 : kTickUnroll)
       for (int j = 0; j < n; ++j) {
         inner_tick_pair<LOG::kNormEveryTick, LAG>(d, u, v2);
         if constexpr (kWatch) {
