@@ -485,7 +485,9 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(mc_host.numel() * 4 + wp_host.numel() * 8 + 8),
                     "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                     "call": "uavb_fly_mission_host (C ABI, pinned host buffers, synchronous); host wall-clock, max over ranks"},
-            "gpu_launches": 6 * args.steps,        # own kernels per step: 2x minsnap_solve, table_meta, target_rows + target_heading, rollout_sliced (torch glue not counted)
+            # own kernels per step (torch glue not counted): correct_classify, minsnap_solve_list x2 (take-off: <= 4 splines, course: <= 8),
+            # correct_sweep x2, minsnap_pack, table_meta, shared_seg_flags, target_rows, target_heading, rollout_sliced
+            "gpu_launches": 11 * args.steps,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_rollout_final.md)",
                          "kernel": "rollout_sliced_kernel<MC,TABLE> (two drones per thread, packed fp32x2)", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,
