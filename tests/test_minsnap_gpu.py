@@ -250,3 +250,28 @@ def test_fma_rate_probe_reports_the_three_operand_ceiling(cuda):
     fp32, fp32_3, fp64 = nat.measure_fma_rates(0)
     assert 30.0 < fp32 < 90.0 and 10.0 < fp64 < 50.0
     assert 0.55 * fp32 < fp32_3 < 0.8 * fp32
+
+
+def test_sampled_table_tiles_for_any_8_byte_aligned_output(cuda, golden):
+    """K3 sends its 32 x 11 tiles with bulk copies that need 16-byte alignment; rows are 88 bytes, so alignment depends on the parity of
+    (output address / 8 + first row of the mission).  The same batch written at an output shifted by 8 bytes must come out identical
+    (ragged row counts: missions start on odd and even rows in both placements)."""
+    import ctypes
+    import torch
+    from uav_ac_b200 import _native as nat, kernels
+    g = golden["planning"]
+    wps, vels = g["c2_waypoints"][:24], g["c2_velocity"][:24]
+    B, S = wps.shape[0], wps.shape[1] - 1
+    c, t, _ = kernels.minsnap_solve(torch.tensor(wps, device=cuda), torch.tensor(vels, device=cuda))
+    offs = torch.arange(B + 1, dtype=torch.int32, device=cuda) * S
+    rows, yaw0, total = kernels.table_meta(c, t.reshape(-1), offs, 0.01)
+    roff = torch.zeros(B + 1, dtype=torch.int32, device=cuda)
+    roff[1:] = torch.cumsum(total, 0)
+    n = int(roff[-1])
+    ref = kernels.minsnap_sample(c, t.reshape(-1), offs, rows, roff, 0.01)
+    buf = torch.full((n * 11 + 1,), float("nan"), dtype=torch.float64, device=cuda)
+    nat.check(nat.lib().uavb_minsnap_sample_f64(nat.ptr(c), nat.ptr(t), nat.ptr(offs), nat.ptr(rows), nat.ptr(roff), B, 0.01,
+                                                ctypes.c_void_p(buf.data_ptr() + 8), nat.stream_ptr(cuda)), "uavb_minsnap_sample_f64")
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(buf[0])) and torch.equal(buf[1:].reshape(n, 11), ref)
+    assert len({int(r) & 1 for r in roff[:-1].tolist()}) == 2

@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const d
   const int s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
   const long long row0 = row_offsets[b];
   const int N = (int)(row_offsets[b + 1] - row0);
-  const int head = (int)(row0 & 1);                        // rows before the first 16-byte aligned one (base is a multiple of 32)
+  // rows before the first 16-byte aligned one: a row is 11 doubles, so the parity of (table address / 8 + first row) decides
+  const int head = (int)(((reinterpret_cast<uintptr_t>(table) >> 3) + (unsigned long long)row0) & 1ull);
   int buf = 0;
 
   // segment cursor shared by the warp: segment `cs` starts at mission row `cf`

@@ -235,12 +235,16 @@ class MissionPlan:
     report: Optional[torch.Tensor] = None      # speculative shared plan: the pinned control block the correction loop reports into
     report_tables: int = 0
     report_event: Optional[object] = None
+    report_ticket: Optional[tuple] = None
 
     def verify(self) -> None:
         """Speculative shared plans (plan_missions(..., shared=True, obstacles=..., table_rows=...)): wait for the loop's report and
         raise if the plan that was flown is not the one the reference would have produced.  A no-op for every other plan."""
         if self.report is None:
             return
+        dev, ticket = self.report_ticket
+        if _REPORTS[dev][1] - ticket > _REPORT_RING:
+            raise RuntimeError(f"speculative plan: its report block has been handed out again ({_REPORT_RING} plans later); call verify() sooner")
         self.report_event.synchronize()
         r, T = self.report.tolist(), self.report_tables
         if any(r[4:8]):
@@ -360,14 +364,18 @@ def _plan_corrected(tables, dt: float, factor: float, obstacles: torch.Tensor) -
 _REPORTS: dict = {}
 
 
-def _report_block(dev) -> torch.Tensor:
-    """One [PLAN_REPORT_INTS] row of a pinned ring (1024 rows per device) for a speculative plan's report."""
+_REPORT_RING = 1024
+
+
+def _report_block(dev):
+    """One [PLAN_REPORT_INTS] row of a pinned ring (_REPORT_RING rows per device) for a speculative plan's report, and its ticket
+    (the row is handed out again _REPORT_RING plans later: verify() refuses a plan whose row has been reused)."""
     ring = _REPORTS.get(dev)
     if ring is None:
-        ring = _REPORTS[dev] = [torch.zeros((1024, nat.PLAN_REPORT_INTS), dtype=torch.int32).pin_memory(), 0]
-    row = ring[0][ring[1] % 1024]
+        ring = _REPORTS[dev] = [torch.zeros((_REPORT_RING, nat.PLAN_REPORT_INTS), dtype=torch.int32).pin_memory(), 0]
+    ticket = ring[1]
     ring[1] += 1
-    return row
+    return ring[0][ticket % _REPORT_RING], (dev, ticket)
 
 
 def _plan_shared_corrected(tables, dt: float, factor: float, table_rows: Optional[int], obstacles: torch.Tensor) -> MissionPlan:
@@ -395,7 +403,7 @@ def _plan_shared_corrected(tables, dt: float, factor: float, table_rows: Optiona
     vels = torch.cat([vel for _, vel in tables]).contiguous() if T > 1 else tables[0][1]
     n_seg, rounds = ctypes.c_int(0), ctypes.c_int(0)
     tab_rows, status = (ctypes.c_int * T)(), (ctypes.c_int * T)()
-    report = _report_block(dev) if table_rows is not None else None
+    report, ticket = _report_block(dev) if table_rows is not None else (None, None)
     with torch.cuda.device(dev):
         nat.check(nat.lib().uavb_plan_shared_f64(T, ptrs, n_wp, nat.ptr(vels, torch.float64, "velocity"), float(factor), float(dt), nat.ptr(obs),
                                                  int(obs.shape[0]), cap, nat.ptr(coeffs), nat.ptr(times), nat.ptr(rows), nat.ptr(seg_table),
@@ -406,7 +414,7 @@ def _plan_shared_corrected(tables, dt: float, factor: float, table_rows: Optiona
     plan = MissionPlan(coeffs[:n], rows[:n], seg_table[:n], seg_yaw0[:n], float(dt), times=times[:n], n_seg_shared=n)
     if report is not None:
         total = int(table_rows)
-        plan.report, plan.report_tables = report, T
+        plan.report, plan.report_tables, plan.report_ticket = report, T, ticket
         plan.report_event = torch.cuda.Event()
         plan.report_event.record(torch.cuda.current_stream(dev))
         plan.correction_rounds = 1
