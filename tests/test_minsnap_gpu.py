@@ -275,3 +275,29 @@ def test_sampled_table_tiles_for_any_8_byte_aligned_output(cuda, golden):
     torch.cuda.synchronize()
     assert bool(torch.isnan(buf[0])) and torch.equal(buf[1:].reshape(n, 11), ref)
     assert len({int(r) & 1 for r in roff[:-1].tolist()}) == 2
+
+
+def test_row_heading_atan2_is_accurate_to_a_few_ulps(cuda):
+    """The table kernels' own fp64 atan2 (constant-bank polynomial, one reciprocal) against np.arctan2 over all octants, magnitudes
+    from the validity threshold to 1e3 m/s, and the octant / quadrant boundaries."""
+    import torch
+    from uav_ac_b200 import _native as nat
+    rng = np.random.default_rng(4)
+    n = 400_000
+    ang = rng.uniform(-np.pi, np.pi, n)
+    mag = 10.0 ** rng.uniform(-2.9, 3.0, n)
+    v = np.stack((mag * np.cos(ang), mag * np.sin(ang), rng.normal(size=n)), axis=1)
+    special = np.array([[1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, -1, 0], [1, 1, 0], [-1, 1, 0], [-1, -1, 0], [1, -1, 0], [2, 1, 0], [1, 2, 0],
+                        [1, 0.5, 0], [0.5, 1, 0], [-1, 1e-9, 0], [-1, -1e-9, 0], [1e-3, 0, 0], [3, 4e-300, 0]], dtype=float)
+    v = np.vstack((special, v))
+    vt = torch.tensor(v, dtype=torch.float64, device=cuda)
+    out = torch.empty(len(v), dtype=torch.float64, device=cuda)
+    # one sequence per row: no unwrap, no hold -- the raw heading of every row
+    offs = torch.arange(len(v) + 1, dtype=torch.int32, device=cuda)
+    nat.check(nat.lib().uavb_minsnap_yaw_profile_f64(nat.ptr(vt), nat.ptr(offs), len(v), len(v), nat.ptr(out), nat.stream_ptr(cuda)), "yaw_profile")
+    got = out.cpu().numpy()
+    ref = np.arctan2(v[:, 1], v[:, 0])
+    err = np.abs(got - ref)
+    print(f"atan2_row: max |err| {err.max():.2e} rad over {len(v)} headings")
+    assert err.max() < 1e-15
+    assert got[2] == np.pi and got[12] > 3.14159 and got[13] < -3.14159          # the branch cut: +pi above, -pi below

@@ -263,6 +263,42 @@ __device__ __forceinline__ void eval_vel_xy(const double* __restrict__ c, double
 
 __device__ __forceinline__ bool yaw_valid(double vx, double vy) { return speed2_unfused(vx, vy) >= kSpeed2Min; }
 
+// atan2 for the heading of a table row (np.arctan2(vy, vx), minimum_snap.py:133), for inputs that passed yaw_valid (never both zero).
+// The library atan2 costs K3 a fifth of its instructions in 32-bit moves that materialise its polynomial constants (ncu: UMOV +
+// IMAD.MOV 22 % of the kernel); here the coefficients are constant-bank operands of the DFMAs and the quotient comes from one
+// reciprocal: with m = min(|x|,|y|), M = max(|x|,|y|):  w = m / M if 2 m <= M, else (m - M) / (m + M) and atan(m / M) = pi/4 + atan(w);
+// |w| <= 1/2, atan(w) = w P(w^2) with a degree-12 Chebyshev fit on [0, 1/4] (max error 4e-18, generated with mpmath); then the octant
+// and quadrant reflections.  Within 2 ulp of the correctly rounded result.
+__constant__ double kAtanPoly[13] = {0.010030841489968486489,  -0.027302779603074175199, 0.041775850326747944004, -0.05118531938647954336,
+                                     0.058574357651656937953,  -0.066636678441838564357, 0.076920579899766187704, -0.090908950580923122328,
+                                     0.11111110602305970347,   -0.14285714274692063502,  0.19999999999875543348,  -0.33333333333332779631,
+                                     1.0};
+__device__ __forceinline__ double rcp_f64(double d) {       // d > 0, normal range
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));     // ~20 bits, two Newton steps
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double atan2_row(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  const bool upper = mn + mn > mx;
+  const double num = upper ? mn - mx : mn, den = upper ? mn + mx : mx;
+  const double r = rcp_f64(den);
+  double w = num * r;
+  w = fma(fma(-w, den, num), r, w);                          // the quotient to ~1 ulp
+  const double z = w * w;
+  double p = kAtanPoly[0];
+#pragma unroll
+  for (int k = 1; k < 13; ++k) p = fma(p, z, kAtanPoly[k]);
+  double a = fma(w, p, upper ? 0.78539816339744830962 : 0.0);
+  a = (ay > ax) ? 1.57079632679489661923 - a : a;
+  a = (x < 0.0) ? 3.14159265358979323846 - a : a;
+  return copysign(a, y);
+}
+
 __global__ void __launch_bounds__(128) table_meta_kernel(const double* __restrict__ coeffs, const double* __restrict__ times,
                                                          const int* __restrict__ seg_offsets, int B, double dt,
                                                          int* __restrict__ rows_out, double* __restrict__ yaw0_out,
@@ -282,7 +318,7 @@ __global__ void __launch_bounds__(128) table_meta_kernel(const double* __restric
       for (int j = 0; j < n; ++j) {
         double vx, vy;
         eval_vel_xy(c, (double)j * dt, &vx, &vy);
-        if (yaw_valid(vx, vy)) { yaw0 = atan2(vy, vx); found = true; break; }
+        if (yaw_valid(vx, vy)) { yaw0 = atan2_row(vy, vx); found = true; break; }
       }
     }
   }
@@ -350,7 +386,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const d
         RowEval r;
         eval_table_row(coeffs + (size_t)s * 24, (double)(g - f) * dt, r, true);
         valid = yaw_valid(r.v[0], r.v[1]);
-        if (valid) raw = atan2(r.v[1], r.v[0]);
+        if (valid) raw = atan2_row(r.v[1], r.v[0]);
       }
       const unsigned bal = __ballot_sync(full, valid);
       if (bal) { first_yaw = __shfl_sync(full, raw, __ffs(bal) - 1); any_valid = true; }
@@ -373,7 +409,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const d
       locate(g, s, f);
       eval_table_row(coeffs + (size_t)s * 24, (double)(g - f) * dt, r, false);
       valid = yaw_valid(r.v[0], r.v[1]);
-      if (valid) raw = atan2(r.v[1], r.v[0]);
+      if (valid) raw = atan2_row(r.v[1], r.v[0]);
     }
     const unsigned bal = __ballot_sync(full, valid);
     // np.unwrap on the valid rows: dd against the previous valid row (in this chunk or carried), correction where |dd| >= pi
@@ -484,7 +520,7 @@ __global__ void __launch_bounds__(256) yaw_raw_kernel(const double* __restrict__
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const double vx = vel[3 * r], vy = vel[3 * r + 1];
-  yaw[r] = (sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy))) >= 1e-3) ? atan2(vy, vx) : nan("");
+  yaw[r] = (sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy))) >= 1e-3) ? atan2_row(vy, vx) : nan("");
 }
 
 // Sampled-point AABB test of the correction loop (minimum_snap.py:84-87): one warp per mission.
