@@ -9,7 +9,8 @@
 //     solve   the missions of the work lists (K1 arithmetic, one thread per mission; the lists are bucketed by spline count so
 //             that missions of up to 4 / 8 splines run the fully unrolled register-resident solver and only longer ones the
 //             rolled one with local arrays)
-//     sweep   one warp per listed mission: the lanes evaluate the sampled positions of every spline (the rows j * dt,
+//     sweep   one CTA of four warps per listed mission (one launch for all buckets), the warps take the splines in turn: the lanes
+//             evaluate the sampled positions of a spline (the rows j * dt,
 //             j < ceil(T_i / dt), by the same Horner recurrence as the sampled table -- the same bits), test them against the
 //             boxes from the mission's cursor on, reduce to (first obstacle hit, mask of its splines), insert the midpoints in
 //             place and append the mission to the next round's list of its new bucket
@@ -74,17 +75,21 @@ __global__ void __launch_bounds__(kCorrectThreads) minsnap_solve_list_kernel(con
 
 __device__ __forceinline__ unsigned long long bits_below(int i) { return i >= 64 ? ~0ull : (1ull << i) - 1ull; }
 
-// One warp per listed mission; see the header.  cuboids: [n_obs][6] doubles shared by all missions (cuboid_stride 0) or one set
-// per mission (cuboid_stride = doubles between consecutive missions' sets).
+// One CTA of kSweepWarps warps per listed mission, every bucket's list in ONE launch (block x belongs to the bucket whose cumulative
+// list length first exceeds x); warp w takes the splines s = w, w + kSweepWarps, ...; see the header.  cuboids: [n_obs][6] doubles
+// shared by all missions (cuboid_stride 0) or one set per mission (cuboid_stride = doubles between consecutive missions' sets).
 __global__ void __launch_bounds__(32 * kSweepWarps) correct_sweep_kernel(const double* __restrict__ coeffs, const double* __restrict__ times,
                                                                         double* __restrict__ waypoints, int* __restrict__ n_wp,
-                                                                        int* __restrict__ obs_idx, const int* __restrict__ list,
-                                                                        const int* __restrict__ n_list, int B, int max_wp, double dt, const double* __restrict__ cuboids, int n_obs,
-                                                                        long long cuboid_stride, int* __restrict__ status, WorkLists next) {
-  const int lane = threadIdx.x & 31;
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (e >= *n_list) return;
-  const int b = list[e];
+                                                                        int* __restrict__ obs_idx, WorkLists in, int B, int max_wp, double dt,
+                                                                        const double* __restrict__ cuboids, int n_obs, long long cuboid_stride,
+                                                                        int* __restrict__ status, WorkLists next) {
+  __shared__ int s_best[kSweepWarps];
+  __shared__ unsigned long long s_mask[kSweepWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int e = blockIdx.x, bucket = 0;
+  while (bucket < kBuckets && e >= in.count[bucket]) { e -= in.count[bucket]; ++bucket; }
+  if (bucket == kBuckets) return;                           // (uniform per CTA)
+  const int b = in.list[(size_t)bucket * B + e];
   const int nw = n_wp[b], S = nw - 1;
   const int o0 = obs_idx[b];
   const double* boxes = cuboids + (size_t)cuboid_stride * b;
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps) correct_sweep_kernel(const d
   int best = n_obs;                       // first obstacle (>= o0) with a sampled point inside, over this lane's rows
   unsigned long long mask = 0ull;         // splines that own such a point of obstacle `best`
   if (status[b] == UAVB_SOLVE_OK) {       // a degenerate mission has NaN coefficients: nothing to test
-    for (int s = 0; s < S; ++s) {
+    for (int s = warp; s < S; s += kSweepWarps) {
       const double* c = coeffs + ((size_t)b * (max_wp - 1) + s) * 24;
       const int n = arange_len(times[(size_t)b * (max_wp - 1) + s], dt);
       if (n <= lane) continue;
@@ -120,16 +125,26 @@ __global__ void __launch_bounds__(32 * kSweepWarps) correct_sweep_kernel(const d
       }
     }
   }
+  // (first obstacle hit, mask of its splines): over the warp, then over the CTA's warps
   int first = best;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) first = min(first, __shfl_xor_sync(full, first, off));
+  if (best != first) mask = 0ull;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mask |= __shfl_xor_sync(full, mask, off);
+  if (lane == 0) { s_best[warp] = first; s_mask[warp] = mask; }
+  __syncthreads();
+  if (warp != 0) return;
+  first = n_obs;
+#pragma unroll
+  for (int w = 0; w < kSweepWarps; ++w) first = min(first, s_best[w]);
   if (first >= n_obs) {                                   // clean against every remaining obstacle: this mission is done
     if (lane == 0) obs_idx[b] = n_obs;
     return;
   }
-  if (best != first) mask = 0ull;
+  mask = 0ull;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) mask |= __shfl_xor_sync(full, mask, off);
+  for (int w = 0; w < kSweepWarps; ++w) mask |= s_best[w] == first ? s_mask[w] : 0ull;
   const int n_new = nw + __popcll(mask);
   if (n_new > max_wp || n_new - 1 > UAVB_MAX_SPLINES) {
     if (lane == 0) { status[b] = UAVB_SOLVE_TOO_MANY; obs_idx[b] = first; }
@@ -234,14 +249,16 @@ int correct_missions(double* waypoints, int* n_waypoints, const double* velocity
       const WorkLists& in = wl[cur];
       const WorkLists& out = wl[cur ^ 1];
       if (rounds > 1) e = cudaMemsetAsync(out.count, 0, sizeof(int) * kBuckets, st);
+      long long n_ctas = 0;
       for (int k = 0; k < kBuckets && e == cudaSuccess && !result; ++k) {
         if (host_counts[k] == 0) continue;
-        const int* list = in.list + (size_t)k * B;
-        result = launch_solve_list(k, waypoints, n_waypoints, velocity, list, in.count + k, host_counts[k], max_wp, factor, coeffs_out, times_out,
-                                   status_out, st);
-        if (result || n_obs == 0) continue;
-        correct_sweep_kernel<<<div_up((long long)host_counts[k] * 32, 32 * kSweepWarps), 32 * kSweepWarps, 0, st>>>(
-            coeffs_out, times_out, waypoints, n_waypoints, obs_idx, list, in.count + k, B, max_wp, dt, cuboids, n_obs, cuboid_stride, status_out, out);
+        n_ctas += host_counts[k];
+        result = launch_solve_list(k, waypoints, n_waypoints, velocity, in.list + (size_t)k * B, in.count + k, host_counts[k], max_wp, factor,
+                                   coeffs_out, times_out, status_out, st);
+      }
+      if (e == cudaSuccess && !result && n_obs > 0 && n_ctas > 0) {   // one sweep launch for every bucket (grid: the sum of the lists' bounds)
+        correct_sweep_kernel<<<(unsigned)n_ctas, 32 * kSweepWarps, 0, st>>>(coeffs_out, times_out, waypoints, n_waypoints, obs_idx, in, B, max_wp, dt,
+                                                                           cuboids, n_obs, cuboid_stride, status_out, out);
         e = cudaGetLastError();
       }
       // work the caller wants behind round 1 and in front of its read-back (valid if nothing was hit: rounds_out == 1)

@@ -326,6 +326,49 @@ __global__ void __launch_bounds__(128) table_meta_kernel(const double* __restric
   if (total_rows_out) total_rows_out[b] = total;
 }
 
+// The same with one WARP per mission, for small batches (a shared mission's two tables): the thread-per-mission kernel walks a
+// vertical take-off's rows one by one looking for a valid heading that never comes (~15 us for one mission); here the lanes take 32
+// rows at a time.  Same values: the same row evaluation, the first valid row in row order.
+__global__ void __launch_bounds__(128) table_meta_warp_kernel(const double* __restrict__ coeffs, const double* __restrict__ times,
+                                                              const int* __restrict__ seg_offsets, int B, double dt,
+                                                              int* __restrict__ rows_out, double* __restrict__ yaw0_out,
+                                                              int* __restrict__ total_rows_out) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const unsigned full = 0xffffffffu;
+  const int s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
+  int total = 0;
+  double yaw0 = 0.0;
+  bool found = false;
+  for (int s = s0; s < s1; ++s) {
+    const int n = arange_len(times[s], dt);
+    if (lane == 0) rows_out[s] = n;
+    total += n;
+    const double* c = coeffs + (size_t)s * 24;
+    for (int base = 0; base < n && !found; base += 32) {
+      const int j = base + lane;
+      double vx = 0.0, vy = 0.0;
+      bool valid = false;
+      if (j < n) {
+        eval_vel_xy(c, (double)j * dt, &vx, &vy);
+        valid = yaw_valid(vx, vy);
+      }
+      const unsigned bal = __ballot_sync(full, valid);
+      if (bal) {
+        const int src = __ffs(bal) - 1;
+        const double y = valid ? atan2_row(vy, vx) : 0.0;
+        yaw0 = __shfl_sync(full, y, src);
+        found = true;
+      }
+    }
+  }
+  if (lane == 0) {
+    yaw0_out[b] = yaw0;
+    if (total_rows_out) total_rows_out[b] = total;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3 sampled table, one pass, one warp per mission.  The lanes take 32 consecutive rows (across spline boundaries),
 // evaluate position / velocity / acceleration, and resolve the yaw column with warp scans that carry their state from
@@ -719,8 +762,12 @@ extern "C" int uavb_minsnap_table_meta_f64(const double* coeffs, const double* t
   int rc = require_device();
   if (rc) return rc;
   if (B == 0) return UAVB_OK;
-  table_meta_kernel<<<div_up(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(coeffs, times, seg_offsets, B, dt, rows_out,
-                                                                                   yaw0_out, total_rows_out);
+  if (B <= 2048)
+    table_meta_warp_kernel<<<div_up((long long)B * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(coeffs, times, seg_offsets, B, dt, rows_out,
+                                                                                                          yaw0_out, total_rows_out);
+  else
+    table_meta_kernel<<<div_up(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(coeffs, times, seg_offsets, B, dt, rows_out,
+                                                                                     yaw0_out, total_rows_out);
   UAVB_CUDA_OK(cudaGetLastError());
   return UAVB_OK;
 }
