@@ -103,6 +103,7 @@ def test_argument_validation_and_no_cpu_path(nat):
     # round-2 entry points: the correction loop, the shared planner, the constraint system
     assert L.uavb_minsnap_correct_f64(one, one, one, 1, 66, 1.5, 0.01, null, 0, 0, one, one, one, None, null) == -1      # max_wp > UAVB_MAX_SPLINES + 1
     assert b"max_wp" in L.uavb_last_error()
+    assert L.uavb_minsnap_correct_f64(null, one, one, 1, 6, 1.5, 0.01, null, 0, 0, one, one, one, None, null) == -1 and b"NULL" in L.uavb_last_error()
     assert L.uavb_minsnap_correct_f64(one, one, one, 1, 6, 1.5, 0.01, null, 2, 0, one, one, one, None, null) == -1       # n_obs > 0 without cuboids
     assert L.uavb_minsnap_correct_f64(one, one, one, 1, 6, 1.5, 0.0, null, 0, 0, one, one, one, None, null) == -1        # dt <= 0
     assert L.uavb_minsnap_correct_f64(one, one, one, 1, 6, 1.5, 0.01, one, 2, 6, one, one, one, None, null) == -1        # cuboid_stride < 6 n_obs

@@ -186,3 +186,40 @@ def test_speculative_shared_plan_is_verified_after_the_fact(cuda, golden):
     v15 = torch.tensor([1.5], **f64)
     with pytest.raises(RuntimeError, match="inside a box"):
         kernels.plan_missions([(course[None].contiguous(), v15)], 0.01, shared=True, obstacles=boxes, table_rows=500).verify()
+
+
+def test_every_bucket_and_the_size_limits(cuda):
+    """Missions of 3 / 6 / 12 / 40 / 64 splines in one batch (all four work-list buckets; 64 = UAVB_MAX_SPLINES) with the boxes far away:
+    one plan round, and every mission's coefficients are K1's for its own spline count.  Then the edges: an empty batch, a
+    two-waypoint mission, a mission that is already at the capacity and gets hit."""
+    import torch
+    from uav_ac_b200 import _native as nat, kernels
+    rng = np.random.default_rng(12)
+    counts = [3, 6, 12, 40, 64, 4, 8, 16, 1]
+    paths = [np.cumsum(rng.uniform([1.0, -1.5, -0.3], [2.5, 1.5, 0.3], (s + 1, 3)), axis=0) for s in counts]
+    vel = torch.tensor(rng.uniform(1.5, 3.0, len(paths)), dtype=torch.float64, device=cuda)
+    far = torch.tensor([[1e6, 1e6 + 1, 1e6, 1e6 + 1, 1e6, 1e6 + 1]], dtype=torch.float64, device=cuda)
+    c, t, seg_off, status, wp, n_wp, rounds = kernels.plan_collision_free(paths, vel, 0.01, far, device=cuda)
+    assert rounds == 1 and status.tolist() == [0] * len(paths) and n_wp.tolist() == [s + 1 for s in counts]
+    for b, (s, p_) in enumerate(zip(counts, paths)):
+        ck, tk, st = kernels.minsnap_solve(torch.tensor(p_[None], dtype=torch.float64, device=cuda), vel[b:b + 1])
+        mine = c[int(seg_off[b]):int(seg_off[b + 1])].reshape(-1, 3).cpu().numpy()
+        assert int(st[0]) == 0 and normwise(mine, ck.reshape(-1, 3).cpu().numpy()) < 1e-12, s
+        assert torch.equal(t[int(seg_off[b]):int(seg_off[b + 1])], tk.reshape(-1))
+    # empty batch: nothing to do, nothing touched
+    e_wp = torch.empty((0, 6, 3), dtype=torch.float64, device=cuda)
+    e_n = torch.empty((0,), dtype=torch.int32, device=cuda)
+    ce, te, ste, re_ = kernels.minsnap_correct(e_wp, e_n, torch.empty((0,), dtype=torch.float64, device=cuda), 0.01, far)
+    assert ce.shape == (0, 5, 8, 3) and re_ == 0
+    # at the capacity already: a hit cannot be answered with a midpoint -> reported, waypoints untouched
+    g_wp = np.array([[0.0, 0, -1], [4, 0, -1], [4, 4, -1], [8, 4, -1.5]])
+    box = torch.tensor([[4.1, 4.6, 0.5, 1.2, -1.2, -0.8]], dtype=torch.float64, device=cuda)      # the reference's corrected scenario
+    wpf, nf = kernels.fixed_pitch([g_wp], 4, cuda)
+    before = wpf.clone()
+    _, _, st2, _ = kernels.minsnap_correct(wpf, nf, torch.tensor([1.5], dtype=torch.float64, device=cuda), 0.01, box)
+    assert st2.tolist() == [nat.SOLVE_TOO_MANY] and nf.tolist() == [4] and torch.equal(wpf, before)
+    # a degenerate mission (repeated waypoint) is flagged and does not disturb its neighbours
+    bad = np.array([[0.0, 0, 0], [1, 0, 0], [1, 0, 0], [2, 0, 0]])
+    c3, _, off3, st3, _, _, _ = kernels.plan_collision_free([paths[0], bad, paths[1]], vel[:3].contiguous(), 0.01, far, device=cuda)
+    assert st3.tolist() == [0, nat.SOLVE_DEGENERATE, 0]
+    assert torch.equal(c3[:int(off3[1])], c[:int(seg_off[1])]) and bool(torch.isnan(c3[int(off3[1]):int(off3[2])]).all())

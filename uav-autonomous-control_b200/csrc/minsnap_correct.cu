@@ -382,8 +382,8 @@ using namespace uavb;
 extern "C" int uavb_minsnap_correct_f64(double* waypoints, int* n_waypoints, const double* velocity, int B, int max_wp, double factor, double dt,
                                         const double* cuboids, int n_obs, long long cuboid_stride, double* coeffs_out, double* times_out,
                                         int* status_out, int* rounds_out, void* stream) {
-  UAVB_REQUIRE(waypoints && n_waypoints && velocity && coeffs_out && times_out && status_out, "minsnap_correct: NULL pointer");
   UAVB_REQUIRE(B >= 0 && max_wp >= 2 && max_wp <= UAVB_MAX_SPLINES + 1, "minsnap_correct: B >= 0 and 2 <= max_wp <= UAVB_MAX_SPLINES + 1 required");
+  UAVB_REQUIRE(B == 0 || (waypoints && n_waypoints && velocity && coeffs_out && times_out && status_out), "minsnap_correct: NULL pointer");
   UAVB_REQUIRE(dt > 0.0, "minsnap_correct: dt > 0 required");
   UAVB_REQUIRE(n_obs >= 0 && (n_obs == 0 || cuboids != nullptr), "minsnap_correct: n_obs > 0 needs cuboids");
   UAVB_REQUIRE(cuboid_stride == 0 || cuboid_stride >= 6LL * n_obs, "minsnap_correct: cuboid_stride must be 0 or >= 6 n_obs");
@@ -397,8 +397,8 @@ extern "C" int uavb_minsnap_correct_f64(double* waypoints, int* n_waypoints, con
 
 extern "C" int uavb_minsnap_pack_f64(const double* coeffs, const double* times, const int* n_waypoints, int B, int max_wp, const int* seg_offsets,
                                      double* coeffs_out, double* times_out, void* stream) {
-  UAVB_REQUIRE(coeffs && times && n_waypoints && seg_offsets && coeffs_out && times_out, "minsnap_pack: NULL pointer");
   UAVB_REQUIRE(B >= 0 && max_wp >= 2, "minsnap_pack: B >= 0 and max_wp >= 2 required");
+  UAVB_REQUIRE(B == 0 || (coeffs && times && n_waypoints && seg_offsets && coeffs_out && times_out), "minsnap_pack: NULL pointer");
   int rc = require_device();
   if (rc) return rc;
   if (B == 0) return UAVB_OK;
