@@ -164,6 +164,26 @@ def stream_ptr(device=None) -> c_void_p:
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _OnDevice:
+    """``on(dev).uavb_xyz(args...)``: the library call with ``dev`` as the CURRENT device (the library sizes grids, picks its scratch
+    pool and validates against cudaGetDevice()), return code checked."""
+
+    def __init__(self, dev):
+        self._dev = torch.device(dev)
+
+    def __getattr__(self, name):
+        fn = getattr(lib(), name)
+
+        def call(*args):
+            with torch.cuda.device(self._dev):
+                check(fn(*args), name)
+        return call
+
+
+def on(dev) -> _OnDevice:
+    return _OnDevice(dev)
+
+
 def ptr(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "tensor") -> c_void_p:
     """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
     if t is None:

@@ -39,9 +39,9 @@ def minsnap_solve(waypoints: torch.Tensor, velocity: torch.Tensor, factor: float
     coeffs = torch.empty((B, 8 * S, 3), dtype=torch.float64, device=dev)
     times = torch.empty((B, S), dtype=torch.float64, device=dev)
     status = torch.empty((B,), dtype=torch.int32, device=dev)
-    nat.check(nat.lib().uavb_minsnap_solve_f64(
+    nat.on(dev).uavb_minsnap_solve_f64(
         nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(velocity, torch.float64, "velocity"), B, S, float(factor),
-        nat.ptr(coeffs), nat.ptr(times), nat.ptr(status), nat.stream_ptr(dev)), "uavb_minsnap_solve_f64")
+        nat.ptr(coeffs), nat.ptr(times), nat.ptr(status), nat.stream_ptr(dev))
     return coeffs, times, status
 
 
@@ -54,10 +54,10 @@ def minsnap_solve_ragged(waypoints: torch.Tensor, wp_offsets: torch.Tensor, velo
     coeffs = torch.empty((n_seg, 8, 3), dtype=torch.float64, device=dev)
     times = torch.empty((n_seg,), dtype=torch.float64, device=dev)
     status = torch.empty((B,), dtype=torch.int32, device=dev)
-    nat.check(nat.lib().uavb_minsnap_solve_ragged_f64(
+    nat.on(dev).uavb_minsnap_solve_ragged_f64(
         nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(wp_offsets, torch.int32, "wp_offsets"),
         nat.ptr(velocity, torch.float64, "velocity"), B, float(factor), nat.ptr(coeffs), nat.ptr(times), nat.ptr(status),
-        nat.stream_ptr(dev)), "uavb_minsnap_solve_ragged_f64")
+        nat.stream_ptr(dev))
     return coeffs, times, status
 
 
@@ -67,8 +67,8 @@ def minsnap_constraints(waypoints: torch.Tensor, times: torch.Tensor):
     B, S = waypoints.shape[0], waypoints.shape[1] - 1
     A = torch.empty((B, 6 * S + 2, 8 * S), dtype=torch.float64, device=waypoints.device)
     b = torch.empty((B, 6 * S + 2, 3), dtype=torch.float64, device=waypoints.device)
-    nat.check(nat.lib().uavb_minsnap_constraints_f64(nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(times, torch.float64, "times"), B, S,
-                                                     nat.ptr(A), nat.ptr(b), nat.stream_ptr(waypoints.device)), "uavb_minsnap_constraints_f64")
+    nat.on(waypoints.device).uavb_minsnap_constraints_f64(nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(times, torch.float64, "times"), B, S,
+                                                     nat.ptr(A), nat.ptr(b), nat.stream_ptr(waypoints.device))
     return A, b
 
 
@@ -84,9 +84,9 @@ def table_meta(coeffs: torch.Tensor, times: torch.Tensor, seg_offsets: torch.Ten
     rows = torch.empty((n_seg,), dtype=torch.int32, device=dev)
     yaw0 = torch.empty((B,), dtype=torch.float64, device=dev)
     total = torch.empty((B,), dtype=torch.int32, device=dev)
-    nat.check(nat.lib().uavb_minsnap_table_meta_f64(
+    nat.on(dev).uavb_minsnap_table_meta_f64(
         nat.ptr(coeffs, torch.float64, "coeffs"), nat.ptr(times, torch.float64, "times"), nat.ptr(seg_offsets, torch.int32, "seg_offsets"),
-        B, float(dt), nat.ptr(rows), nat.ptr(yaw0), nat.ptr(total), nat.stream_ptr(dev)), "uavb_minsnap_table_meta_f64")
+        B, float(dt), nat.ptr(rows), nat.ptr(yaw0), nat.ptr(total), nat.stream_ptr(dev))
     return rows, yaw0, total
 
 
@@ -96,10 +96,10 @@ def minsnap_sample(coeffs: torch.Tensor, times: torch.Tensor, seg_offsets: torch
     B = seg_offsets.numel() - 1
     n_rows = int(row_offsets[-1].item())
     table = torch.empty((n_rows, 11), dtype=torch.float64, device=coeffs.device)
-    nat.check(nat.lib().uavb_minsnap_sample_f64(
+    nat.on(coeffs.device).uavb_minsnap_sample_f64(
         nat.ptr(coeffs, torch.float64, "coeffs"), nat.ptr(times, torch.float64, "times"), nat.ptr(seg_offsets, torch.int32, "seg_offsets"),
         nat.ptr(seg_rows, torch.int32, "seg_rows"), nat.ptr(row_offsets, torch.int32, "row_offsets"), B, float(dt), nat.ptr(table),
-        nat.stream_ptr(coeffs.device)), "uavb_minsnap_sample_f64")
+        nat.stream_ptr(coeffs.device))
     return table
 
 
@@ -108,10 +108,9 @@ def table_hits(table: torch.Tensor, row_offsets: torch.Tensor, cuboid: torch.Ten
     -- the test of the correction loop (minimum_snap.py:84-87, 327-357)."""
     B = row_offsets.numel() - 1
     stride = 0 if cuboid.dim() == 1 else 6
-    nat.check(nat.lib().uavb_minsnap_table_hits_f64(
+    nat.on(table.device).uavb_minsnap_table_hits_f64(
         nat.ptr(table, torch.float64, "table"), nat.ptr(row_offsets, torch.int32, "row_offsets"), B,
-        nat.ptr(cuboid, torch.float64, "cuboid"), stride, nat.ptr(hit_mask, torch.int64, "hit_mask"), nat.stream_ptr(table.device)),
-        "uavb_minsnap_table_hits_f64")
+        nat.ptr(cuboid, torch.float64, "cuboid"), stride, nat.ptr(hit_mask, torch.int64, "hit_mask"), nat.stream_ptr(table.device))
     return hit_mask
 
 
@@ -160,10 +159,10 @@ def minsnap_correct(waypoints: torch.Tensor, n_waypoints: torch.Tensor, velocity
             obs = obs.reshape(-1, 6)
             n_obs = int(obs.shape[0])
     rounds = ctypes.c_int(0)
-    nat.check(nat.lib().uavb_minsnap_correct_f64(
+    nat.on(dev).uavb_minsnap_correct_f64(
         nat.ptr(waypoints, torch.float64, "waypoints"), nat.ptr(n_waypoints, torch.int32, "n_waypoints"), nat.ptr(velocity, torch.float64, "velocity"),
         B, max_wp, float(factor), float(dt), nat.ptr(obs), n_obs, stride, nat.ptr(coeffs), nat.ptr(times), nat.ptr(status), ctypes.byref(rounds),
-        nat.stream_ptr(dev)), "uavb_minsnap_correct_f64")
+        nat.stream_ptr(dev))
     return coeffs, times, status, rounds.value
 
 
@@ -178,9 +177,9 @@ def pack_segments(coeffs: torch.Tensor, times: torch.Tensor, n_waypoints: torch.
         n_seg = int(seg_offsets[-1].item())
     c = torch.empty((n_seg, 8, 3), dtype=torch.float64, device=dev)
     t = torch.empty((n_seg,), dtype=torch.float64, device=dev)
-    nat.check(nat.lib().uavb_minsnap_pack_f64(nat.ptr(coeffs, torch.float64, "coeffs"), nat.ptr(times, torch.float64, "times"),
+    nat.on(dev).uavb_minsnap_pack_f64(nat.ptr(coeffs, torch.float64, "coeffs"), nat.ptr(times, torch.float64, "times"),
                                               nat.ptr(n_waypoints, torch.int32, "n_waypoints"), B, max_wp, nat.ptr(seg_offsets), nat.ptr(c), nat.ptr(t),
-                                              nat.stream_ptr(dev)), "uavb_minsnap_pack_f64")
+                                              nat.stream_ptr(dev))
     return c, t, seg_offsets
 
 
@@ -404,12 +403,10 @@ def _plan_shared_corrected(tables, dt: float, factor: float, table_rows: Optiona
     n_seg, rounds = ctypes.c_int(0), ctypes.c_int(0)
     tab_rows, status = (ctypes.c_int * T)(), (ctypes.c_int * T)()
     report, ticket = _report_block(dev) if table_rows is not None else (None, None)
-    with torch.cuda.device(dev):
-        nat.check(nat.lib().uavb_plan_shared_f64(T, ptrs, n_wp, nat.ptr(vels, torch.float64, "velocity"), float(factor), float(dt), nat.ptr(obs),
-                                                 int(obs.shape[0]), cap, nat.ptr(coeffs), nat.ptr(times), nat.ptr(rows), nat.ptr(seg_table),
-                                                 nat.ptr(seg_yaw0), ctypes.byref(n_seg), tab_rows, status, ctypes.byref(rounds),
-                                                 ctypes.c_void_p(report.data_ptr()) if report is not None else None, nat.stream_ptr(dev)),
-                  "uavb_plan_shared_f64")
+    nat.on(dev).uavb_plan_shared_f64(T, ptrs, n_wp, nat.ptr(vels, torch.float64, "velocity"), float(factor), float(dt), nat.ptr(obs),
+                                     int(obs.shape[0]), cap, nat.ptr(coeffs), nat.ptr(times), nat.ptr(rows), nat.ptr(seg_table),
+                                     nat.ptr(seg_yaw0), ctypes.byref(n_seg), tab_rows, status, ctypes.byref(rounds),
+                                     ctypes.c_void_p(report.data_ptr()) if report is not None else None, nat.stream_ptr(dev))
     n = n_seg.value
     plan = MissionPlan(coeffs[:n], rows[:n], seg_table[:n], seg_yaw0[:n], float(dt), times=times[:n], n_seg_shared=n)
     if report is not None:
@@ -451,13 +448,13 @@ def _plan_shared(tables, dt: float, factor: float, table_rows: Optional[int], ob
     coeffs = torch.empty((n_seg, 8, 3), dtype=torch.float64, device=dev)
     times = torch.empty((n_seg,), dtype=torch.float64, device=dev)
     status = torch.empty((T,), dtype=torch.int32, device=dev)
-    L, st, off = nat.lib(), nat.stream_ptr(dev), 0
+    st, off = nat.stream_ptr(dev), 0
     for k, (wp, vel) in enumerate(tables):
         if wp.shape[0] != 1 or vel.shape != (1,):
             raise ValueError("shared=True needs a single mission per table")
-        nat.check(L.uavb_minsnap_solve_f64(nat.ptr(wp, torch.float64, "waypoints"), nat.ptr(vel, torch.float64, "velocity"), 1, splines[k], float(factor),
+        nat.on(dev).uavb_minsnap_solve_f64(nat.ptr(wp, torch.float64, "waypoints"), nat.ptr(vel, torch.float64, "velocity"), 1, splines[k], float(factor),
                                            ctypes.c_void_p(coeffs.data_ptr() + off * 192), ctypes.c_void_p(times.data_ptr() + off * 8),
-                                           ctypes.c_void_p(status.data_ptr() + k * 4), st), "uavb_minsnap_solve_f64")
+                                           ctypes.c_void_p(status.data_ptr() + k * 4), st)
         off += splines[k]
     rows, yaw0, total = table_meta(coeffs, times, offsets, dt)
     seg_yaw0 = torch.zeros((n_seg,), dtype=torch.float64, device=dev).index_copy_(0, starts, yaw0)
@@ -475,9 +472,9 @@ def rollout_targets(plan: MissionPlan, n_rows: Optional[int] = None) -> torch.Te
     if n_rows is None:
         n_rows = int(plan.total_rows.sum().item())
     out = torch.empty((n_rows, nat.TARGET_ROW_BYTES), dtype=torch.uint8, device=plan.seg_coeffs.device)
-    nat.check(nat.lib().uavb_rollout_targets_f64(
+    nat.on(out.device).uavb_rollout_targets_f64(
         nat.ptr(plan.seg_coeffs, torch.float64, "seg_coeffs"), nat.ptr(plan.seg_rows, torch.int32, "seg_rows"), nat.ptr(plan.seg_table, torch.int32, "seg_table"),
-        nat.ptr(plan.seg_yaw0, torch.float64, "seg_yaw0"), n_seg, float(plan.dt), nat.ptr(out), n_rows, nat.stream_ptr(out.device)), "uavb_rollout_targets_f64")
+        nat.ptr(plan.seg_yaw0, torch.float64, "seg_yaw0"), n_seg, float(plan.dt), nat.ptr(out), n_rows, nat.stream_ptr(out.device))
     return out
 
 
@@ -601,8 +598,8 @@ def mc_uniform(seed: int, B: int, lo: Sequence[float], hi: Sequence[float], *, i
     lo_t = torch.tensor(list(lo), dtype=torch.float32, device=dev)
     hi_t = torch.tensor(list(hi), dtype=torch.float32, device=dev)
     out = torch.empty((lo_t.numel(), B), dtype=torch.float32, device=dev)
-    nat.check(nat.lib().uavb_mc_uniform_f32(int(seed), int(index_base), int(stream_id), int(B), int(lo_t.numel()), nat.ptr(lo_t), nat.ptr(hi_t),
-                                            nat.ptr(out), nat.stream_ptr(dev)), "uavb_mc_uniform_f32")
+    nat.on(dev).uavb_mc_uniform_f32(int(seed), int(index_base), int(stream_id), int(B), int(lo_t.numel()), nat.ptr(lo_t), nat.ptr(hi_t),
+                                            nat.ptr(out), nat.stream_ptr(dev))
     return out
 
 
@@ -611,6 +608,5 @@ def mc_missions(seed: int, B: int, S: int = 4, *, index_base: int = 0, device=No
     dev = _dev(device)
     wp = torch.empty((B, S + 1, 3), dtype=torch.float64, device=dev)
     vel = torch.empty((B,), dtype=torch.float64, device=dev)
-    nat.check(nat.lib().uavb_mc_missions_f64(int(seed), int(index_base), int(B), int(S), nat.ptr(wp), nat.ptr(vel), nat.stream_ptr(dev)),
-              "uavb_mc_missions_f64")
+    nat.on(dev).uavb_mc_missions_f64(int(seed), int(index_base), int(B), int(S), nat.ptr(wp), nat.ptr(vel), nat.stream_ptr(dev))
     return wp, vel
