@@ -132,3 +132,44 @@ def test_config2_every_rollout_of_the_headline_batch_against_the_c_oracle(cuda):
     assert np.array_equal(m[:, 1], m_ref[:, 1]) and np.array_equal(m[:, 6], m_ref[:, 6])            # flags and first-hit ticks, bit for bit
     assert np.abs(m[:, 0] - m_ref[:, 0]).max() < 1e-4 and np.abs(m[:, 2:5] - m_ref[:, 2:5]).max() < 1e-4 and np.array_equal(m[:, 7], m_ref[:, 7])
     assert int((m[:, 5] != 0).sum()) == 0
+
+
+def test_correction_loop_leaves_no_sampled_point_inside_a_box_at_full_size(cuda):
+    """10^5 random five-waypoint missions x 4 shared boxes through the device-side correction loop; size-independent property: for
+    every mission that finished (status OK), the sampled (N, 11) table of its final plan -- K3, a different kernel from the loop's own
+    sweep -- has no row inside any box, and missions that were never hit keep their five waypoints.  Missions whose waypoint sits in
+    a box cannot be cleared (the reference loops forever) and are reported as UAVB_SOLVE_TOO_MANY."""
+    import torch
+    from uav_ac_b200 import _native as nat, kernels
+    B, cap = 100_000, 33
+    wp, vel = kernels.mc_missions(123, B, 4, device=cuda)
+    rng = np.random.default_rng(5)
+    ctr, half = rng.uniform([4, 3, -4.5], [20, 11, -1.5], (4, 3)), rng.uniform(0.15, 0.4, (4, 3))
+    boxes = torch.tensor(np.stack((ctr[:, 0] - half[:, 0], ctr[:, 0] + half[:, 0], ctr[:, 1] - half[:, 1], ctr[:, 1] + half[:, 1],
+                                   ctr[:, 2] - half[:, 2], ctr[:, 2] + half[:, 2]), axis=-1), dtype=torch.float64, device=cuda)
+    w, n = kernels.fixed_pitch(wp, cap, cuda)
+    c, t, status, rounds = kernels.minsnap_correct(w, n, vel, 0.01, boxes)
+    ok = status == 0
+    assert int(ok.sum()) > 0.97 * B and set(status.unique().tolist()) <= {0, nat.SOLVE_TOO_MANY}
+    # a waypoint inside a box <=> cannot be cleared
+    p = wp[:, :, None, :]                                                        # [B, 5, 1, 3]
+    inside = ((boxes[None, None, :, 0] <= p[..., 0]) & (p[..., 0] <= boxes[None, None, :, 1]) & (boxes[None, None, :, 2] <= p[..., 1])
+              & (p[..., 1] <= boxes[None, None, :, 3]) & (boxes[None, None, :, 4] <= p[..., 2]) & (p[..., 2] <= boxes[None, None, :, 5])).any(dim=2).any(dim=1)
+    # (not every one: the last waypoint of a mission is never sampled -- np.arange excludes T -- so a box that holds only that point
+    # within one step of its face may go unnoticed, exactly as in the reference)
+    assert float((status[inside] == nat.SOLVE_TOO_MANY).float().mean()) > 0.9
+    grown = n > 5
+    print(f"correction loop at full size: {rounds} rounds, {int(grown.sum())} missions grew (up to {int(n.max())} waypoints), "
+          f"{int((status != 0).sum())} cannot be cleared, {int(inside.sum())} of them with a waypoint inside a box")
+    # K3 tables of the finished missions
+    idx = ok.nonzero().squeeze(1)
+    cp, tp, seg_off = kernels.pack_segments(c[idx].contiguous(), t[idx].contiguous(), n[idx].contiguous())
+    rows, yaw0, total = kernels.table_meta(cp, tp, seg_off, 0.01)
+    roff = torch.zeros(idx.numel() + 1, dtype=torch.int32, device=cuda)
+    roff[1:] = torch.cumsum(total, 0)
+    table = kernels.minsnap_sample(cp, tp, seg_off, rows, roff, 0.01)
+    mask = torch.zeros(idx.numel(), dtype=torch.int64, device=cuda)
+    for k in range(4):
+        kernels.table_hits(table, roff, boxes[k].contiguous(), mask)
+    assert int((mask != 0).sum()) == 0
+    assert bool((n[ok & ~grown] == 5).all()) and torch.equal(w[~grown & ok, :5], wp[~grown & ok])
