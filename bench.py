@@ -347,19 +347,46 @@ def run_b200(args):
     results = [kernels.RolloutResult(gather.shard[i], None, None, None) for i in range(2)]
     state = {"n": None, "k": 0, "plans": []}
 
+    side = torch.cuda.Stream(dev)                            # the NEXT step's plan is enqueued here while this step's K2 flies
+    state.update(pending=None, remaining=0)
+
+    def make_plan(wp, vel, n_ticks):
+        return kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True,
+                                     table_rows=None if n_ticks is None else n_ticks // FREQUENCY, obstacles=obs64)
+
+    def issue_plan(wp, vel):
+        """A speculative plan on the side stream, ordered behind everything the launching stream holds NOW (so it belongs to the
+        step that issues it), with the event K2 waits for."""
+        main = torch.cuda.current_stream(dev)
+        mark = torch.cuda.Event()
+        mark.record(main)
+        side.wait_event(mark)
+        with torch.cuda.stream(side):
+            plan = make_plan(wp, vel, state["n"])
+            ready = torch.cuda.Event()
+            ready.record(side)
+        state["plans"].append(plan)                          # speculative plan (no host round trip): its report is checked in drain()
+        return plan, ready
+
     def hot_path(wp, vel, mc, result):
         """Plan (both tables through K1 and the obstacle-correction sweep, table geometry, set-point table) + K2 over the shard; the
         per-rollout metrics land in result.metrics.  After the first step the table length is known and the plan is speculative
-        (kernels.plan_missions: no host round trip, the correction loop's report is verified in drain(), inside the timed region)."""
-        n_ticks = state["n"]
-        plan = kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True,
-                                     table_rows=None if n_ticks is None else n_ticks // FREQUENCY, obstacles=obs64)
-        if n_ticks is None:                                  # mission length is data dependent: read it once, outside the timed steps
-            n_ticks = state["n"] = FREQUENCY * int(plan.total_rows.item())
+        (kernels.plan_missions: no host round trip, the correction loop's report is verified in drain(), inside the timed region).
+        Steps are software-pipelined: the plan of step s + 1 is enqueued on a side stream behind the LAUNCH of K2(s) -- its few small
+        kernels run in the SM slots K2(s) frees at its tail -- and K2(s + 1) waits for its event.  The first step of a timed
+        region plans inside the region (drain() drops a plan made ahead), the last one plans nothing ahead: K plans per K steps."""
+        if state["n"] is None:                               # mission length is data dependent: read it once, outside the timed steps
+            plan = make_plan(wp, vel, None)
+            state["n"] = FREQUENCY * int(plan.total_rows.item())
         else:
-            state["plans"].append(plan)                      # speculative plan (no host round trip): its report is checked in drain()
-        kernels.rollout(plan, B, n_ticks, start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc[:11], mc_mass=mc[11],
+            plan, ready = state["pending"] if state["pending"] is not None else issue_plan(wp, vel)
+            state["pending"] = None
+            torch.cuda.current_stream(dev).wait_event(ready)
+        kernels.rollout(plan, B, state["n"], start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc[:11], mc_mass=mc[11],
                         mc_inertia=mc[12:15], obstacles=obs, want_state=False, out=result, index_base=begin)
+        state["remaining"] -= 1
+        if state["remaining"] > 0:
+            state["pending"] = issue_plan(wp, vel)
 
     def step_device():
         k = state["k"]
@@ -374,6 +401,7 @@ def run_b200(args):
         for plan in state["plans"]:                          # every speculative plan of the region is the plan the reference makes
             plan.verify()
         state["plans"].clear()
+        state["pending"] = None
 
     mc_mass_h, mc_inertia_h, mc_gains_h = mc_host[11], mc_host[12:15], mc_host[:11]     # contiguous pinned views, SoA
     wp_np = np.ascontiguousarray(LAB_COURSE_WAYPOINTS, dtype=np.float64)
@@ -390,10 +418,12 @@ def run_b200(args):
     def timed(fn, steps, warmup, sampler=None, wall=False, after=None):
         """K timed steps between barriers + synchronize; device time from CUDA events on the launching (current torch)
         stream, or host wall-clock for the synchronous host-buffer call (wall=True); max over ranks."""
+        state["remaining"] = warmup
         for _ in range(warmup):
             fn()
         if after:
             after()
+        state["remaining"] = steps
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -403,7 +433,10 @@ def run_b200(args):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         wall_ms = 0.0
         for s in range(steps):
-            flush.fill_(s & 0xFF)                                                           # flush L2 between timed iterations
+            if s == 0 and not wall:
+                flush_and_space(flush, 0)                                                   # L2 flush + ~0.3 ms of queued work: the first step's launches are enqueued before the GPU reaches them
+            else:
+                flush.fill_(s & 0xFF)                                                       # flush L2 between timed iterations
             if wall:
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()

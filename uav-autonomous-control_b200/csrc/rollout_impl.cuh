@@ -47,6 +47,11 @@ template <class R> struct RolloutDev {
   VehU<R> u;      // launch-uniform constants (constant bank)
   VehP<R> vp;     // per-rollout constants when no Monte-Carlo override is given (constant bank)
   int coeff_cache_offset;   // offset (in doubles) of the [24][64] coefficient staging area in dynamic shared memory, -1 = none
+  // Sliced fp32 launches with Monte-Carlo overrides: the per-rollout constants (VehP) as [kVehpWords][vehp_stride] floats, written by a
+  // pair's first slice and read by its later ones instead of redoing the ~20 fp64 divisions of make_vehp per drone and slice
+  // (ncu: the slice prologue was half of the 10 us a slice costs the headline launch); nullptr = recompute.  Same values either way.
+  float* vehp_cache;
+  long long vehp_stride;
 };
 
 // Obstacle set: SHARED = one set for the launch, staged in the CTA's dynamic shared memory (LDS.64 broadcast reads);
@@ -283,6 +288,32 @@ template <class R> __device__ __forceinline__ void load_vehp(VehP<R>& v, const u
   make_vehp<R>(v, a.veh, mc);
 }
 
+// The fields of VehP<float> in declaration order (the layout of RolloutDev::vehp_cache).
+#define UAVB_VEHP_FIELDS(X)                                                                                                          \
+  X(kf_dt_over_m) X(kf_dt_over_m2) X(dIx) X(dIy) X(dIz) X(Ikp_p) X(Ikp_q) X(Ikp_r) X(dt_invIx) X(dt_invIy) X(dt_invIz) X(Gx) X(Gy) X(Gz) \
+  X(Jp) X(Jq) X(Jr) X(Wx) X(Wy) X(Wz) X(Kx) X(Ky) X(Kz) X(dvx) X(dvy) X(dvz) X(mass) X(kp_xy) X(kd_xy) X(kp_z) X(kd_z) X(ki_z)         \
+  X(kp_roll) X(kp_pitch) X(kp_yaw) X(acc_max)
+#define UAVB_COUNT_FIELD(f) +1
+constexpr int kVehpWords = 0 UAVB_VEHP_FIELDS(UAVB_COUNT_FIELD);
+static_assert(sizeof(VehP<float>) == 4 * kVehpWords, "UAVB_VEHP_FIELDS must list every field of VehP");
+// column pair (2j, 2j+1) of the cache <-> the two VehP of a pair; fields the kernel never reads are never loaded
+__device__ __forceinline__ void vehp_cache_store(float* cache, long long stride, long long i0, const VehP<float>& a, const VehP<float>& b) {
+  float2* o = reinterpret_cast<float2*>(cache + i0);
+  const long long s2 = stride >> 1;
+  int k = 0;
+#define UAVB_ST(f) o[(k++) * s2] = make_float2(a.f, b.f);
+  UAVB_VEHP_FIELDS(UAVB_ST)
+#undef UAVB_ST
+}
+__device__ __forceinline__ void vehp_cache_load(const float* cache, long long stride, long long i0, VehP<float>& a, VehP<float>& b) {
+  const float2* o = reinterpret_cast<const float2*>(cache + i0);
+  const long long s2 = stride >> 1;
+  int k = 0;
+#define UAVB_LD(f) { const float2 t = o[(k++) * s2]; a.f = t.x; b.f = t.y; }
+  UAVB_VEHP_FIELDS(UAVB_LD)
+#undef UAVB_LD
+}
+
 __device__ __forceinline__ void mission_view(MissionView& m, const RolloutDev<float>& p, long long i, int column, int columns) {
   const uavb_rollout_args& a = p.a;
   m.coeffs = a.seg_coeffs; m.rows = a.seg_rows; m.table = a.seg_table; m.yaw0 = a.seg_yaw0;
@@ -338,7 +369,7 @@ __device__ __forceinline__ void write_outputs(const uavb_rollout_args& a, long l
 // 3 = the gated position list of the viewer (PairTrajLog; its state rides in the carry block between slices).
 template <int LOG, bool MC, bool TABLE, bool LAG>
 __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long j, int n_ticks, bool from_carry, bool to_carry,
-                                           bool finish, int launch_tick0, const LogTma* maps = nullptr) {
+                                           bool finish, int launch_tick0, const LogTma* maps = nullptr, bool first_slice = true) {
   const uavb_rollout_args& a = p.a;
   const long long B = a.B;
   const long long i0 = 2 * j;
@@ -350,8 +381,14 @@ __device__ __forceinline__ void pair_slice(const RolloutDev<float>& p, long long
   VehP<float> vloc[2];
   VehP2 v2;
   if constexpr (MC) {
-    load_vehp<float>(vloc[0], a, i0);
-    load_vehp<float>(vloc[1], a, i1);
+    constexpr bool kCache = LOG != 3;                       // (the flown-path kernel has no register to spare for the two pointers)
+    if (kCache && p.vehp_cache != nullptr && !first_slice) {   // (uniform) a later slice of a sliced launch: the constants its first slice made
+      vehp_cache_load(p.vehp_cache, p.vehp_stride, i0, vloc[0], vloc[1]);
+    } else {
+      load_vehp<float>(vloc[0], a, i0);
+      load_vehp<float>(vloc[1], a, i1);
+      if (kCache && p.vehp_cache != nullptr) vehp_cache_store(p.vehp_cache, p.vehp_stride, i0, vloc[0], vloc[1]);
+    }
     zip_vehp(v2, vloc[0], vloc[1]);
   }
   const VehP<float>& va = MC ? vloc[0] : p.vp;
@@ -498,11 +535,15 @@ __global__ void __maxnreg__(kRolloutRegs) rollout_kernel(const __grid_constant__
 // (c, g) needs (c-1, g), which was handed out one full sweep of the groups earlier, so the wait on its completion flag
 // practically never spins -- and cannot deadlock, because whoever holds the earlier item is running.  The tail shrinks
 // from one mission to one slice.
+constexpr int kSliceTab = 64;
 struct SliceSched {
   int* counter;        // next item
   int* done;           // [n_groups] slices completed per group
   int n_groups, n_chunks, chunk_ticks;
   int final_carry;     // the caller asked for the carry block of the end state
+  int n_tab;           // > 0: slice c covers ticks [tab[c], tab[c + 1]) (n_chunks <= kSliceTab slices of unequal length); 0: c * chunk_ticks
+  int tab[kSliceTab + 1];
+  __device__ __forceinline__ int begin(int c) const { return n_tab ? tab[c] : c * chunk_ticks; }
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -534,8 +575,9 @@ __device__ __forceinline__ void sliced_body(const RolloutDev<float>& p, const Sl
     const long long j = (long long)g * blockDim.x + threadIdx.x;        // pair index: drones 2j, 2j+1
     if (2 * j < p.a.B) {
       const bool last = c == sch.n_chunks - 1;
-      const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
-      pair_slice<LOG, MC, TABLE, LAG>(p, j, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks, maps);
+      const int t0 = sch.begin(c);
+      const int ticks = last ? p.a.n_ticks - t0 : sch.begin(c + 1) - t0;
+      pair_slice<LOG, MC, TABLE, LAG>(p, j, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, t0, maps, c == 0);
     }
     __threadfence();
     __syncthreads();
@@ -575,7 +617,7 @@ __global__ void __maxnreg__(kRolloutRegs) rollout_sliced_scalar_kernel(const __g
     const int c = it / sch.n_groups, g = it - c * sch.n_groups;
     const long long i = (long long)g * blockDim.x + threadIdx.x;
     if (i < p.a.B) {
-      const bool last = c == sch.n_chunks - 1;
+      const bool last = c == sch.n_chunks - 1;                 // (always equal slices here: sch.n_tab == 0)
       const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
       drone_slice<float, false, MC, false>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
     }

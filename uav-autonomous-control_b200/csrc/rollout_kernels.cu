@@ -122,6 +122,8 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
   const int grid = div_up(a->B, per_cta);
   size_t smem = (a->n_obs > 0 && a->aabb_set == nullptr) ? sizeof(float) * 6 * a->n_obs : 0;
   p.coeff_cache_offset = -1;
+  p.vehp_cache = nullptr;
+  p.vehp_stride = 0;
   const bool from_table = a->shared_targets != nullptr && a->mission_seg_begin == nullptr;
   if (!from_table && sizeof(R) == 4) {                            // fp32 kernels stage the current spline in shared memory
     smem = (smem + 7) / 8 * 8;
@@ -156,7 +158,7 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     chunk = ((chunk + period - 1) / period) * period;
     if (chunk < kMinChunkTicks) chunk = ((kMinChunkTicks + period - 1) / period) * period;
     const int n_chunks = a->n_ticks > 0 ? (a->n_ticks + chunk - 1) / chunk : 1;
-    StreamScratch flags(st), carry(st);
+    StreamScratch flags(st), carry(st), consts(st);
     const size_t n_flags = (size_t)grid + 1;
     cudaError_t e = flags.alloc(n_flags * sizeof(int));
     if (e == cudaSuccess) e = cudaMemsetAsync(flags.p, 0, n_flags * sizeof(int), st);
@@ -166,6 +168,12 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
       e = carry.alloc(sizeof(float) * UAVB_CARRY_WORDS * (size_t)a->B);
       p.a.carry = static_cast<float*>(carry.p);
     }
+    if (e == cudaSuccess && mc_any && n_chunks > 1 && !scalar32) {      // the pairs' per-rollout constants, made by slice 0 (rollout_impl.cuh)
+      const long long padded = 2LL * div_up(a->B, 2);
+      e = consts.alloc(sizeof(float) * kVehpWords * (size_t)padded);
+      p.vehp_cache = static_cast<float*>(consts.p);
+      p.vehp_stride = padded;
+    }
     if (e != cudaSuccess) {
       cudaGetLastError();
       return set_error(UAVB_ENOMEM, "rollout: scratch allocation failed: %s", cudaGetErrorString(e));
@@ -173,6 +181,31 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     sch.counter = static_cast<int*>(flags.p);
     sch.done = sch.counter + 1;
     sch.n_groups = grid; sch.n_chunks = n_chunks; sch.chunk_ticks = chunk;
+    sch.n_tab = 0;
+    // Slices of DECREASING length for the pair kernels (unless the caller forces a slice count): every slice costs a carry round trip
+    // (~5 us per 1e5 rollouts), the tail of the launch is one slice of the last kind long -- so each slice takes a fifth of what is left
+    // (whole outer periods), down to a length that is <= 0.5 % of a resident CTA's share of the launch and >= 200 ticks.  Measured on the
+    // headline launch (1e5 x 10 760 ticks, 1 563 groups on 1 184 resident CTAs): 15 such slices 4.605 ms against 4.653 ms for the 25 equal
+    // slices of the rule above (tools/pipeline_probe.py).  Results do not depend on the slicing (tests/test_rollout_gpu.py).
+    if (!scalar32 && a->n_slices <= 0 && n_chunks > 1) {
+      const double share = (double)grid / (double)slots * (double)a->n_ticks;       // ticks a resident CTA flies in this launch
+      int min_len = (int)(share / 200.0);
+      if (min_len < 200) min_len = 200;
+      min_len = (min_len + period - 1) / period * period;
+      int t = 0, n = 0;
+      sch.tab[0] = 0;
+      while (t < a->n_ticks) {
+        const int left = a->n_ticks - t;
+        int len = left / 5;
+        if (len < min_len) len = min_len;
+        len = (len + period - 1) / period * period;
+        if (len > left || n == kSliceTab - 1) len = left;
+        if (left - len < min_len / 2) len = left;                                    // no sliver at the end
+        t += len;
+        sch.tab[++n] = t;
+      }
+      sch.n_tab = n; sch.n_chunks = n;
+    }
     const int pgrid = slots < grid ? slots : grid;
     // state log: through the TMA unit when the [samples x 13][B] log is a legal tensor (rows a multiple of 16 bytes, 16-byte aligned)
     LogTma maps;
