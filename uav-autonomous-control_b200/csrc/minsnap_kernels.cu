@@ -393,7 +393,7 @@ __device__ __forceinline__ void eval_table_row(const double* __restrict__ c, dou
   }
 }
 
-__global__ void __launch_bounds__(32 * kSampleWarps) sample_table_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
+__global__ void __launch_bounds__(32 * kSampleWarps, 8) sample_table_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
                                                                          const int* __restrict__ seg_rows, const int* __restrict__ row_offsets,
                                                                          int B, double dt, double* __restrict__ table) {
   __shared__ __align__(16) double s_tile[kSampleWarps][2][kTileDoubles];
