@@ -354,12 +354,10 @@ def run_b200(args):
         return kernels.plan_missions([(wp[None, :2].contiguous(), vel), (wp[None, 1:].contiguous(), vel)], FREQUENCY * veh.dt, shared=True,
                                      table_rows=None if n_ticks is None else n_ticks // FREQUENCY, obstacles=obs64)
 
-    def issue_plan(wp, vel):
-        """A speculative plan on the side stream, ordered behind everything the launching stream holds NOW (so it belongs to the
-        step that issues it), with the event K2 waits for."""
-        main = torch.cuda.current_stream(dev)
-        mark = torch.cuda.Event()
-        mark.record(main)
+    def issue_plan(wp, vel, mark):
+        """A speculative plan on the side stream, ordered behind `mark` -- the point of the launching stream at which the step that
+        issues it began, so the plan belongs to that step's timed bracket but does not wait for the step's K2 --, with the event the
+        K2 that flies it waits for."""
         side.wait_event(mark)
         with torch.cuda.stream(side):
             plan = make_plan(wp, vel, state["n"])
@@ -375,18 +373,21 @@ def run_b200(args):
         Steps are software-pipelined: the plan of step s + 1 is enqueued on a side stream behind the LAUNCH of K2(s) -- its few small
         kernels run in the SM slots K2(s) frees at its tail -- and K2(s + 1) waits for its event.  The first step of a timed
         region plans inside the region (drain() drops a plan made ahead), the last one plans nothing ahead: K plans per K steps."""
+        main = torch.cuda.current_stream(dev)
+        mark = torch.cuda.Event()
+        mark.record(main)                                    # this step begins here on the launching stream
         if state["n"] is None:                               # mission length is data dependent: read it once, outside the timed steps
             plan = make_plan(wp, vel, None)
             state["n"] = FREQUENCY * int(plan.total_rows.item())
         else:
-            plan, ready = state["pending"] if state["pending"] is not None else issue_plan(wp, vel)
+            plan, ready = state["pending"] if state["pending"] is not None else issue_plan(wp, vel, mark)
             state["pending"] = None
-            torch.cuda.current_stream(dev).wait_event(ready)
+            main.wait_event(ready)
         kernels.rollout(plan, B, state["n"], start=start, goal=goal, vehicle=veh, frequency=FREQUENCY, mc_gains=mc[:11], mc_mass=mc[11],
                         mc_inertia=mc[12:15], obstacles=obs, want_state=False, out=result, index_base=begin)
         state["remaining"] -= 1
         if state["remaining"] > 0:
-            state["pending"] = issue_plan(wp, vel)
+            state["pending"] = issue_plan(wp, vel, mark)
 
     def step_device():
         k = state["k"]
@@ -519,8 +520,9 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(metrics_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                     "call": "uavb_fly_mission_host (C ABI, pinned host buffers, synchronous); host wall-clock, max over ranks"},
             # own kernels per step (torch glue not counted): correct_classify, minsnap_solve_list x2 (take-off: <= 4 splines, course: <= 8),
-            # correct_sweep x2, minsnap_pack, table_meta, shared_seg_flags, target_rows, target_heading, rollout_sliced
-            "gpu_launches": 11 * args.steps,
+            # correct_sweep (one launch for every bucket), minsnap_pack, table_meta_warp, shared_seg_flags, target_rows, target_heading,
+            # rollout_sliced -- the ncu launch list of the same command counts the same ten (profiles/r02_launches_final2.md)
+            "gpu_launches": 10 * args.steps,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_rollout_final.md)",
                          "kernel": "rollout_sliced_kernel<MC,TABLE> (two drones per thread, packed fp32x2)", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,

@@ -240,9 +240,11 @@ typedef struct uavb_rollout_args {
                                      uavb_rollout_targets_f64 ([n_target_rows] records of 56 bytes); NULL = the kernel
                                      evaluates the polynomials itself.  Both forms give bit-identical rollouts.        */
   int           n_target_rows;
-  int           n_slices;     /* 0 = library policy.  > 0: cut the launch into this many time slices (fp32 only; clamped to whole
-                                 outer periods of >= 100 ticks).  Per-rollout results do not depend on it -- the tests fly the
-                                 same batch with several values to prove exactly that.                                  */
+  int           n_slices;     /* 0 = library policy (one slice when every work group has a resident CTA, otherwise slices of
+                                 decreasing length: each a fifth of the remaining ticks, at least 200).  > 0: cut the launch into
+                                 this many EQUAL time slices (fp32 only; clamped to whole outer periods of >= 100 ticks).
+                                 Per-rollout results do not depend on it -- the tests fly the same batch with several values to
+                                 prove exactly that.                                                                    */
 
   const double* start;        /* initial position, [3] (start_stride 0) or [B][3] (start_stride 3)    */
   int           start_stride;

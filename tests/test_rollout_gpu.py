@@ -348,6 +348,25 @@ def test_montecarlo_batch_matches_c_oracle_on_every_rollout(cuda, golden):
     assert (met[:, 7] == m_ref[:, 7]).all() and (met[:, 5] == 0).all()
 
 
+def test_default_slicing_of_a_large_batch_is_bit_identical_to_one_slice(cuda):
+    """A batch with more work groups than resident CTAs is cut into slices of DECREASING length by default, and a pair's later slices
+    load the per-rollout constants its first slice cached (rollout_kernels.cu, RolloutDev::vehp_cache): neither may change a bit
+    against the same batch flown as one slice or as equal slices -- with Monte-Carlo overrides, an odd batch size, boxes, and a
+    tick count that is not a multiple of the outer period."""
+    import torch
+    from uav_ac_b200.simulation.scene import LAB_COURSE_OBSTACLES
+    plan = lab_course_plan(cuda, 3.0)
+    B, n = 90_001, 2507                                              # 1 407 work groups of 64 drones > 148 x 8 resident CTAs
+    rng = np.random.default_rng(21)
+    mc = mc_arrays(cuda, B, rng.uniform(0.8, 1.2, (B, 11)), rng.uniform(0.9, 1.1, B), rng.uniform(0.9, 1.1, (B, 3)))
+    obs = torch.tensor(LAB_COURSE_OBSTACLES, dtype=torch.float32, device=cuda)
+    runs = [_fly(cuda, plan, B, n, n_slices=k, obstacles=obs, want_carry=True, **mc) for k in (0, 1, 6)]
+    for r in runs[1:]:
+        assert torch.equal(r.metrics, runs[0].metrics) and torch.equal(r.state, runs[0].state)
+        assert torch.equal(r.carry.view(torch.int32)[:50], runs[0].carry.view(torch.int32)[:50])
+    assert bool(torch.isfinite(runs[0].state).all())
+
+
 def test_time_sliced_schedule_is_bit_identical_to_a_single_slice(cuda, monkeypatch):
     """The persistent work queue ((slice, group) items, state parked in the carry block between slices) must not change
     a single bit: 5 000 per-rollout missions with wind and obstacle sets flown as one slice, as 7 slices and as 60 slices."""

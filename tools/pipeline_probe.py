@@ -1,6 +1,7 @@
 """Development probe: where the 0.2 ms between the K2 launch (4.77 ms) and the bench step (4.97 ms) goes, and what removes it.
 
-  A. K2 alone against the number of time slices (rollout(..., n_slices=n); results do not depend on it)
+  A. K2 alone against the number of EQUAL time slices (rollout(..., n_slices=n); n = 0 is the library's policy: slices of decreasing
+     length; results do not depend on the slicing)
   B. the speculative planner alone (device time of one plan_missions call with the queue primed)
   C. K steps of plan + K2: on one stream (bench.py of round 2 so far) / the NEXT step's plan on a side stream while K2 flies
 
@@ -51,16 +52,6 @@ for ns in [0] + [int(x) for x in os.environ.get("SLICES", "13,19,25,31,37,50,75,
         if i >= 2: ts.append(a.elapsed_time(b))
     print(f"A  n_slices={ns:4d}: K2 {statistics.mean(ts):.4f} ms (min {min(ts):.4f})", flush=True)
 
-for tab in [t for t in os.environ.get("TABS", "").split(";") if t]:
-    os.environ["UAVB_SLICE_TAB"] = tab
-    ts = []
-    for i in range(5):
-        space(i)
-        a, b = ev(), ev()
-        a.record(); kernels.rollout(plan0, B, n_ticks, out=out[1], **kw); b.record(); torch.cuda.synchronize()
-        if i >= 2: ts.append(a.elapsed_time(b))
-    print(f"A  tab={tab}: K2 {statistics.mean(ts):.4f} ms (min {min(ts):.4f}) same metrics {bool(torch.equal(out[0].metrics, out[1].metrics))}", flush=True)
-os.environ.pop("UAVB_SLICE_TAB", None)
 if os.environ.get("ONLY_A"): sys.exit(0)
 
 # ---- B
@@ -116,8 +107,7 @@ def run_piped(K):
         main.wait_event(ready[s])
         kernels.rollout(plans[s], B, n_ticks, out=out[s % 2], **kw)
         if s + 1 < K:
-            mark = torch.cuda.Event(); mark.record(main)      # behind this step's K2 launch in host order; the side stream does NOT wait for K2
-            issue(evs[s][0])
+            issue(evs[s][0])                                  # behind this step's K2 launch in host order; the side stream does NOT wait for K2
         evs[s][1].record()
     torch.cuda.synchronize()
     for p in plans: p.verify()
