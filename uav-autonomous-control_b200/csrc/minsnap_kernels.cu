@@ -5,6 +5,7 @@
 // (SURVEY 8(d)), i.e. HBM-bound.  The per-mission output (8 S x 3 doubles, contiguous) is staged in
 // shared memory and leaves the CTA as one contiguous tile so every 32-byte sector is written whole.
 #include <stdlib.h>
+#include <mutex>
 
 #include "minsnap_core.cuh"
 #include "rollout_core.cuh"
@@ -143,28 +144,37 @@ template <int MAXS, int MINB>
 __global__ void __launch_bounds__(kStreamThreads, MINB) minsnap_solve_stream_kernel(
     const double* __restrict__ waypoints, const double* __restrict__ velocity, int B, int S, double factor, double* __restrict__ times_out,
     int* __restrict__ status_out, const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ double s_out[];
-  __shared__ uint64_t s_bar;
-  char* tiles = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(s_out) + 1023) & ~(uintptr_t)1023);
-  double* s_wp = reinterpret_cast<double*>(tiles + 3 * kStreamSubTileBytes);       // [64][3 (S+1)]
+  // Dynamic shared memory only (so that it starts 1024-byte aligned, as the 128-byte swizzle of the tensor stores needs): TWO staging
+  // tiles of three 8 KB sub-tiles -- splines 0-1 and 2-3 of a tile leave from different ones, so nobody waits for the TMA unit to
+  // drain a tile before the next pair of splines is staged (the kernel is bound by HBM writes: that read-out waits for the write
+  // queue) --, then the waypoints of the next tile, then the mbarrier: 56 840 bytes at S = 4, four CTAs per SM.
+  extern __shared__ __align__(1024) double s_out[];
+  char* tiles = reinterpret_cast<char*>(s_out);
+  double* s_wp = reinterpret_cast<double*>(tiles + 6 * kStreamSubTileBytes);       // [64][3 (S+1)]
   const int wpd = 3 * (S + 1);
-  double* s_vel = s_wp + kStreamThreads * wpd;                                   // [64]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wp + kStreamThreads * wpd);
+  if ((smem_u32(tiles) & 1023u) != 0u) __trap();           // the staging tiles must sit on the swizzle period
   char* row = tiles + threadIdx.x * 128;
   const unsigned sw = (threadIdx.x & 7u) << 4;
   const int n_tiles = (B + kStreamThreads - 1) / kStreamThreads;
-  // the input of tile t: one bulk copy per array when the tile is whole, a cooperative copy for the ragged last tile (a bulk copy
-  // needs a multiple of 16 bytes, 64 missions always are)
+  // the waypoints of tile t: one bulk copy when the tile is whole, a cooperative copy for the ragged last tile (a bulk copy
+  // needs a multiple of 16 bytes, 64 missions always are); the velocity of a thread's next mission travels in a register
   auto prefetch = [&](int tile) {                         // thread 0
     if ((long long)(tile + 1) * kStreamThreads > B) return;
-    const uint32_t wp_bytes = (uint32_t)(kStreamThreads * wpd * 8), vel_bytes = kStreamThreads * 8;
-    mbar_expect_tx(&s_bar, wp_bytes + vel_bytes);
-    bulk_load_1d(s_wp, waypoints + (size_t)tile * kStreamThreads * wpd, wp_bytes, &s_bar);
-    bulk_load_1d(s_vel, velocity + (size_t)tile * kStreamThreads, vel_bytes, &s_bar);
+    const uint32_t wp_bytes = (uint32_t)(kStreamThreads * wpd * 8);
+    mbar_expect_tx(s_bar, wp_bytes);
+    bulk_load_1d(s_wp, waypoints + (size_t)tile * kStreamThreads * wpd, wp_bytes, s_bar);
+  };
+  auto velocity_of = [&](int tile) {                      // this thread's mission of `tile` (the tile's first one past the end of the batch)
+    if (tile >= n_tiles) return 0.0;
+    const long long m = (long long)tile * kStreamThreads + threadIdx.x;
+    return __ldg(velocity + (m < B ? m : (long long)tile * kStreamThreads));
   };
   if (threadIdx.x == 0) {
-    mbar_init(&s_bar, 1);
+    mbar_init(s_bar, 1);
     if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x);
   }
+  double vel_next = velocity_of(blockIdx.x);
   __syncthreads();
   unsigned phase = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -172,11 +182,10 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) minsnap_solve_stream_ker
     const int n_here = (int)((B - base) < kStreamThreads ? (B - base) : kStreamThreads);
     const bool live = (int)threadIdx.x < n_here;
     if (n_here == kStreamThreads) {
-      mbar_wait(&s_bar, phase);
+      mbar_wait(s_bar, phase);
       phase ^= 1u;
     } else {                                              // ragged last tile (the last iteration of one CTA)
       for (int e = threadIdx.x; e < n_here * wpd; e += kStreamThreads) s_wp[e] = __ldg(waypoints + (size_t)base * wpd + e);
-      if (live) s_vel[threadIdx.x] = __ldg(velocity + base + threadIdx.x);
       __syncthreads();
     }
     // this thread's mission into registers (threads past the end of the batch solve the tile's first mission and store nothing)
@@ -185,29 +194,30 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) minsnap_solve_stream_ker
 #pragma unroll
     for (int k = 0; k < 3 * (MAXS + 1); ++k)
       if (k < wpd) wreg[k] = s_wp[src * wpd + k];
-    const double vel = s_vel[src];
-    if (threadIdx.x == 0) bulk_wait_read<0>();            // ... and the previous tile's last tensor store has read the staging tile
+    const double vel = vel_next;
+    vel_next = velocity_of(tile + (int)gridDim.x);        // in flight during this tile's solve
+    if (threadIdx.x == 0) bulk_wait_read<1>();            // ... and the store that last read the FIRST staging tile (two stores ago) is done with it
     __syncthreads();                                      // the input buffer is free: fetch the tile this CTA solves next
     if (threadIdx.x == 0 && tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
     double* tout = times_out + (size_t)(base + src) * S;
     const int st = minsnap_solve_one<MAXS>(
         S, vel, factor, [&wreg](int i, int ax) { return wreg[3 * i + ax]; },
         [row, sw](int seg, int j, int ax, double val) {
-          const int off = (seg & 1) * 24 + j * 3 + ax, q = off >> 4, d = off & 15;
-          *reinterpret_cast<double*>(row + q * kStreamSubTileBytes + ((((unsigned)d >> 1) << 4) ^ sw) + (d & 1) * 8) = val;
+          const int off = (seg & 1) * 24 + j * 3 + ax, q = off >> 4, d = off & 15, half = (seg >> 1) & 1;
+          *reinterpret_cast<double*>(row + (half * 3 + q) * kStreamSubTileBytes + ((((unsigned)d >> 1) << 4) ^ sw) + (d & 1) * 8) = val;
         },
         [tout, live](int seg, double t) { if (live) tout[seg] = t; },
         [&](int seg) {
           const bool last = seg == S - 1;
           if (!(seg & 1) && !last) return;
-          const int first = (seg & 1) ? seg - 1 : seg, n_sub = (seg & 1) ? 3 : 2;
+          const int first = (seg & 1) ? seg - 1 : seg, n_sub = (seg & 1) ? 3 : 2, half = (seg >> 1) & 1;
           fence_proxy_async_smem();
           __syncthreads();
           if (threadIdx.x == 0) {
-            for (int q = 0; q < n_sub; ++q) tensor_store_2d(&tmap, first * 24 + q * 16, (int)base, tiles + q * kStreamSubTileBytes);
+            for (int q = 0; q < n_sub; ++q) tensor_store_2d(&tmap, first * 24 + q * 16, (int)base, tiles + (half * 3 + q) * kStreamSubTileBytes);
             bulk_commit();
-            if (!last) bulk_wait_read<0>();               // the next pair of splines overwrites the tile right away; after the last
-          }                                               // flush the wait moves to the next tile's barrier (a whole solve later)
+            if (!last) bulk_wait_read<1>();               // the OTHER staging tile's last store (a whole tile ago) has read it: it is staged next
+          }
           if (!last) __syncthreads();
         });
     if (live && status_out) status_out[base + threadIdx.x] = st;
@@ -717,7 +727,7 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
     int sms = 0;
     rc = sm_count_cached(&sms);
     if (rc) return rc;
-    const size_t smem = (size_t)3 * kStreamSubTileBytes + 1024 + sizeof(double) * kStreamThreads * (3 * (S + 1) + 1);
+    const size_t smem = (size_t)6 * kStreamSubTileBytes + sizeof(double) * kStreamThreads * 3 * (S + 1) + sizeof(uint64_t);
     const int n_tiles = div_up(B, kStreamThreads);
     CUtensorMap tms;
     if (kStreamThreads != kSolveThreads) {                 // the streaming kernel's tile has its own box height
@@ -727,6 +737,16 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
       tm = tms;
     }
     const int grid = n_tiles < kStreamCtasPerSm * sms ? n_tiles : kStreamCtasPerSm * sms;
+    static std::once_flag attr_once[kMaxDevices];          // > 48 KB of dynamic shared memory needs the opt-in, once per device
+    int dev = 0;
+    UAVB_CUDA_OK(cudaGetDevice(&dev));
+    cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once[dev < kMaxDevices ? dev : kMaxDevices - 1], [&] {
+      attr_err = cudaFuncSetAttribute(minsnap_solve_stream_kernel<4, kStreamCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(minsnap_solve_stream_kernel<4, kStreamCtasPerSm>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    });
+    UAVB_CUDA_OK(attr_err);
     minsnap_solve_stream_kernel<4, kStreamCtasPerSm><<<grid, kStreamThreads, smem, st>>>(waypoints, velocity, B, S, factor, times_out, status_out, tm);
     UAVB_CUDA_OK(cudaGetLastError());
     return UAVB_OK;
