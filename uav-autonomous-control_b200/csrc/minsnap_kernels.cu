@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) minsnap_solve_stream_ker
   char* tiles = reinterpret_cast<char*>(s_out);
   double* s_wp = reinterpret_cast<double*>(tiles + 6 * kStreamSubTileBytes);       // [64][3 (S+1)]
   const int wpd = 3 * (S + 1);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wp + kStreamThreads * wpd);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wp + kStreamThreads * 3 * (MAXS + 1));   // (a fixed place: behind the largest waypoint tile)
   if ((smem_u32(tiles) & 1023u) != 0u) __trap();           // the staging tiles must sit on the swizzle period
   char* row = tiles + threadIdx.x * 128;
   const unsigned sw = (threadIdx.x & 7u) << 4;
@@ -727,7 +727,7 @@ extern "C" int uavb_minsnap_solve_f64(const double* waypoints, const double* vel
     int sms = 0;
     rc = sm_count_cached(&sms);
     if (rc) return rc;
-    const size_t smem = (size_t)6 * kStreamSubTileBytes + sizeof(double) * kStreamThreads * 3 * (S + 1) + sizeof(uint64_t);
+    const size_t smem = (size_t)6 * kStreamSubTileBytes + sizeof(double) * kStreamThreads * 3 * (4 + 1) + sizeof(uint64_t);   // MAXS = 4
     const int n_tiles = div_up(B, kStreamThreads);
     CUtensorMap tms;
     if (kStreamThreads != kSolveThreads) {                 // the streaming kernel's tile has its own box height
