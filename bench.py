@@ -8,7 +8,9 @@
 Workload (config.workload): BASELINE.json configs[2] -- 10^5 lab_course rollouts per GPU with Monte-Carlo PID gains and
 mass/inertia perturbations, velocity 3.0 (config.ini) => 10 760 ticks each, 1.076e9 drone-sim-steps per GPU and step.  One "step" =
 one pass of the hot path over the batch: min-snap solve of the mission (K1, take-off + course tables), table geometry, persistent
-rollout (K2) of every drone over the whole mission, metrics written.  Weak scaling: every rank flies its own 10^5 rollouts
+rollout (K2) of every drone over the whole mission, metrics written.  Consecutive steps are software-pipelined: the planner of step
+s + 1 is enqueued on a side stream while K2 of step s flies (K plans per K timed steps, the first one exposed; see hot_path).
+Weak scaling: every rank flies its own 10^5 rollouts
 (Monte-Carlo inputs keyed by the global rollout index); the per-rollout metrics of a step are all-gathered over NCCL
 asynchronously (sharding.MetricGather), overlapping the next step's kernels, and the last gather is inside the timed region.
 
@@ -41,7 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_TICK = 269          # algorithmic flop per drone tick with 4 AABBs: 239 in the 1 kHz body + 298/10 from the 100 Hz loop (DESIGN.md "K2 work per tick")
-K2_DRAM_BYTES_PER_LAUNCH = 9.3e6    # ncu: 6.2 MB read + 3.0 MB written per launch of the bench workload (metrics-only: ~0 B per tick; profiles/r02_ncu_rollout_final.md)
+K2_DRAM_BYTES_PER_LAUNCH = 9.0e6    # ncu: 6.2 MB read + 2.9 MB written per launch of the bench workload (metrics-only: ~0 B per tick; profiles/r02_ncu_rollout_final2.md)
 LOG_BYTES_PER_TICK = 52      # 13 fp32 state words
 ROLLOUTS_PER_GPU = 100_000   # BASELINE configs[2]
 VELOCITY = 3.0               # config.ini:7
@@ -524,7 +526,7 @@ def run_b200(args):
             # rollout_sliced -- the ncu launch list of the same command counts the same ten (profiles/r02_launches_final2.md)
             "gpu_launches": 10 * args.steps,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                         "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_rollout_final.md)",
+                         "traffic": K2_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_rollout_final2.md)",
                          "kernel": "rollout_sliced_kernel<MC,TABLE> (two drones per thread, packed fp32x2)", "kernel_ms": k2_ms, "flop_per_tick": FLOP_PER_TICK,
                          "peak_source": "uavb_measure_fma_rates in this run (MEASURED_PEAKS.json carries no fp32 figure)",
                          "peak_three_operand": fp32_peak3, "frac_of_three_operand_peak": achieved / fp32_peak3 if fp32_peak3 else None,
@@ -622,7 +624,7 @@ def per_rollout_missions(wl, kernels, dev, fp32_peak, fp32_peak3):
             "value": float(B) * n_ticks / (ms * 1e-3), "unit": "steps/s", "rollouts": B, "ticks": n_ticks, "kernel_ms": ms,
             "collision_fraction": float((m[:, 1] > 0).float().mean()), "failed_fraction": float((m[:, 5] != 0).float().mean()),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                         "peak_three_operand": fp32_peak3, "flop_per_tick": FLOP_PER_TICK, "kernel": "rollout_sliced_kernel<MC,!TABLE>", "traffic": None}}
+                         "peak_three_operand": fp32_peak3, "flop_per_tick": FLOP_PER_TICK, "kernel": "rollout_sliced_scalar_kernel<MC> (one drone per thread, on-the-fly set-points)", "traffic": None}}
 
 
 def log_mode_roofline(kernels, plan, kw, dev, n_ticks, peaks, flush):
@@ -677,7 +679,9 @@ def solve_rate(kernels, host_api, dev, flush, peaks):
     peak = peaks.get("hbm_gbs", 6650.0)
     out = {"metric": "min-snap solves/s", "value": Bm / t, "unit": "solves/s", "missions": Bm, "splines": 4, "kernel_ms": t * 1e3,
            "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peak, "unit": "GB/s", "frac": byts / t / 1e9 / peak,
-                        "traffic": None, "kernel": "minsnap_solve_kernel<4,kStagePair,6>", "note": "includes output allocation by torch (cached allocator)"}}
+                        "traffic": 8.78e8 * Bm / 1e6, "traffic_unit": "bytes per launch, dram read+write (ncu --set full, profiles/r02_ncu_minsnap_final.md: 130 MB read + 748 MB written per 1e6 solves)",
+                        "kernel": "minsnap_solve_stream_kernel<4,4> (persistent, bulk-load prefetch, two staging tiles, tensor stores)",
+                        "note": "includes output allocation by torch (cached allocator)"}}
     if hasattr(host_api, "minsnap_solve_host"):
         wp_h, vel_h = wp.cpu().pin_memory(), vel.cpu().pin_memory()
         c_h = torch.empty((Bm, 32, 3), dtype=torch.float64).pin_memory()
