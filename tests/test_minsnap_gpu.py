@@ -131,6 +131,32 @@ def test_one_million_missions_satisfy_the_constraint_rows(cuda):
         assert normwise(cs[i], minsnap_np.solve_coeffs(wps[i], vs[i], "solve")[0]) < TOL
 
 
+def test_streaming_solver_is_position_independent_over_many_tiles_and_a_ragged_tail(cuda):
+    """The streaming K1 (S = 4: persistent CTAs walk 64-mission tiles, two staging tiles, bulk-load prefetch, a ragged last tile) must
+    give every mission the bits it gets when it is solved in a small batch of its own: 75 813 missions are more than two tiles per
+    resident CTA (148 x 4 CTAs) plus a last tile of 37, and the slices re-solved alone sit at other tile offsets, in other staging
+    halves and in other CTAs."""
+    import torch
+    from uav_ac_b200 import kernels
+    B = 2 * 64 * 148 * 4 + 37
+    wp, vel = kernels.mc_missions(11, B, 4)
+    c, t, st = kernels.minsnap_solve(wp, vel)
+    torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0
+    for lo, hi in ((0, 1000), (37_000, 38_111), (B - 101, B), (B - 37, B), (B - 1, B)):
+        c2, t2, st2 = kernels.minsnap_solve(wp[lo:hi].contiguous(), vel[lo:hi].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(c2, c[lo:hi]) and torch.equal(t2, t[lo:hi]) and torch.equal(st2, st[lo:hi]), (lo, hi)
+    # and against the NumPy oracle on a sample that includes the ragged tail
+    from oracle import minsnap_np
+    idx = list(range(0, B, 7919)) + list(range(B - 5, B))
+    wph, velh = wp.cpu().numpy(), vel.cpu().numpy()
+    ch = c.cpu().numpy()
+    for i in idx:
+        ref, _ = minsnap_np.solve_coeffs(wph[i], velh[i], "solve")
+        assert normwise(ch[i], ref) < TOL, i
+
+
 def test_degenerate_missions_are_flagged(cuda):
     w = np.array([[[0, 0, 0], [1, 0, 0], [1, 0, 0], [2, 1, 0.0]], [[0, 0, 0], [1, 0, 0], [1, 1, 0], [2, 1, 0.0]]])
     c, t, s = _solve(cuda, w, [1.0, 1.0])
