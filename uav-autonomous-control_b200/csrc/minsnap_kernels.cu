@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128) table_meta_warp_kernel(const double* __re
 // leaves as ONE bulk asynchronous copy (cp.async.bulk, 2 816 contiguous bytes) issued by lane 0 while the warp evaluates the next
 // 32 rows; a bulk copy needs 16-byte alignment at both ends and rows are 88 bytes, so a mission that starts on an odd table row
 // stages its tile 8 bytes up and writes its first row -- and a chunk with an odd row count its last row -- with plain stores.
-constexpr int kSampleWarps = 4;
+constexpr int kSampleWarps = 1;
 constexpr int kTileDoubles = 32 * 11 + 2;                  // + the 8-byte shift, rounded to 16 bytes
 
 struct RowEval {
@@ -403,7 +403,7 @@ __device__ __forceinline__ void eval_table_row(const double* __restrict__ c, dou
   }
 }
 
-__global__ void __launch_bounds__(32 * kSampleWarps, 8) sample_table_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
+__global__ void __launch_bounds__(32 * kSampleWarps, 32 / kSampleWarps) sample_table_kernel(const double* __restrict__ coeffs, const int* __restrict__ seg_offsets,
                                                                          const int* __restrict__ seg_rows, const int* __restrict__ row_offsets,
                                                                          int B, double dt, double* __restrict__ table) {
   __shared__ __align__(16) double s_tile[kSampleWarps][2][kTileDoubles];
