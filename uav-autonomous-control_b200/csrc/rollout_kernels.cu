@@ -189,22 +189,23 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     // slices of the rule above (tools/pipeline_probe.py).  Results do not depend on the slicing (tests/test_rollout_gpu.py).
     if (!scalar32 && a->n_slices <= 0 && n_chunks > 1) {
       const double share = (double)grid / (double)slots * (double)a->n_ticks;       // ticks a resident CTA flies in this launch
-      int min_len = (int)(share / 200.0);
+      int min_len = share / 200.0 < (double)a->n_ticks ? (int)(share / 200.0) : a->n_ticks;     // (never longer than the launch: no overflow below)
       int floor_len = 200, part = 5;
 #ifdef UAVB_DEV
       if (const char* e = getenv("UAVB_SLICE_MIN")) floor_len = atoi(e) > 0 ? atoi(e) : floor_len;      // development builds only
       if (const char* e = getenv("UAVB_SLICE_PART")) part = atoi(e) > 1 ? atoi(e) : part;
 #endif
       if (min_len < floor_len) min_len = floor_len;
-      min_len = (min_len + period - 1) / period * period;
+      min_len = (int)(((long long)min_len + period - 1) / period * period);
       int t = 0, n = 0;
       sch.tab[0] = 0;
       while (t < a->n_ticks) {
         const int left = a->n_ticks - t;
         int len = left / part;
         if (len < min_len) len = min_len;
-        len = (len + period - 1) / period * period;
-        if (len > left || n == kSliceTab - 1) len = left;
+        const long long whole = ((long long)len + period - 1) / period * period;      // whole outer periods
+        len = whole < left ? (int)whole : left;
+        if (n == kSliceTab - 1) len = left;
         if (left - len < min_len / 2) len = left;                                    // no sliver at the end
         t += len;
         sch.tab[++n] = t;
