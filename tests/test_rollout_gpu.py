@@ -367,6 +367,23 @@ def test_default_slicing_of_a_large_batch_is_bit_identical_to_one_slice(cuda):
     assert bool(torch.isfinite(runs[0].state).all())
 
 
+def test_default_slicing_of_per_rollout_missions_is_bit_identical_to_one_slice(cuda):
+    """The same for the one-drone-per-thread kernel that flies per-rollout missions: 80 001 rollouts are more work groups (of 32) than
+    the 148 x 16 resident CTAs, so the default launch cuts slices of decreasing length; one slice and four equal slices must give
+    the same bits."""
+    import torch
+    from uav_ac_b200 import kernels
+    B, n = 80_001, 1803
+    wp, vel = kernels.mc_missions(17, B, 4)
+    plan = kernels.plan_missions([(wp, vel)], 0.01)
+    wind = kernels.mc_uniform(5, B, [-0.08] * 3, [0.08] * 3)
+    runs = [kernels.rollout(plan, B, n, start=wp[:, 0].contiguous(), goal=wp[:, -1].contiguous(), mc_wind=wind, n_slices=k) for k in (0, 1, 4)]
+    torch.cuda.synchronize()
+    for r in runs[1:]:
+        assert torch.equal(r.metrics, runs[0].metrics) and torch.equal(r.state, runs[0].state)
+    assert bool(torch.isfinite(runs[0].state).all())
+
+
 def test_time_sliced_schedule_is_bit_identical_to_a_single_slice(cuda, monkeypatch):
     """The persistent work queue ((slice, group) items, state parked in the carry block between slices) must not change
     a single bit: 5 000 per-rollout missions with wind and obstacle sets flown as one slice, as 7 slices and as 60 slices."""

@@ -617,9 +617,10 @@ __global__ void __maxnreg__(kRolloutRegs) rollout_sliced_scalar_kernel(const __g
     const int c = it / sch.n_groups, g = it - c * sch.n_groups;
     const long long i = (long long)g * blockDim.x + threadIdx.x;
     if (i < p.a.B) {
-      const bool last = c == sch.n_chunks - 1;                 // (always equal slices here: sch.n_tab == 0)
-      const int ticks = last ? p.a.n_ticks - c * sch.chunk_ticks : sch.chunk_ticks;
-      drone_slice<float, false, MC, false>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, c * sch.chunk_ticks);
+      const bool last = c == sch.n_chunks - 1;
+      const int t0 = sch.begin(c);
+      const int ticks = last ? p.a.n_ticks - t0 : sch.begin(c + 1) - t0;
+      drone_slice<float, false, MC, false>(p, s_boxes, i, ticks, c > 0 || p.a.resume != 0, !last || sch.final_carry != 0, last, t0);
     }
     __threadfence();
     __syncthreads();

@@ -182,12 +182,12 @@ template <class R> static int launch_rollout(const uavb_rollout_args* a, void* s
     sch.done = sch.counter + 1;
     sch.n_groups = grid; sch.n_chunks = n_chunks; sch.chunk_ticks = chunk;
     sch.n_tab = 0;
-    // Slices of DECREASING length for the pair kernels (unless the caller forces a slice count): every slice costs a carry round trip
+    // Slices of DECREASING length (unless the caller forces a slice count): every slice costs a carry round trip
     // (~5 us per 1e5 rollouts), the tail of the launch is one slice of the last kind long -- so each slice takes a fifth of what is left
     // (whole outer periods), down to a length that is <= 0.5 % of a resident CTA's share of the launch and >= 200 ticks.  Measured on the
     // headline launch (1e5 x 10 760 ticks, 1 563 groups on 1 184 resident CTAs): 15 such slices 4.605 ms against 4.653 ms for the 25 equal
     // slices of the rule above (tools/pipeline_probe.py).  Results do not depend on the slicing (tests/test_rollout_gpu.py).
-    if (!scalar32 && a->n_slices <= 0 && n_chunks > 1) {
+    if (a->n_slices <= 0 && n_chunks > 1) {
       const double share = (double)grid / (double)slots * (double)a->n_ticks;       // ticks a resident CTA flies in this launch
       int min_len = share / 200.0 < (double)a->n_ticks ? (int)(share / 200.0) : a->n_ticks;     // (never longer than the launch: no overflow below)
       int floor_len = 200, part = 5;
