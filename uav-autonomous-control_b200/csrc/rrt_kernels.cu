@@ -15,7 +15,7 @@
 
 namespace uavb {
 
-constexpr int kRrtWarpsPerCta = 4;
+constexpr int kRrtWarpsPerCta = 1;      // one mission per CTA: a finished mission frees its slot at once (tree sizes vary by an order of magnitude)
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double round2(double x) { return __ddiv_rn(rint(__dmul_rn(x, 100.0)), 100.0); }   // np.round(x, 2)
